@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- learner transitions/sec (GAE + all PPO epochs) on synthetic stompy_pro-shaped
+trajectories (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is ONE learner update of the hot path (/root/reference/minppo/train.py:185-281): GAE
+over the [T x N] trajectory, E epochs x M minibatches of shuffle/gather + ActorCritic
+forward/backward + PPO loss + global-norm clip + Adam.
+
+  N == 1 : BASELINE.json configs[1]: 2048 envs x 128 steps, 256x256 MLPs, 4 epochs x 32 minibatches.
+  N  > 1 : configs[3]: 16384 envs x 64 steps (GLOBAL batch fixed), env-sharded over N GPUs with a
+           per-minibatch NCCL gradient all-reduce -> "scaling": "strong".
+
+`value`  = unique transitions per second = T*N / t_update, inputs resident in HBM, CUDA-graph replay.
+`e2e`    = same metric through Learner.update_host: pinned HOST buffers, H2D of the trajectory +
+           train state and D2H of the new train state + losses inside the timed region.
+D = 225 / A = 10 are a DECLARED STAND-IN for stompy_pro (its MJCF is fetched at run time by the
+reference).  `--impl reference`: JAX is not installable in this image, so the
+reference arm times the oracle's PyTorch-CPU restatement of the same update ("kind": "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+OBS_DIM, ACT_DIM = 225, 10          # declared stand-in
+METRIC = "learner transitions/sec (GAE+PPO epochs)"
+UNIT = "transitions/s"
+
+
+def workload(n_gpus: int):
+    if n_gpus == 1:
+        return dict(name="configs[1]: 2048 envs x 128 steps, 256x256 MLPs, 4 epochs x 32 minibatches",
+                    num_envs=2048, num_steps=128, num_minibatches=32, update_epochs=4)
+    return dict(name="configs[3]: 16384 envs x 64 steps env-sharded, 256x256 MLPs, 4 epochs x 32 minibatches",
+                num_envs=16384, num_steps=64, num_minibatches=32, update_epochs=4)
+
+
+def make_hyper(w):
+    from oracle import ppo_numpy as P
+
+    # anneal_lr=True with the default 1e9 total timesteps (config.py:79, 83) -- the reference's defaults
+    return P.Hyper(num_envs=w["num_envs"], num_steps=w["num_steps"], num_minibatches=w["num_minibatches"],
+                   update_epochs=w["update_epochs"], anneal_lr=True)
+
+
+def synth_shard(hp, rank: int, world: int, seed: int = 0):
+    """Synthetic shard [T, N/world, ...] in float32 NumPy.  Params from the init gains; value / log_prob
+    from a forward pass under those params (float32 torch CPU for speed); reward ~ N(0,1); done ~ B(0.01)."""
+    import torch
+
+    from oracle import ppo_numpy as P
+
+    T, Nl = hp.num_steps, hp.num_envs // world
+    params = P.init_params(OBS_DIM, ACT_DIM, hp.hidden_size, hp.num_layers, seed, np.float32)
+    g = torch.Generator().manual_seed(1234 + rank)
+    obs = torch.randn(T * Nl, OBS_DIM, generator=g)
+    pt = P.tree_like(params, lambda x: torch.from_numpy(x))["params"]
+
+    def mlp(m, x, tanh):
+        for i in range(hp.num_layers):
+            x = x @ m[f"Dense_{i}"]["kernel"] + m[f"Dense_{i}"]["bias"]
+            x = torch.tanh(x) if tanh else torch.relu(x)
+        return x @ m[f"Dense_{hp.num_layers}"]["kernel"] + m[f"Dense_{hp.num_layers}"]["bias"]
+
+    with torch.no_grad():
+        mean = mlp(pt["MLP_0"], obs, hp.use_tanh)
+        value = mlp(pt["MLP_1"], obs, False)[:, 0]
+        scale = torch.exp(pt["log_std"])
+        action = mean + scale * torch.randn(mean.shape, generator=g)
+        z = (action - mean) / scale
+        log_prob = (-0.5 * z * z - 0.5 * np.log(2 * np.pi)).sum(-1) - torch.log(scale).sum()
+        last_val = mlp(pt["MLP_1"], torch.randn(Nl, OBS_DIM, generator=g), False)[:, 0]
+    traj = {
+        "obs": obs.reshape(T, Nl, OBS_DIM).numpy(), "action": action.reshape(T, Nl, ACT_DIM).numpy(),
+        "value": value.reshape(T, Nl).numpy(), "log_prob": log_prob.reshape(T, Nl).numpy(),
+        "reward": torch.randn(T, Nl, generator=g).numpy(),
+        "done": (torch.rand(T, Nl, generator=g) < 0.01).numpy(),
+    }
+    return params, traj, last_val.numpy()
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = samples in the upper half of what was seen (the sampler also sees idle gaps)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle's PyTorch-CPU restatement on a bounded sample
+# ------------------------------------------------------------------------------------------
+def cpu_update_time(hp, sample_minibatches: int, repeats: int = 1):
+    """Seconds for one FULL update on the host cores, extrapolated from a bounded sample:
+    t = t(GAE + perms + shuffled copy of one epoch, measured) * E_scale + t(minibatch step) * E*M.
+    The sample runs the first `sample_minibatches` minibatches of epoch 0 (oracle/ppo_torch.py)."""
+    import torch
+
+    from oracle import ppo_numpy as P
+    from oracle import ppo_torch as PT
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params, traj, last_val = synth_shard(hp, 0, 1)
+    pt = PT.to_torch(params, torch.float32)
+    opt = {"count": 0, "mu": P.tree_like(pt, torch.zeros_like), "nu": P.tree_like(pt, torch.zeros_like)}
+    tr = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in traj.items()}
+    lv = torch.from_numpy(last_val)
+    rng = np.array([0, 1337], np.uint32)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        PT.update(pt, opt, tr, lv, rng, hp, epochs=1, minibatches=0)           # GAE + perm + shuffled copy
+        t_epoch_fixed = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        PT.update(pt, opt, tr, lv, rng, hp, epochs=1, minibatches=sample_minibatches)
+        t_sample = time.perf_counter() - t0
+        t_step = max(t_sample - t_epoch_fixed, 1e-9) / sample_minibatches
+        full = t_epoch_fixed * hp.update_epochs + t_step * hp.update_epochs * hp.num_minibatches
+        best = full if best is None else min(best, full)
+    return best, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(args.gpus)
+    hp = make_hyper(w)
+    B = hp.batch_size
+    sample = 4 if B >= (1 << 20) else 8
+    for _ in range(args.warmup):
+        cpu_update_time(hp, 1)
+    times = []
+    for _ in range(args.steps):
+        t, cores = cpu_update_time(hp, sample)
+        times.append(t)
+    t_upd = float(np.median(times))
+    val = B / t_upd
+    sample_desc = (f"per step: GAE + 1 permutation + 1 shuffled copy measured once, first {sample} of "
+                   f"{hp.update_epochs * hp.num_minibatches} minibatch steps measured, extrapolated to the full update")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_upd * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "obs_dim": OBS_DIM, "act_dim": ACT_DIM, "shape_note": "D/A are a declared stand-in"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample_desc + "; CPU restatement (PyTorch fp32), not JAX"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from minppo_b200 import _lib
+    from minppo_b200.learner import HostBatch, Learner, Memory, TrainState, calculate_gae, nccl_unique_id
+    from oracle import ppo_numpy as P
+    from tests.helpers import hyper_to_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ids = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+
+    w = workload(world)
+    hp = make_hyper(w)
+    B = hp.batch_size
+    cfg = hyper_to_config(hp, fast_tanh=bool(args.fast_tanh), use_graph=True)
+    learner = Learner(cfg, OBS_DIM, ACT_DIM, dev, world, rank, nccl_id)
+    params, traj, last_val = synth_shard(hp, rank, world)
+    flat = P.flatten_params(params, hp.num_layers)
+    t = lambda x: torch.as_tensor(np.ascontiguousarray(x)).to(dev)
+    mem = Memory(done=t(traj["done"]), action=t(traj["action"]), value=t(traj["value"]), reward=t(traj["reward"]),
+                 log_prob=t(traj["log_prob"]), obs=t(traj["obs"]))
+    lv = t(last_val)
+    ts = TrainState.create(flat, dev)
+    rng = torch.tensor([0, 1337], dtype=torch.int32, device=dev)
+    rng_out = torch.empty_like(rng)
+    losses = torch.empty((hp.update_epochs, hp.num_minibatches, 4), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_update():
+        learner.update(ts, mem, lv, rng, losses, rng_out)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # ---- device-resident number ---------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        one_update()
+    barrier()
+    learner.check()
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        one_update()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    learner.check()
+    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tt.item()) / args.steps
+    value = B / (ms_per_step * 1e-3)
+    final_losses = losses.cpu().numpy()
+
+    # ---- end-to-end through host buffers --------------------------------------------------------
+    hb = HostBatch(learner)
+    for k in ("obs", "action", "value", "reward", "log_prob", "last_val"):
+        hb.h[k].copy_(torch.from_numpy(np.ascontiguousarray(traj[k] if k != "last_val" else last_val)))
+    hb.h["done"].copy_(torch.from_numpy(traj["done"].view(np.uint8)))
+    hb.h["rng"].copy_(torch.tensor([0, 1337], dtype=torch.int32))
+    hb.h["params"].copy_(torch.from_numpy(flat))
+    for _ in range(2):
+        learner.update_host(hb)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        learner.update_host(hb)          # blocks until the results are on the host
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    et = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_val = B / float(et.item())
+
+    # ---- per-kernel-class timing (eager, CUDA events on the launching stream) ----------------------
+    prof = None
+    gae_roof = None
+    if rank == 0:
+        import ctypes as C
+
+        learner.use_graph = False
+        learner.lib.minppo_ctx_profile(learner._h, 1)
+        one_update()
+        n = len(_lib.PROFILE_CLASSES)
+        msv = (C.c_float * n)()
+        cnt = (C.c_int32 * n)()
+        _lib.check(learner.lib.minppo_ctx_profile_read(learner._h, msv, cnt, n))
+        learner.lib.minppo_ctx_profile(learner._h, 0)
+        learner.use_graph = True
+        prof = {name: {"ms_per_update": float(msv[i]), "scopes": int(cnt[i])} for i, name in enumerate(_lib.PROFILE_CLASSES)}
+    if world > 1:
+        # the other ranks must take part in the collectives of rank 0's profiled update
+        if rank != 0:
+            learner.use_graph = False
+            one_update()
+            learner.use_graph = True
+        barrier()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        # dominant kernel = the GEMM class with the most time; algorithmic FLOPs per launch
+        H, L, D, A = hp.hidden_size, hp.num_layers, OBS_DIM, ACT_DIM
+        rows = hp.minibatch_size / world
+        flops = {
+            "fwd_gemm": 2 * rows * 2 * (D * H + (L - 1) * H * H) / L,         # per launch (one layer, both nets), averaged
+            "bwd_gemm": 2 * rows * 2 * H * H,                                 # per launch (one layer, both nets)
+            "dw_gemm": 2 * rows * 2 * (D * H + (L - 1) * H * H),              # one launch covers all layers, both nets
+        }
+        dom = max(flops, key=lambda k: prof[k]["ms_per_update"])
+        launches = max(prof[dom]["scopes"], 1)
+        dur_s = prof[dom]["ms_per_update"] * 1e-3 / launches
+        achieved = flops[dom] / dur_s / 1e12 if dur_s > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": f"umma_gemm_kernel ({dom})", "achieved": achieved, "peak": tf_peak,
+                    "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                    "flops_per_launch": flops[dom], "avg_launch_us": dur_s * 1e6, "peak_source": peak_src + ", sustained bf16"}
+        # GAE against the HBM roofline at a bandwidth-relevant size (config 3 scale: 128 x 1M)
+        Tg, Ng = 128, 1 << 20
+        gg = torch.Generator(device=dev).manual_seed(0)
+        r_ = torch.randn(Tg, Ng, device=dev, generator=gg)
+        v_ = torch.randn(Tg, Ng, device=dev, generator=gg)
+        d_ = torch.rand(Tg, Ng, device=dev, generator=gg) < 0.01
+        lv_ = torch.randn(Ng, device=dev, generator=gg)
+        gm = Memory(d_, None, v_, r_, None, None)
+        for _ in range(3):
+            calculate_gae(gm, lv_, hp.gamma, hp.gae_lambda)
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        g0.record()
+        for _ in range(reps):
+            calculate_gae(gm, lv_, hp.gamma, hp.gae_lambda)       # 2.3 GB per call >> 126 MB L2
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gms = g0.elapsed_time(g1) / reps
+        gbytes = Tg * Ng * 17 + 4 * Ng
+        gae_roof = {"bound": "hbm", "kernel": "gae_single_kernel<4,4>", "shape": [Tg, Ng], "achieved": gbytes / (gms * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": gbytes / (gms * 1e-3) / 1e9 / hbm_peak,
+                    "frac_of_8TBs_spec": gbytes / (gms * 1e-3) / 1e9 / 8000.0, "bytes_per_transition": 17, "ms": gms,
+                    "peak_source": peak_src}
+        del r_, v_, d_, lv_, gm
+
+        # ---- CPU baseline beside it (N == 1 only) ---------------------------------------------------
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            t_cpu, cores = cpu_update_time(hp, 8)
+            cpu = {"value": B / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "GAE + 1 permutation + 1 shuffled epoch copy measured, first 8 of 128 minibatch steps measured, "
+                             "extrapolated to the full update; CPU restatement (PyTorch fp32), not JAX"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "bf16 tensor-core GEMMs (fp32 accumulate), fp32 elsewhere", "data": "synthetic",
+            "config": {"workload": w["name"], "obs_dim": OBS_DIM, "act_dim": ACT_DIM,
+                       "shape_note": "D=225/A=10 are a declared stand-in for stompy_pro (SURVEY.md F9)",
+                       "parallelism": f"env-sharded dp{world}" if world > 1 else "single GPU",
+                       "l2_policy": "inputs larger than L2 (obs 236 MB per update vs 126 MB L2)",
+                       "fast_tanh": bool(args.fast_tanh), "sample_passes_per_s": value * hp.update_epochs},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": hb.d2h_bytes(),
+                    "ms_per_step": float(et.item()) * 1e3},
+            "gpu_launches": learner.launches_per_update() * args.steps,
+            "launches_per_update": learner.launches_per_update(),
+            "roofline": roofline, "gae_roofline": gae_roof, "kernel_classes": prof,
+            "final_loss": [float(x) for x in final_losses[-1, -1]],
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    learner.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fast-tanh", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,208 @@
+// minppo_b200 -- gradient reduction + global-norm clip + Adam, one multi-tensor kernel
+// (replaces optax.chain(clip_by_global_norm, adam) and TrainState.apply_gradients,
+//  /root/reference/minppo/train.py:98-101, 114-124, 248).
+//
+// The whole parameter set lives in one contiguous fp32 arena (leaf order = JAX's sorted
+// flatten order of the pickle tree); mu / nu are arenas of the same shape.
+//
+// Phase R (reduce): every gradient element is the fixed-order sum of the per-tile / per-split
+//   partials the backward kernels wrote (no atomics -> bitwise reproducible), written to gflat;
+//   the minibatch loss sums ride along at gflat[P .. P+4).
+// Phase A (apply): sum of squares -> grid barrier -> clip scale -> Adam -> params, mu, nu and the
+//   bf16 weight images the tcgen05 GEMMs read (transposed [out][in] for forward, [in][out] for dX).
+// Single GPU runs R+A in one launch; with env-sharded ranks R, NCCL all-reduce(gflat), A.
+#include "common.cuh"
+#include "minppo_internal.h"
+
+namespace minppo {
+
+constexpr int OPT_THREADS = 256;
+
+MINPPO_DEVINL float block_sum(float v, float* scratch /*[OPT_THREADS/32]*/) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (OPT_THREADS / 32) ? scratch[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+  }
+  __syncthreads();
+  return s;                                   // valid in warp 0
+}
+
+// Sense-free grid barrier on a monotonically increasing 64-bit counter.  All blocks of the
+// grid are co-resident (grid <= #SMs, one block per SM).  A bounded spin turns a scheduling
+// surprise into an error flag instead of a hung GPU.
+MINPPO_DEVINL void grid_barrier(unsigned long long* counter, int* err_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long old = atomicAdd(counter, 1ULL);
+    const unsigned long long target = (old / gridDim.x + 1ULL) * gridDim.x;
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned long long*>(counter) < target) {
+      if (clock64() - t0 > 4000000000LL) { atomicExch(err_flag, MINPPO_ERR_BARRIER); break; }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(OPT_THREADS) opt_kernel(const OptArgs a) {
+  __shared__ float scratch[OPT_THREADS / 32];
+  __shared__ float s_bcast[2];
+  const int P = a.P;
+  const int gtid = blockIdx.x * OPT_THREADS + threadIdx.x;
+  const int gthreads = gridDim.x * OPT_THREADS;
+
+  if (a.do_reduce) {
+    for (int i = gtid; i < P + 2; i += gthreads) {
+      float g = 0.f;
+      if (i < P) {
+        // locate the leaf (<= MINPPO_MAX_LEAVES entries, ascending offsets)
+        int l = 0;
+        while (l + 1 < a.nleaves && i >= a.leaf[l + 1].offset) ++l;
+        const OptLeaf& L = a.leaf[l];
+        const int e = i - L.offset;
+        const float* src = L.grad_src + L.src_offset + e;
+        for (int p = 0; p < L.nparts; ++p) g += src[static_cast<size_t>(p) * L.part_stride];
+        g += L.grad_bias;                                  // -ent_coef on log_std (rank 0 only)
+      } else {
+        const float* src = a.loss_src + a.loss_src_offset + (i - P);
+        for (int p = 0; p < a.loss_nparts; ++p) g += src[static_cast<size_t>(p) * a.loss_part_stride];
+      }
+      a.gflat[i] = g;
+    }
+    if (!a.do_apply) return;
+    // phase A re-reads gflat written by other threads of the same launch only after the barrier below
+  }
+
+  if (a.do_apply) {
+    const int count = *a.count;                            // Adam step count BEFORE this step
+    float ent = a.entropy_const;                           // A * (0.5 + 0.5 log 2pi) + sum log|scale|
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.losses_out) {
+      // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the barrier)
+      for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(a.params[a.off_logstd + j])));
+    }
+    float ss = 0.f;
+    if (a.do_reduce) {
+      // own elements were just written by this very thread: same index mapping
+      for (int i = gtid; i < P; i += gthreads) { const float g = a.gflat[i]; ss = fmaf(g, g, ss); }
+    } else {
+      for (int i = gtid; i < P; i += gthreads) { const float g = a.gflat[i]; ss = fmaf(g, g, ss); }
+    }
+    const float bs = block_sum(ss, scratch);
+    if (threadIdx.x == 0) a.block_ss[blockIdx.x] = bs;
+    grid_barrier(a.barrier, a.err_flag);
+    if (threadIdx.x < 32) {
+      float s = 0.f;
+      for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += 32) s += a.block_ss[b];
+      s = warp_sum(s);
+      if (threadIdx.x == 0) s_bcast[0] = sqrtf(s);
+    }
+    __syncthreads();
+    const float gnorm = s_bcast[0];
+    const bool trigger = gnorm < a.max_norm;               // optax.clip_by_global_norm
+    // learning rate, train.py:98-101 (annealed) or opt.lr
+    float lr;
+    if (a.anneal) {
+      const float frac = 1.0f - static_cast<float>(count / a.anneal_div) / static_cast<float>(a.num_updates);
+      lr = a.lr * frac;
+    } else {
+      lr = a.lr;
+    }
+    const float cnt1 = static_cast<float>(count + 1);
+    const float c1 = 1.0f - powf(a.b1, cnt1);
+    const float c2 = 1.0f - powf(a.b2, cnt1);
+    for (int i = gtid; i < P; i += gthreads) {
+      float g = a.gflat[i];
+      if (!trigger) g = (g / gnorm) * a.max_norm;
+      const float mu = a.one_minus_b1 * g + a.b1 * a.mu[i];
+      const float nu = a.one_minus_b2 * (g * g) + a.b2 * a.nu[i];
+      const float u = (mu / c1) / (sqrtf(nu / c2 + a.eps_root) + a.eps);
+      const float p = a.params[i] + (-lr) * u;
+      a.params[i] = p;
+      a.mu[i] = mu;
+      a.nu[i] = nu;
+      int l = 0;
+      while (l + 1 < a.nleaves && i >= a.leaf[l + 1].offset) ++l;
+      const OptLeaf& L = a.leaf[l];
+      if (L.img_t || L.img_n) {
+        const int e = i - L.offset;
+        const int r = e / L.cols, c = e % L.cols;          // kernel [in=r][out=c]
+        const __nv_bfloat16 b = __float2bfloat16_rn(p);
+        if (L.img_t) L.img_t[static_cast<size_t>(c) * L.ld_t + r] = b;
+        if (L.img_n) L.img_n[static_cast<size_t>(r) * L.ld_n + c] = b;
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      *a.count = count + 1;
+      if (a.losses_out) {
+        // gflat[P] = sum max(vl, vlc), gflat[P+1] = sum min(l1, l2) over the global minibatch
+        const float value_loss = 0.5f * a.gflat[P] * a.inv_mb;
+        const float actor_loss = -a.gflat[P + 1] * a.inv_mb;
+        a.losses_out[0] = actor_loss + a.vf_coef * value_loss - a.ent_coef * ent;
+        a.losses_out[1] = value_loss;
+        a.losses_out[2] = actor_loss;
+        a.losses_out[3] = ent;
+        if (a.gnorm_out) *a.gnorm_out = gnorm;
+      }
+    }
+  }
+}
+
+// fp32 [rows][cols] -> bf16 [rows][ld] (zero padded); used for the observation image and
+// for the initial weight images.
+__global__ void f32_to_bf16_image_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                         long long rows, int cols, int ld) {
+  const long long pairs_per_row = ld / 2;
+  const long long total = rows * pairs_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / pairs_per_row;
+    const int c = static_cast<int>(i % pairs_per_row) * 2;
+    const float* s = src + r * cols;
+    const float x0 = c < cols ? s[c] : 0.f;
+    const float x1 = c + 1 < cols ? s[c + 1] : 0.f;
+    reinterpret_cast<uint32_t*>(dst)[i] = pack_bf16x2(x0, x1);
+  }
+}
+
+// weight images from the fp32 arena (ctx_create / set_params): same mapping as the apply phase
+__global__ void weight_images_kernel(const OptArgs a) {
+  const int gthreads = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.P; i += gthreads) {
+    int l = 0;
+    while (l + 1 < a.nleaves && i >= a.leaf[l + 1].offset) ++l;
+    const OptLeaf& L = a.leaf[l];
+    if (L.img_t || L.img_n) {
+      const int e = i - L.offset;
+      const int r = e / L.cols, c = e % L.cols;
+      const __nv_bfloat16 b = __float2bfloat16_rn(a.params[i]);
+      if (L.img_t) L.img_t[static_cast<size_t>(c) * L.ld_t + r] = b;
+      if (L.img_n) L.img_n[static_cast<size_t>(r) * L.ld_n + c] = b;
+    }
+  }
+}
+
+int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream) {
+  opt_kernel<<<blocks, OPT_THREADS, 0, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
+}
+
+int weight_images_launch(const OptArgs& a, cudaStream_t stream) {
+  weight_images_kernel<<<148, 256, 0, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
+}
+
+int obs_image_launch(const float* obs, __nv_bfloat16* img, long long rows, int cols, int ld, cudaStream_t stream) {
+  const long long total = rows * (ld / 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (blocks < 1) blocks = 1;
+  f32_to_bf16_image_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(obs, img, rows, cols, ld);
+  return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
+}
+
+}  // namespace minppo

@@ -1,0 +1,878 @@
+// minppo_b200 -- context, step orchestration and the C ABI (include/minppo_b200.h).
+//
+// One learner update (replaces /root/reference/minppo/train.py:185-281):
+//   per update : GAE -> all E permutations -> per-minibatch row lists -> advantage statistics
+//                -> bf16 observation image
+//   per (epoch, minibatch), strictly sequential (train.py:268, 274):
+//     fwd  layer 0      tcgen05 GEMM, A rows gathered by index, bias+activation epilogue
+//     fwd  layer 1..L-1 tcgen05 GEMM (TMA both operands)
+//     heads + PPO loss + dZ of the last hidden layer (SIMT fp32)
+//     bwd  layer L-1..1 tcgen05 GEMM dA = dZ W^T, f' epilogue, bias-grad column sums
+//     dW   all layers   tcgen05 split-K GEMM act^T dZ -> per-split partials
+//     optimizer         partial reduction [+ NCCL all-reduce] + global-norm clip + Adam + bf16 images
+// The whole sequence is captured into one CUDA graph per pointer set.
+#include <cuda.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "minppo_internal.h"
+#include "umma_gemm.cuh"
+
+namespace minppo {
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return MINPPO_ERR_CUDA;                                                             \
+    }                                                                                     \
+  } while (0)
+#define RET(call)            \
+  do {                       \
+    int r_ = (call);         \
+    if (r_ != 0) return r_;  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// bf16 2-D row-major tensor [outer][inner] with `ld` elements per row; box {box_inner, box_outer}; 128B swizzle
+static int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MINPPO_ERR_CUDA; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return MINPPO_ERR_CUDA; }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that single-GPU use never needs the library
+// ------------------------------------------------------------------------------------------
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api = {};
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+      api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+    }
+  }
+  return api.ok ? &api : nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// parameter layout
+// ------------------------------------------------------------------------------------------
+struct LeafInfo {
+  int net;       // 0 actor (MLP_0), 1 critic (MLP_1), 2 log_std
+  int layer;     // Dense_<layer>
+  int is_kernel;
+  long long offset, rows, cols;
+};
+static long long build_layout(const minppo_config& c, std::vector<LeafInfo>* out) {
+  long long off = 0;
+  const int L = c.num_layers;
+  for (int net = 0; net < 2; ++net) {
+    long long fan_in = c.obs_dim;
+    for (int l = 0; l <= L; ++l) {
+      const long long o = l < L ? c.hidden_size : (net == 0 ? c.act_dim : 1);
+      if (out) out->push_back({net, l, 0, off, 1, o});
+      off += o;
+      if (out) out->push_back({net, l, 1, off, fan_in, o});
+      off += fan_in * o;
+      fan_in = o;
+    }
+  }
+  if (out) out->push_back({2, 0, 0, off, 1, c.act_dim});
+  off += c.act_dim;
+  return off;
+}
+
+static int validate_config(const minppo_config& c) {
+  if (c.num_envs <= 0 || c.num_steps <= 0 || c.num_minibatches <= 0 || c.update_epochs <= 0 || c.obs_dim <= 0 ||
+      c.act_dim <= 0 || c.num_layers < 1) {
+    set_error("non-positive size in minppo_config");
+    return MINPPO_ERR_ARG;
+  }
+  if (c.hidden_size % 64 != 0 || c.hidden_size > 256 || c.hidden_size <= 0) {
+    set_error("model.hidden_size=%d unsupported: must be a multiple of 64 and <= 256", c.hidden_size);
+    return MINPPO_ERR_UNSUPPORTED;
+  }
+  if (c.act_dim > 32) { set_error("act_dim=%d unsupported (<= 32)", c.act_dim); return MINPPO_ERR_UNSUPPORTED; }
+  if (2 * (c.num_layers + 1) * 2 + 1 > MINPPO_MAX_LEAVES) { set_error("too many layers"); return MINPPO_ERR_UNSUPPORTED; }
+  if (2 * c.num_layers > GEMM_MAX_GROUPS) { set_error("num_layers=%d unsupported (<= %d)", c.num_layers, GEMM_MAX_GROUPS / 2); return MINPPO_ERR_UNSUPPORTED; }
+  const long long B = static_cast<long long>(c.num_envs) * c.num_steps;
+  const long long mb = B / c.num_minibatches;
+  if (mb * c.num_minibatches != B) {
+    // train.py:253-255
+    set_error("`batch_size` must be equal to `num_steps * num_envs`");
+    return MINPPO_ERR_ARG;
+  }
+  if (c.world_size < 1 || c.rank < 0 || c.rank >= c.world_size || c.num_envs % c.world_size != 0) {
+    set_error("bad sharding: world_size=%d rank=%d num_envs=%d", c.world_size, c.rank, c.num_envs);
+    return MINPPO_ERR_ARG;
+  }
+  if (c.prng_mode != MINPPO_PRNG_LEGACY && c.prng_mode != MINPPO_PRNG_PARTITIONABLE) {
+    set_error("bad prng_mode %d", c.prng_mode);
+    return MINPPO_ERR_ARG;
+  }
+  if (B > 0x7fffffffLL) { set_error("batch too large"); return MINPPO_ERR_UNSUPPORTED; }
+  return 0;
+}
+
+}  // namespace minppo
+
+using namespace minppo;
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct NetBufs {
+  std::vector<__nv_bfloat16*> act;     // act[l], l = 1..L   [M_pad][H]
+  std::vector<__nv_bfloat16*> dz;      // dz[l],  l = 1..L   [M_pad][H]
+  std::vector<__nv_bfloat16*> wt;      // wt[l],  l = 0..L-1 [H][Kp_l]   (kernel^T)
+  std::vector<__nv_bfloat16*> wn;      // wn[l],  l = 1..L-1 [H][H]      (kernel as stored)
+  std::vector<float*> dw_part;         // dw_part[l], l = 0..L-1 [S][in_l][H]
+  std::vector<float*> colsum;          // colsum[l],  l = 1..L-1 [m_tiles][H]  -> bias grad of layer l-1
+  std::vector<CUtensorMap> m_act_k, m_act_mn, m_dz_k, m_dz_mn, m_wt, m_wn;
+};
+
+struct UpdatePtrs {
+  float *params, *mu, *nu;
+  int32_t* count;
+  const float *obs, *action, *value, *reward, *log_prob;
+  const uint8_t* done;
+  const float* last_val;
+  const uint32_t* key_in;
+  uint32_t* key_out;
+  float* losses_out;
+  bool operator==(const UpdatePtrs& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
+};
+
+struct minppo_ctx {
+  minppo_config cfg;
+  int device, sm_count;
+  int T, N, Nl, n0, M, E, L, H, D, Dp, A;
+  long long B, Bl, P;
+  int mb, cap, M_pad, m_tiles, tiles64, S;
+  std::vector<LeafInfo> leaves;
+  // device buffers
+  std::vector<void*> allocs;
+  float *adv, *tgt, *stats, *gflat, *block_ss, *head_part, *gnorms, *losses_scratch;
+  int32_t *perms, *rowidx, *counts;
+  void* perm_ws;
+  size_t perm_ws_bytes;
+  __nv_bfloat16* obs_img;
+  unsigned long long* barrier;
+  int* err_flag;
+  NetBufs net[2];
+  int head_stride, po_w3a, po_b3a, po_w3c, po_b3c, po_logstd, po_bh_a, po_bh_c, po_loss;
+  int opt_blocks;
+  // graph cache
+  cudaStream_t cap_stream;
+  cudaGraph_t graph;
+  cudaGraphExec_t graph_exec;
+  UpdatePtrs graph_ptrs;
+  bool have_graph;
+  long long launches;
+  // nccl
+  ncclComm_t comm;
+  bool have_comm;
+  // per-kernel-class event profiling (eager mode only)
+  bool profiling;
+  std::vector<cudaEvent_t> prof_events;      // pairs (begin, end)
+  std::vector<int> prof_class;               // class of each pair
+  size_t prof_used;
+};
+
+enum : int { PC_GAE = 0, PC_PERM, PC_PREP, PC_OBS_IMAGE, PC_WEIGHT_IMAGES, PC_FWD_GEMM, PC_HEAD_LOSS, PC_BWD_GEMM,
+             PC_DW_GEMM, PC_OPT, PC_ALLREDUCE, PC_COUNT };
+
+// RAII: records an event pair around the launches issued in its scope when profiling is on.
+struct ProfScope {
+  minppo_ctx* c; cudaStream_t s; size_t idx; bool on;
+  ProfScope(minppo_ctx* ctx, int cls, cudaStream_t stream) : c(ctx), s(stream), idx(0), on(ctx->profiling) {
+    if (!on) return;
+    if (c->prof_used + 2 > c->prof_events.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      c->prof_events.push_back(a); c->prof_events.push_back(b);
+      c->prof_class.push_back(cls);
+    } else {
+      c->prof_class[c->prof_used / 2] = cls;
+    }
+    idx = c->prof_used;
+    c->prof_used += 2;
+    cudaEventRecord(c->prof_events[idx], s);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(c->prof_events[idx + 1], s); }
+};
+#define PROF(cls) ProfScope prof_scope_(c, cls, stream)
+
+namespace minppo {
+
+template <typename T>
+static int dev_alloc(minppo_ctx* c, T** p, size_t n, bool zero = true) {
+  void* q = nullptr;
+  const size_t bytes = (n * sizeof(T) + 255) & ~static_cast<size_t>(255);
+  CK(cudaMalloc(&q, bytes));
+  if (zero) CK(cudaMemset(q, 0, bytes));
+  c->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+static const LeafInfo& find_leaf(const minppo_ctx* c, int net, int layer, int is_kernel) {
+  for (const auto& l : c->leaves)
+    if (l.net == net && l.layer == layer && l.is_kernel == is_kernel) return l;
+  return c->leaves[0];
+}
+
+static int act_kind(const minppo_ctx* c, int net) {
+  if (net == 1 || !c->cfg.use_tanh) return ACT_RELU;        // critic is relu always (train.py:82)
+  return c->cfg.fast_tanh ? ACT_TANH_FAST : ACT_TANH;
+}
+
+static int init_kernel_attrs() {
+  static bool done = false;
+  if (done) return 0;
+  CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_DACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_PARTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  if (head_loss_init()) { set_error("head_loss_init failed"); return MINPPO_ERR_CUDA; }
+  done = true;
+  return 0;
+}
+
+template <int EPI>
+static int launch_gemm(const GemmParams& p, int ctas, cudaStream_t stream) {
+  umma_gemm_kernel<EPI><<<ctas, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+  if (cudaGetLastError() != cudaSuccess) { set_error("umma_gemm launch failed"); return MINPPO_ERR_CUDA; }
+  return 0;
+}
+
+// ---- optimizer argument block ---------------------------------------------------------------
+static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) {
+  memset(o, 0, sizeof(*o));
+  const minppo_config& cfg = c->cfg;
+  const int L = c->L, H = c->H;
+  int n = 0;
+  for (const auto& lf : c->leaves) {
+    OptLeaf& ol = o->leaf[n++];
+    ol.offset = static_cast<int>(lf.offset);
+    ol.cols = static_cast<int>(lf.cols);
+    ol.grad_bias = 0.f;
+    ol.img_t = nullptr; ol.img_n = nullptr; ol.ld_t = 0; ol.ld_n = 0;
+    if (lf.net == 2) {                         // log_std
+      ol.grad_src = c->head_part; ol.src_offset = c->po_logstd; ol.nparts = c->tiles64; ol.part_stride = c->head_stride;
+      ol.grad_bias = cfg.rank == 0 ? -static_cast<float>(cfg.ent_coef) : 0.f;
+    } else if (lf.layer == L) {                // output heads
+      ol.grad_src = c->head_part; ol.nparts = c->tiles64; ol.part_stride = c->head_stride;
+      if (lf.is_kernel) ol.src_offset = lf.net == 0 ? c->po_w3a : c->po_w3c;
+      else ol.src_offset = lf.net == 0 ? c->po_b3a : c->po_b3c;
+    } else if (lf.is_kernel) {                 // hidden kernels: split-K partials of the dW GEMM
+      const int in_l = lf.layer == 0 ? c->D : H;
+      ol.grad_src = c->net[lf.net].dw_part[lf.layer]; ol.src_offset = 0; ol.nparts = c->S; ol.part_stride = in_l * H;
+      ol.img_t = c->net[lf.net].wt[lf.layer]; ol.ld_t = lf.layer == 0 ? c->Dp : H;
+      if (lf.layer >= 1) { ol.img_n = c->net[lf.net].wn[lf.layer]; ol.ld_n = H; }
+    } else if (lf.layer == L - 1) {            // bias of the last hidden layer: head kernel column sums
+      ol.grad_src = c->head_part; ol.src_offset = lf.net == 0 ? c->po_bh_a : c->po_bh_c;
+      ol.nparts = c->tiles64; ol.part_stride = c->head_stride;
+    } else {                                   // bias of layer l < L-1: column sums of dz[l+1]
+      ol.grad_src = c->net[lf.net].colsum[lf.layer + 1]; ol.src_offset = 0; ol.nparts = c->m_tiles; ol.part_stride = H;
+    }
+  }
+  o->nleaves = n;
+  o->P = static_cast<int>(c->P);
+  o->A = c->A;
+  o->gflat = c->gflat;
+  o->loss_src = c->head_part; o->loss_src_offset = c->po_loss; o->loss_nparts = c->tiles64; o->loss_part_stride = c->head_stride;
+  o->params = u.params; o->mu = u.mu; o->nu = u.nu; o->count = u.count;
+  o->block_ss = c->block_ss; o->barrier = c->barrier; o->err_flag = c->err_flag;
+  o->off_logstd = static_cast<int>(c->leaves.back().offset);
+  o->anneal = cfg.anneal_lr ? 1 : 0;
+  o->anneal_div = c->mb * c->E;                                                     // train.py:100
+  const long long nu = cfg.total_timesteps / cfg.num_steps / cfg.num_envs;          // train.py:93
+  o->num_updates = static_cast<int>(nu > 0x7fffffffLL ? 0x7fffffffLL : nu);
+  o->lr = static_cast<float>(cfg.anneal_lr ? cfg.training_lr : cfg.opt_lr);
+  o->max_norm = static_cast<float>(cfg.max_grad_norm);
+  o->b1 = static_cast<float>(cfg.adam_b1); o->b2 = static_cast<float>(cfg.adam_b2);
+  o->one_minus_b1 = static_cast<float>(1.0 - cfg.adam_b1); o->one_minus_b2 = static_cast<float>(1.0 - cfg.adam_b2);
+  o->eps = static_cast<float>(cfg.adam_eps); o->eps_root = static_cast<float>(cfg.adam_eps_root);
+  o->inv_mb = static_cast<float>(1.0 / c->mb);
+  o->vf_coef = static_cast<float>(cfg.vf_coef); o->ent_coef = static_cast<float>(cfg.ent_coef);
+  o->entropy_const = static_cast<float>(c->A * (0.5 + 0.5 * log(2.0 * M_PI)));
+}
+
+static int nccl_allreduce(minppo_ctx* c, float* buf, size_t n, cudaStream_t stream) {
+  NcclApi* api = nccl_api();
+  ncclResult_t r = api->AllReduce(buf, buf, n, ncclFloat, ncclSum, c->comm, stream);
+  if (r != ncclSuccess) { set_error("ncclAllReduce failed: %s", api->GetErrorString(r)); return MINPPO_ERR_NCCL; }
+  return 0;
+}
+
+// ---- one minibatch step --------------------------------------------------------------------
+static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t stream) {
+  const int L = c->L, H = c->H;
+  const int32_t* ridx = c->rowidx + static_cast<size_t>(s) * c->cap;
+  // forward
+  for (int l = 0; l < L; ++l) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.ngroups = 2;
+    for (int net = 0; net < 2; ++net) {
+      GemmGroup& g = p.g[net];
+      NetBufs& nb = c->net[net];
+      g.cta_begin = net * c->m_tiles;
+      g.bmode = B_TMA_K;
+      g.tmB = nb.m_wt[l];
+      if (l == 0) {
+        g.amode = A_GATHER_K; g.rowidx = ridx; g.gimage = c->obs_img; g.ldg = c->Dp; g.kb_total = c->Dp / 64;
+      } else {
+        g.amode = A_TMA_K; g.tmA = nb.m_act_k[l]; g.kb_total = H / 64;
+      }
+      g.out = nb.act[l + 1]; g.ldo = H;
+      g.bias = u.params + find_leaf(c, net, l, 0).offset;
+      g.act = act_kind(c, net);
+      g.N = H; g.m_tiles = c->m_tiles; g.splits = 1; g.m_store = c->M_pad;
+    }
+    PROF(PC_FWD_GEMM);
+    RET(launch_gemm<EPI_ACT>(p, 2 * c->m_tiles, stream));
+    c->launches++;
+  }
+  // heads + loss + dz[L]
+  {
+    HeadLossArgs a;
+    memset(&a, 0, sizeof(a));
+    a.h_a = c->net[0].act[L]; a.h_c = c->net[1].act[L];
+    a.dz_a = c->net[0].dz[L]; a.dz_c = c->net[1].dz[L];
+    a.params = u.params; a.rowidx = ridx; a.count = c->counts + s;
+    a.adv_sum = c->stats + s; a.adv_sq = c->stats + c->E * c->M + s;
+    a.action = u.action; a.v_old = u.value; a.logp_old = u.log_prob; a.adv = c->adv; a.tgt = c->tgt;
+    a.partials = c->head_part; a.partial_stride = c->head_stride;
+    a.po_w3a = c->po_w3a; a.po_b3a = c->po_b3a; a.po_w3c = c->po_w3c; a.po_b3c = c->po_b3c;
+    a.po_logstd = c->po_logstd; a.po_bh_a = c->po_bh_a; a.po_bh_c = c->po_bh_c; a.po_loss = c->po_loss;
+    a.off_w3a = static_cast<int>(find_leaf(c, 0, L, 1).offset); a.off_b3a = static_cast<int>(find_leaf(c, 0, L, 0).offset);
+    a.off_w3c = static_cast<int>(find_leaf(c, 1, L, 1).offset); a.off_b3c = static_cast<int>(find_leaf(c, 1, L, 0).offset);
+    a.off_logstd = static_cast<int>(c->leaves.back().offset);
+    a.H = H; a.A = c->A; a.ldh = H; a.cap = c->cap;
+    a.act_a = act_kind(c, 0) == ACT_RELU ? ACTK_RELU : ACTK_TANH; a.act_c = ACTK_RELU;
+    a.inv_mb = static_cast<float>(1.0 / c->mb);
+    a.clip_eps = static_cast<float>(c->cfg.clip_eps); a.vf_coef = static_cast<float>(c->cfg.vf_coef);
+    PROF(PC_HEAD_LOSS);
+    RET(head_loss_launch(a, c->tiles64, stream));
+    c->launches++;
+  }
+  // backward through hidden layers: dz[l] = (dz[l+1] W_l^T) * f'(act[l])
+  for (int l = L - 1; l >= 1; --l) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.ngroups = 2;
+    for (int net = 0; net < 2; ++net) {
+      GemmGroup& g = p.g[net];
+      NetBufs& nb = c->net[net];
+      g.cta_begin = net * c->m_tiles;
+      g.amode = A_TMA_K; g.tmA = nb.m_dz_k[l + 1];
+      g.bmode = B_TMA_K; g.tmB = nb.m_wn[l];
+      g.kb_total = H / 64;
+      g.out = nb.dz[l]; g.ldo = H;
+      g.hprev = nb.act[l]; g.ldh = H;
+      g.colsum = nb.colsum[l];
+      g.act = act_kind(c, net);
+      g.N = H; g.m_tiles = c->m_tiles; g.splits = 1; g.m_store = c->M_pad;
+    }
+    PROF(PC_BWD_GEMM);
+    RET(launch_gemm<EPI_DACT>(p, 2 * c->m_tiles, stream));
+    c->launches++;
+  }
+  // weight gradients: dW_l = act[l]^T dz[l+1], split-K over minibatch rows
+  {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    int ng = 0, cta = 0;
+    for (int net = 0; net < 2; ++net) {
+      NetBufs& nb = c->net[net];
+      for (int l = 0; l < L; ++l) {
+        GemmGroup& g = p.g[ng++];
+        g.cta_begin = cta;
+        const int in_l = l == 0 ? c->D : H;
+        const int in_pad = l == 0 ? c->Dp : H;
+        if (l == 0) { g.amode = A_GATHER_MN; g.rowidx = ridx; g.gimage = c->obs_img; g.ldg = c->Dp; }
+        else { g.amode = A_TMA_MN; g.tmA = nb.m_act_mn[l]; }
+        g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
+        g.kb_total = c->M_pad / 64;
+        g.out = nb.dw_part[l];
+        g.N = H; g.m_tiles = (in_pad + 127) / 128; g.splits = c->S; g.m_store = in_l;
+        cta += g.m_tiles * g.splits;
+      }
+    }
+    p.ngroups = ng;
+    PROF(PC_DW_GEMM);
+    RET(launch_gemm<EPI_PARTIAL>(p, cta, stream));
+    c->launches++;
+  }
+  // optimizer
+  {
+    OptArgs o;
+    fill_opt_args(c, u, &o);
+    o.losses_out = u.losses_out ? u.losses_out + static_cast<size_t>(s) * 4 : c->losses_scratch;
+    o.gnorm_out = c->gnorms + s;
+    if (c->cfg.world_size == 1) {
+      o.do_reduce = 1; o.do_apply = 1;
+      PROF(PC_OPT);
+      RET(opt_launch(o, c->opt_blocks, stream));
+      c->launches++;
+    } else {
+      o.do_reduce = 1; o.do_apply = 0;
+      { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream)); }
+      { PROF(PC_ALLREDUCE); RET(nccl_allreduce(c, c->gflat, static_cast<size_t>(c->P) + 2, stream)); }
+      o.do_reduce = 0; o.do_apply = 1;
+      { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream)); }
+      c->launches += 3;
+    }
+  }
+  return 0;
+}
+
+static int enqueue_update(minppo_ctx* c, const UpdatePtrs& u, cudaStream_t stream) {
+  const minppo_config& cfg = c->cfg;
+  c->launches = 0;
+  const float gamma = static_cast<float>(cfg.gamma);
+  const float gl = static_cast<float>(cfg.gamma * cfg.gae_lambda);      // python-float product, then f32 (train.py:194)
+  c->prof_used = 0;
+  {
+    PROF(PC_GAE);
+    RET(gae_launch(u.reward, u.value, u.done, u.last_val, c->adv, c->tgt, c->T, c->Nl, gamma, gl, c->sm_count, 0, stream));
+    c->launches++;
+  }
+  {
+    PROF(PC_PERM);
+    RET(perm_launch(u.key_in, u.key_out, cfg.prng_mode, c->E, c->B, c->perms, c->perm_ws, c->perm_ws_bytes, stream));
+    c->launches += perm_launch_count(c->B) + (u.key_out ? 1 : 0);
+  }
+  const int EM = c->E * c->M;
+  {
+    PROF(PC_PREP);
+    RET(compact_rows_launch(c->perms, c->rowidx, c->counts, c->E, c->M, c->B, c->mb, c->cap, c->N, c->n0, c->Nl, stream));
+    RET(adv_stats_launch(c->adv, c->rowidx, c->counts, c->stats, EM, c->cap, c->mb, 0, stream));
+    if (cfg.world_size > 1) RET(nccl_allreduce(c, c->stats, EM, stream));
+    RET(adv_stats_launch(c->adv, c->rowidx, c->counts, c->stats, EM, c->cap, c->mb, 1, stream));
+    if (cfg.world_size > 1) RET(nccl_allreduce(c, c->stats + EM, EM, stream));
+    c->launches += 3 + (cfg.world_size > 1 ? 2 : 0);
+  }
+  {
+    PROF(PC_OBS_IMAGE);
+    RET(obs_image_launch(u.obs, c->obs_img, c->Bl, c->D, c->Dp, stream));
+    c->launches++;
+  }
+  // the weight images must match the caller's params at entry (they may have been replaced)
+  {
+    OptArgs o;
+    fill_opt_args(c, u, &o);
+    PROF(PC_WEIGHT_IMAGES);
+    RET(weight_images_launch(o, stream));
+    c->launches++;
+  }
+  for (int s = 0; s < EM; ++s) RET(enqueue_step(c, u, s, stream));
+  return 0;
+}
+
+}  // namespace minppo
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* minppo_last_error(void) { return g_err; }
+int minppo_version(void) { return 100; }
+
+int minppo_gae_chunked(const float* reward, const float* value, const uint8_t* done, const float* last_val,
+                       float* adv_out, float* tgt_out, int32_t T, int64_t N, double gamma, double gae_lambda,
+                       int32_t chunks, void* stream) {
+  if (!reward || !value || !done || !last_val || !adv_out || !tgt_out || T <= 0 || N <= 0) {
+    set_error("minppo_gae: null pointer or non-positive size");
+    return MINPPO_ERR_ARG;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int r = gae_launch(reward, value, done, last_val, adv_out, tgt_out, T, N, static_cast<float>(gamma),
+                     static_cast<float>(gamma * gae_lambda), sms, chunks, static_cast<cudaStream_t>(stream));
+  if (r) { set_error("gae launch failed: %s", cudaGetErrorString(cudaGetLastError())); return MINPPO_ERR_CUDA; }
+  return 0;
+}
+int minppo_gae(const float* reward, const float* value, const uint8_t* done, const float* last_val, float* adv_out,
+               float* tgt_out, int32_t T, int64_t N, double gamma, double gae_lambda, void* stream) {
+  return minppo_gae_chunked(reward, value, done, last_val, adv_out, tgt_out, T, N, gamma, gae_lambda, 0, stream);
+}
+
+size_t minppo_permutation_workspace_size(int32_t epochs, int64_t B) { return perm_workspace_bytes(epochs, B); }
+
+int minppo_permutation(const uint32_t* key_in, uint32_t* key_out, int32_t prng_mode, int32_t epochs, int64_t B,
+                       int32_t* perm_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!key_in || !perm_out || !workspace) { set_error("minppo_permutation: null pointer"); return MINPPO_ERR_ARG; }
+  if (prng_mode != MINPPO_PRNG_LEGACY && prng_mode != MINPPO_PRNG_PARTITIONABLE) { set_error("bad prng_mode"); return MINPPO_ERR_ARG; }
+  int r = perm_launch(key_in, key_out, prng_mode, epochs, B, perm_out, workspace, workspace_bytes,
+                      static_cast<cudaStream_t>(stream));
+  if (r == MINPPO_ERR_ARG) set_error("minppo_permutation: bad size");
+  else if (r == MINPPO_ERR_WORKSPACE) set_error("minppo_permutation: workspace too small");
+  else if (r) set_error("minppo_permutation: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return r;
+}
+
+int64_t minppo_param_layout(const minppo_config* cfg, int32_t* nleaves, int64_t* offsets, int64_t* rows,
+                            int64_t* cols) {
+  if (!cfg) { set_error("null config"); return MINPPO_ERR_ARG; }
+  std::vector<LeafInfo> lv;
+  const long long P = build_layout(*cfg, &lv);
+  if (nleaves) *nleaves = static_cast<int32_t>(lv.size());
+  for (size_t i = 0; i < lv.size(); ++i) {
+    if (offsets) offsets[i] = lv[i].offset;
+    if (rows) rows[i] = lv[i].rows;
+    if (cols) cols[i] = lv[i].cols;
+  }
+  return P;
+}
+
+int minppo_nccl_unique_id(void* id128_host) {
+  NcclApi* api = nccl_api();
+  if (!api) { set_error("libnccl.so.2 could not be loaded"); return MINPPO_ERR_NCCL; }
+  ncclUniqueId id;
+  ncclResult_t r = api->GetUniqueId(&id);
+  if (r != ncclSuccess) { set_error("ncclGetUniqueId: %s", api->GetErrorString(r)); return MINPPO_ERR_NCCL; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128_host, &id, 128);
+  return 0;
+}
+
+int minppo_ctx_destroy(minppo_ctx* c) {
+  if (!c) return 0;
+  if (c->have_graph) { cudaGraphExecDestroy(c->graph_exec); cudaGraphDestroy(c->graph); }
+  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  if (c->have_comm) nccl_api()->CommDestroy(c->comm);
+  for (void* p : c->allocs) cudaFree(p);
+  delete c;
+  return 0;
+}
+
+int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host, minppo_ctx** out) {
+  if (!cfg || !out) { set_error("null argument"); return MINPPO_ERR_ARG; }
+  RET(validate_config(*cfg));
+  minppo_ctx* c = new minppo_ctx();
+  c->cfg = *cfg;
+  c->have_graph = false; c->have_comm = false; c->cap_stream = nullptr; c->launches = 0;
+  c->profiling = false; c->prof_used = 0;
+  int rc = 0;
+  auto fail = [&](int code) { minppo_ctx_destroy(c); return code; };
+  if (cudaGetDevice(&c->device) != cudaSuccess) { set_error("no CUDA device"); return fail(MINPPO_ERR_CUDA); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return fail(MINPPO_ERR_CUDA); }
+  if (prop.major != 10) {
+    set_error("minppo_b200 requires an sm_100a (B200) device; found sm_%d%d", prop.major, prop.minor);
+    return fail(MINPPO_ERR_UNSUPPORTED);
+  }
+  c->sm_count = prop.multiProcessorCount;
+  if ((rc = init_kernel_attrs())) return fail(rc);
+
+  c->T = cfg->num_steps; c->N = cfg->num_envs; c->Nl = c->N / cfg->world_size; c->n0 = cfg->rank * c->Nl;
+  c->M = cfg->num_minibatches; c->E = cfg->update_epochs; c->L = cfg->num_layers; c->H = cfg->hidden_size;
+  c->D = cfg->obs_dim; c->Dp = (c->D + 63) / 64 * 64; c->A = cfg->act_dim;
+  c->B = static_cast<long long>(c->T) * c->N; c->Bl = static_cast<long long>(c->T) * c->Nl;
+  c->mb = static_cast<int>(c->B / c->M);
+  if (cfg->world_size == 1) c->cap = c->mb;
+  else {
+    long long cap = (3LL * c->mb / cfg->world_size + 1) / 2 + 256;    // 1.5 x mean + 256 rows
+    if (cap > c->mb) cap = c->mb;
+    if (cap > c->Bl) cap = c->Bl;
+    c->cap = static_cast<int>(cap);
+  }
+  c->M_pad = (c->cap + 127) / 128 * 128;
+  c->cap = c->M_pad;                                  // row lists are padded to whole GEMM tiles
+  c->m_tiles = c->M_pad / 128;
+  c->tiles64 = c->M_pad / 64;
+  c->P = build_layout(*cfg, &c->leaves);
+  // split-K of the dW GEMMs: fill the SMs once
+  {
+    int per_split = 0;
+    for (int l = 0; l < c->L; ++l) per_split += 2 * (((l == 0 ? c->Dp : c->H) + 127) / 128);
+    int S = cfg->dw_splits > 0 ? cfg->dw_splits : (c->sm_count / (per_split > 0 ? per_split : 1));
+    const int kb_total = c->M_pad / 64;
+    if (S > kb_total) S = kb_total;
+    if (S > 32) S = 32;
+    if (S < 1) S = 1;
+    // no empty splits: ceil(kb_total / S) * (S - 1) < kb_total
+    while (S > 1 && ((kb_total + S - 1) / S) * (S - 1) >= kb_total) --S;
+    c->S = S;
+  }
+  c->opt_blocks = c->sm_count;
+  const int H = c->H, L = c->L, A = c->A;
+  // head partial layout
+  {
+    int o = 0;
+    c->po_w3a = o; o += H * A;
+    c->po_b3a = o; o += A;
+    c->po_w3c = o; o += H;
+    c->po_b3c = o; o += 1;
+    c->po_logstd = o; o += A;
+    c->po_bh_a = o; o += H;
+    c->po_bh_c = o; o += H;
+    c->po_loss = o; o += 2;
+    c->head_stride = (o + 3) / 4 * 4;
+  }
+  const int EM = c->E * c->M;
+#define ALLOC(ptr, n) if ((rc = dev_alloc(c, &(ptr), (n)))) return fail(rc)
+  ALLOC(c->adv, static_cast<size_t>(c->Bl));
+  ALLOC(c->tgt, static_cast<size_t>(c->Bl));
+  ALLOC(c->stats, static_cast<size_t>(2 * EM));
+  ALLOC(c->gflat, static_cast<size_t>(c->P) + 4);
+  ALLOC(c->block_ss, static_cast<size_t>(c->opt_blocks));
+  ALLOC(c->head_part, static_cast<size_t>(c->tiles64) * c->head_stride);
+  ALLOC(c->gnorms, static_cast<size_t>(EM));
+  ALLOC(c->losses_scratch, 4);
+  ALLOC(c->perms, static_cast<size_t>(c->E) * c->B);
+  ALLOC(c->rowidx, static_cast<size_t>(EM) * c->cap);
+  ALLOC(c->counts, static_cast<size_t>(EM));
+  c->perm_ws_bytes = perm_workspace_bytes(c->E, c->B);
+  { uint8_t* p; ALLOC(p, c->perm_ws_bytes); c->perm_ws = p; }
+  ALLOC(c->obs_img, static_cast<size_t>(c->Bl) * c->Dp + 256);   // slack: MN gather may read one chunk past Dp
+  ALLOC(c->barrier, 1);
+  ALLOC(c->err_flag, 1);
+  for (int net = 0; net < 2; ++net) {
+    NetBufs& nb = c->net[net];
+    nb.act.assign(L + 1, nullptr); nb.dz.assign(L + 1, nullptr); nb.wt.assign(L, nullptr); nb.wn.assign(L, nullptr);
+    nb.dw_part.assign(L, nullptr); nb.colsum.assign(L, nullptr);
+    nb.m_act_k.resize(L + 1); nb.m_act_mn.resize(L + 1); nb.m_dz_k.resize(L + 1); nb.m_dz_mn.resize(L + 1);
+    nb.m_wt.resize(L); nb.m_wn.resize(L);
+    for (int l = 1; l <= L; ++l) {
+      ALLOC(nb.act[l], static_cast<size_t>(c->M_pad) * H);
+      ALLOC(nb.dz[l], static_cast<size_t>(c->M_pad) * H);
+      if ((rc = make_tmap(&nb.m_act_k[l], nb.act[l], H, c->M_pad, H, 64, 128))) return fail(rc);
+      if ((rc = make_tmap(&nb.m_act_mn[l], nb.act[l], H, c->M_pad, H, 64, 64))) return fail(rc);
+      if ((rc = make_tmap(&nb.m_dz_k[l], nb.dz[l], H, c->M_pad, H, 64, 128))) return fail(rc);
+      if ((rc = make_tmap(&nb.m_dz_mn[l], nb.dz[l], H, c->M_pad, H, 64, 64))) return fail(rc);
+    }
+    for (int l = 0; l < L; ++l) {
+      const int kp = l == 0 ? c->Dp : H;
+      const int in_l = l == 0 ? c->D : H;
+      ALLOC(nb.wt[l], static_cast<size_t>(H) * kp);
+      if ((rc = make_tmap(&nb.m_wt[l], nb.wt[l], kp, H, kp, 64, H))) return fail(rc);
+      if (l >= 1) {
+        ALLOC(nb.wn[l], static_cast<size_t>(H) * H);
+        if ((rc = make_tmap(&nb.m_wn[l], nb.wn[l], H, H, H, 64, H))) return fail(rc);
+        ALLOC(nb.colsum[l], static_cast<size_t>(c->m_tiles) * H);
+      }
+      ALLOC(nb.dw_part[l], static_cast<size_t>(c->S) * in_l * H);
+    }
+  }
+#undef ALLOC
+  if (cfg->world_size > 1) {
+    NcclApi* api = nccl_api();
+    if (!api) { set_error("libnccl.so.2 could not be loaded"); return fail(MINPPO_ERR_NCCL); }
+    if (!nccl_unique_id_host) { set_error("world_size > 1 requires a NCCL unique id"); return fail(MINPPO_ERR_ARG); }
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id_host, 128);
+    ncclResult_t r = api->CommInitRank(&c->comm, cfg->world_size, id, cfg->rank);
+    if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", api->GetErrorString(r)); return fail(MINPPO_ERR_NCCL); }
+    c->have_comm = true;
+  }
+  if (cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    return fail(MINPPO_ERR_CUDA);
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("context initialisation failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(MINPPO_ERR_CUDA); }
+  *out = c;
+  return 0;
+}
+
+int minppo_update(minppo_ctx* c, float* params, float* mu, float* nu, int32_t* count, const float* obs,
+                  const float* action, const float* value, const float* reward, const float* log_prob,
+                  const uint8_t* done, const float* last_val, const uint32_t* key_in, uint32_t* key_out,
+                  float* losses_out, int32_t use_graph, void* stream_v) {
+  if (!c || !params || !mu || !nu || !count || !obs || !action || !value || !reward || !log_prob || !done ||
+      !last_val || !key_in) {
+    set_error("minppo_update: null pointer");
+    return MINPPO_ERR_ARG;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  UpdatePtrs u;
+  memset(&u, 0, sizeof(u));
+  u.params = params; u.mu = mu; u.nu = nu; u.count = count; u.obs = obs; u.action = action; u.value = value;
+  u.reward = reward; u.log_prob = log_prob; u.done = done; u.last_val = last_val; u.key_in = key_in;
+  u.key_out = key_out; u.losses_out = losses_out;
+  if (!use_graph) return enqueue_update(c, u, stream);
+  const bool was_profiling = c->profiling;
+  c->profiling = false;                         // event records are not captured; profile in eager mode
+  struct Restore { minppo_ctx* c; bool v; ~Restore() { c->profiling = v; } } restore{c, was_profiling};
+  if (!(c->have_graph && c->graph_ptrs == u)) {
+    if (c->have_graph) { cudaGraphExecDestroy(c->graph_exec); cudaGraphDestroy(c->graph); c->have_graph = false; }
+    CK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int r = enqueue_update(c, u, c->cap_stream);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->cap_stream, &g);
+    if (r != 0) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
+    c->graph = g;
+    CK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+    c->graph_ptrs = u;
+    c->have_graph = true;
+  }
+  CK(cudaGraphLaunch(c->graph_exec, stream));
+  return 0;
+}
+
+int minppo_ctx_check(minppo_ctx* c, void* stream_v) {
+  if (!c) return MINPPO_ERR_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  CK(cudaStreamSynchronize(stream));
+  int flag = 0;
+  CK(cudaMemcpy(&flag, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) { set_error("device-side error flag %d", flag); return flag; }
+  const int EM = c->E * c->M;
+  std::vector<int32_t> counts(EM);
+  CK(cudaMemcpy(counts.data(), c->counts, EM * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int s = 0; s < EM; ++s)
+    if (counts[s] > c->cap) { set_error("minibatch %d: %d local rows exceed capacity %d", s, counts[s], c->cap); return MINPPO_ERR_WORKSPACE; }
+  std::vector<float> gn(EM);
+  CK(cudaMemcpy(gn.data(), c->gnorms, EM * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int s = 0; s < EM; ++s)
+    if (!isfinite(gn[s])) { set_error("non-finite gradient norm at minibatch step %d", s); return MINPPO_ERR_NONFINITE; }
+  return 0;
+}
+
+int64_t minppo_update_launch_count(const minppo_ctx* c) { return c ? c->launches : 0; }
+
+int minppo_ctx_profile(minppo_ctx* c, int32_t enable) {
+  if (!c) return MINPPO_ERR_ARG;
+  c->profiling = enable != 0;
+  c->prof_used = 0;
+  return 0;
+}
+
+int minppo_ctx_profile_read(minppo_ctx* c, float* ms_per_class_host, int32_t* launches_per_class_host, int32_t nclasses) {
+  if (!c || !ms_per_class_host || !launches_per_class_host) { set_error("null argument"); return MINPPO_ERR_ARG; }
+  CK(cudaDeviceSynchronize());
+  for (int i = 0; i < nclasses; ++i) { ms_per_class_host[i] = 0.f; launches_per_class_host[i] = 0; }
+  for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+    const int cls = c->prof_class[i / 2];
+    if (cls < nclasses) { ms_per_class_host[cls] += ms; launches_per_class_host[cls] += 1; }
+  }
+  return 0;
+}
+
+int minppo_ctx_read(minppo_ctx* c, int32_t what, void* dst, size_t bytes, void* stream_v) {
+  if (!c || !dst) { set_error("null argument"); return MINPPO_ERR_ARG; }
+  const void* src = nullptr;
+  size_t have = 0;
+  const size_t EM = static_cast<size_t>(c->E) * c->M;
+  switch (what) {
+    case 0: src = c->adv; have = c->Bl * 4; break;
+    case 1: src = c->tgt; have = c->Bl * 4; break;
+    case 2: src = c->perms; have = static_cast<size_t>(c->E) * c->B * 4; break;
+    case 3: src = c->gflat; have = (c->P + 4) * 4; break;
+    case 4: src = c->gnorms; have = EM * 4; break;
+    case 5: src = c->counts; have = EM * 4; break;
+    case 6: src = c->stats; have = 2 * EM * 4; break;
+    default: set_error("minppo_ctx_read: unknown buffer %d", what); return MINPPO_ERR_ARG;
+  }
+  if (bytes > have) { set_error("minppo_ctx_read: %zu bytes requested, buffer has %zu", bytes, have); return MINPPO_ERR_ARG; }
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream_v)));
+  return 0;
+}
+
+int minppo_debug_gemm(int32_t mode, const void* a_bf16, const void* b_bf16, const int32_t* rowidx, float* cmat,
+                      int32_t M, int32_t N, int32_t K, int32_t lda, int32_t splits, void* stream_v) {
+  if (!a_bf16 || !b_bf16 || !cmat || M % 128 || K % 64 || N % 64 || N > 256 || N <= 0 || splits < 1 || mode < 0 ||
+      mode > 3 || ((mode >= 2) && !rowidx)) {
+    set_error("minppo_debug_gemm: bad argument");
+    return MINPPO_ERR_ARG;
+  }
+  RET(init_kernel_attrs());
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.ngroups = 1;
+  GemmGroup& g = p.g[0];
+  g.cta_begin = 0; g.N = N; g.m_tiles = M / 128; g.splits = splits; g.kb_total = K / 64; g.m_store = M; g.out = cmat;
+  switch (mode) {
+    case 0:
+      g.amode = A_TMA_K; g.bmode = B_TMA_K;
+      RET(make_tmap(&g.tmA, a_bf16, K, M, lda ? lda : K, 64, 128));
+      RET(make_tmap(&g.tmB, b_bf16, K, N, K, 64, N));
+      break;
+    case 1:
+      g.amode = A_TMA_MN; g.bmode = B_TMA_MN;
+      RET(make_tmap(&g.tmA, a_bf16, M, K, lda ? lda : M, 64, 64));
+      RET(make_tmap(&g.tmB, b_bf16, N, K, N, 64, 64));
+      break;
+    case 2:
+      g.amode = A_GATHER_K; g.bmode = B_TMA_K; g.rowidx = rowidx;
+      g.gimage = reinterpret_cast<const __nv_bfloat16*>(a_bf16); g.ldg = lda;
+      RET(make_tmap(&g.tmB, b_bf16, K, N, K, 64, N));
+      break;
+    case 3:
+      g.amode = A_GATHER_MN; g.bmode = B_TMA_MN; g.rowidx = rowidx;
+      g.gimage = reinterpret_cast<const __nv_bfloat16*>(a_bf16); g.ldg = lda;
+      RET(make_tmap(&g.tmB, b_bf16, N, K, N, 64, 64));
+      break;
+  }
+  return launch_gemm<EPI_PARTIAL>(p, g.m_tiles * splits, static_cast<cudaStream_t>(stream_v));
+}
+
+}  // extern "C"

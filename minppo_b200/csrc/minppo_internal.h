@@ -1,0 +1,103 @@
+// minppo_b200 -- declarations shared between the .cu translation units (not part of the ABI).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/minppo_b200.h"
+
+namespace minppo {
+
+enum : int { ACTK_TANH = 0, ACTK_RELU = 1, ACTK_TANH_FAST = 2 };   // == ACT_* in umma_gemm.cuh
+
+// ---- gae.cu ------------------------------------------------------------------------------
+void gae_plan(int T, long long N, int sm_count, int* vec, int* chunks, int* seg_len);
+int gae_launch(const float* reward, const float* value, const uint8_t* done, const float* last_val, float* adv,
+               float* tgt, int T, long long N, float gamma, float gl, int sm_count, int force_chunks,
+               cudaStream_t stream);
+
+// ---- prng_sort.cu ------------------------------------------------------------------------
+size_t perm_workspace_bytes(int epochs, long long B);
+int perm_launch(const uint32_t* key_in_dev, uint32_t* key_out_dev, int mode, int epochs, long long B,
+                int32_t* perm_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+int perm_launch_count(long long B);
+
+// ---- minibatch.cu ------------------------------------------------------------------------
+// rowidx[(e*M+k)*cap + j] = local flat index of the j-th row of minibatch (e,k) that this rank
+// owns, in permutation order; entries j >= count are 0.  counts[e*M+k] = number owned.
+int compact_rows_launch(const int32_t* perms, int32_t* rowidx, int32_t* counts, int E, int M, long long B, int mb,
+                        int cap, int N, int n0, int Nl, cudaStream_t stream);
+// stats[s] = sum of adv over owned rows of minibatch s = e*M+k (pass 0); stats[EM+s] = sum (adv - mean)^2
+// with mean = stats[s] / mb (pass 1, after the sums have been all-reduced if sharded).
+int adv_stats_launch(const float* adv, const int32_t* rowidx, const int32_t* counts, float* stats, int EM, int cap,
+                     int mb, int pass, cudaStream_t stream);
+
+// ---- head_loss.cu ------------------------------------------------------------------------
+struct HeadLossArgs {
+  const __nv_bfloat16* h_a;      // last hidden activation, actor  [M_pad][ldh]
+  const __nv_bfloat16* h_c;      // last hidden activation, critic [M_pad][ldh]
+  __nv_bfloat16* dz_a;           // out: dL/dz of the last hidden layer (actor)
+  __nv_bfloat16* dz_c;
+  const float* params;           // fp32 arena
+  const int32_t* rowidx;         // [cap] local flat transition index per minibatch row
+  const int32_t* count;          // [1] rows owned by this rank in this minibatch
+  const float* adv_sum;          // [1] sum adv over the GLOBAL minibatch
+  const float* adv_sq;           // [1] sum (adv - mean)^2 over the GLOBAL minibatch
+  const float* action;           // [Bl][A]
+  const float* v_old;            // [Bl]   Memory.value
+  const float* logp_old;         // [Bl]   Memory.log_prob
+  const float* adv;              // [Bl]
+  const float* tgt;              // [Bl]
+  float* partials;               // [tiles][partial_stride]
+  int partial_stride;
+  int po_w3a, po_b3a, po_w3c, po_b3c, po_logstd, po_bh_a, po_bh_c, po_loss;   // offsets inside a partial
+  int off_w3a, off_b3a, off_w3c, off_b3c, off_logstd;                          // offsets inside the arena
+  int H, A, ldh, cap;
+  int act_a, act_c;              // ACTK_* of the hidden layers
+  float inv_mb, clip_eps, vf_coef;
+};
+int head_loss_init();
+int head_loss_launch(const HeadLossArgs& a, int tiles, cudaStream_t stream);
+
+// ---- adam.cu -----------------------------------------------------------------------------
+struct OptLeaf {
+  int offset;                    // first element in the arena
+  int cols;                      // kernel: out features; bias / log_std: length
+  const float* grad_src;         // partial buffer base
+  int src_offset;                // offset of this leaf inside one partial
+  int nparts;                    // partials to sum (fixed order)
+  int part_stride;               // floats between consecutive partials
+  float grad_bias;               // constant added to every element (-ent_coef for log_std)
+  __nv_bfloat16* img_t;          // bf16 image [out][ld_t] (transposed; forward GEMM B operand) or null
+  __nv_bfloat16* img_n;          // bf16 image [in][ld_n]  (dX GEMM B operand) or null
+  int ld_t, ld_n;
+};
+struct OptArgs {
+  OptLeaf leaf[MINPPO_MAX_LEAVES];
+  int nleaves, P, A;
+  int do_reduce, do_apply;
+  float* gflat;                  // [P + 4]
+  const float* loss_src;         // loss partial sums (2 per partial)
+  int loss_src_offset, loss_nparts, loss_part_stride;
+  float* params; float* mu; float* nu;
+  int32_t* count;
+  float* block_ss;               // [grid]
+  unsigned long long* barrier;
+  int* err_flag;
+  float* losses_out;             // [4] or null
+  float* gnorm_out;              // [1] or null
+  int off_logstd;
+  int anneal, anneal_div, num_updates;
+  float lr, max_norm, b1, b2, one_minus_b1, one_minus_b2, eps, eps_root;
+  float inv_mb, vf_coef, ent_coef, entropy_const;
+};
+int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream);
+int weight_images_launch(const OptArgs& a, cudaStream_t stream);
+int obs_image_launch(const float* obs, __nv_bfloat16* img, long long rows, int cols, int ld, cudaStream_t stream);
+
+// ---- error plumbing (learner.cu) -----------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+}  // namespace minppo

@@ -1,0 +1,310 @@
+// minppo_b200 -- PRNG-derived minibatch permutation on device
+// (replaces jax.random.split / jax.random.permutation at /root/reference/minppo/train.py:252,258).
+//
+//   permutation(key, B) = _shuffle: `rounds` x { key, sub = split(key); bits = random_bits(sub, 32, B);
+//                                                 stable sort_key_val(bits, x) }          (jax/_src/random.py)
+// Bit-exact with the oracle (oracle/threefry.py): Threefry-2x32/20 in both JAX bit-stream
+// modes, and a STABLE least-significant-digit radix sort (4 passes of 8 bits).  Duplicate
+// 32-bit sort keys do occur at B >= 2^18, so stability is observable and required.
+//
+// All `E` epochs of one update are generated in one batch (blockIdx.y = epoch): the key
+// chain depends only on the input key, never on data.
+#include "common.cuh"
+#include "minppo_internal.h"
+
+namespace minppo {
+
+// ---------------------------------------------------------------------------------------
+// Threefry-2x32, 20 rounds
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+__host__ __device__ inline void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t& o0,
+                                             uint32_t& o1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  x0 += ks[0];
+  x1 += ks[1];
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x0 += x1;
+      x1 = rotl32(x1, R[g & 1][i]);
+      x1 ^= x0;
+    }
+    x0 += ks[(g + 1) % 3];
+    x1 += ks[(g + 2) % 3] + static_cast<uint32_t>(g + 1);
+  }
+  o0 = x0;
+  o1 = x1;
+}
+
+// split(key) -> (first, second) child keys
+__host__ __device__ inline void key_split(const uint32_t key[2], int mode, uint32_t a[2], uint32_t b[2]) {
+  if (mode == MINPPO_PRNG_LEGACY) {
+    // threefry_2x32(key, iota(4)): pairs (0,2) and (1,3); output = concat(o0[0:2], o1[0:2]) -> [[o0_0,o0_1],[o1_0,o1_1]]
+    uint32_t p0, q0, p1, q1;
+    threefry2x32(key[0], key[1], 0u, 2u, p0, q0);
+    threefry2x32(key[0], key[1], 1u, 3u, p1, q1);
+    a[0] = p0; a[1] = p1; b[0] = q0; b[1] = q1;
+  } else {
+    threefry2x32(key[0], key[1], 0u, 0u, a[0], a[1]);
+    threefry2x32(key[0], key[1], 0u, 1u, b[0], b[1]);
+  }
+}
+
+// random_bits(key, 32, (n,))[i]
+__device__ __forceinline__ uint32_t random_bits_at(const uint32_t key[2], int mode, uint32_t i, uint32_t n) {
+  uint32_t o0, o1;
+  if (mode == MINPPO_PRNG_LEGACY) {
+    const uint32_t h = (n + 1u) >> 1;                 // padded half length
+    if (i < h) {
+      const uint32_t hi = i + h;
+      threefry2x32(key[0], key[1], i, hi < n ? hi : 0u, o0, o1);   // pad counter is 0
+      return o0;
+    }
+    threefry2x32(key[0], key[1], i - h, i, o0, o1);
+    return o1;
+  }
+  threefry2x32(key[0], key[1], 0u, i, o0, o1);
+  return o0 ^ o1;
+}
+
+// Derive, for epoch e and sort round r, the subkey used for random bits, from the update's
+// input key.  Chain: rng_{e+1}, k_e = split(rng_e);  inside permutation: k, s_r = split(k).
+__host__ __device__ inline void round_subkey(const uint32_t key_in[2], int mode, int epoch, int round,
+                                             uint32_t sub[2]) {
+  uint32_t rng[2] = {key_in[0], key_in[1]}, a[2], b[2];
+  for (int e = 0; e <= epoch; ++e) {
+    key_split(rng, mode, a, b);
+    rng[0] = a[0]; rng[1] = a[1];
+  }
+  uint32_t k[2] = {b[0], b[1]};                      // k_e
+  for (int r = 0; r <= round; ++r) {
+    key_split(k, mode, a, b);
+    k[0] = a[0]; k[1] = a[1];
+  }
+  sub[0] = b[0]; sub[1] = b[1];
+}
+
+__global__ void key_advance_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_out, int mode,
+                                   int epochs) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint32_t rng[2] = {key_in[0], key_in[1]}, a[2], b[2];
+    for (int e = 0; e < epochs; ++e) {
+      key_split(rng, mode, a, b);
+      rng[0] = a[0]; rng[1] = a[1];
+    }
+    key_out[0] = rng[0];
+    key_out[1] = rng[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// stable LSD radix sort, 8-bit digits; tile = 256 threads x ITEMS consecutive elements per warp
+// ---------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 8;                         // 32-element strips per warp
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 2048
+
+// bits for this round are produced on the fly in pass 0 (keys_in == nullptr)
+struct SortArgs {
+  const uint32_t* key_in_dev;   // update input key [2]
+  int mode, round;
+  uint32_t n;
+  const uint32_t* keys_in;      // [E][n] (pass > 0)
+  uint32_t* keys_out;           // [E][n]
+  const int32_t* vals_in;       // [E][n] or nullptr (round 0, pass 0: iota)
+  int32_t* vals_out;            // [E][n]
+  uint32_t* hist;               // [E][256][tiles]
+  int shift;
+  int tiles;
+};
+
+__device__ __forceinline__ uint32_t rs_load_key(const SortArgs& a, int epoch, uint32_t i, const uint32_t sub[2]) {
+  if (a.keys_in) return a.keys_in[static_cast<size_t>(epoch) * a.n + i];
+  return random_bits_at(sub, a.mode, i, a.n);
+}
+
+// Per-warp digit ranking of this warp's RS_ITEMS strips (in element order -> stable).
+// wcount[warp][digit] ends as the warp's digit histogram; rank[s] = # earlier elements of the
+// same digit within the warp.
+__device__ __forceinline__ void rs_rank(const uint32_t (&key)[RS_ITEMS], const bool (&valid)[RS_ITEMS], int shift,
+                                        uint32_t* wc /*[256] for this warp*/, uint32_t (&rank)[RS_ITEMS]) {
+  const uint32_t lane = lane_id();
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int s = 0; s < RS_ITEMS; ++s) {
+    const uint32_t d = (key[s] >> shift) & 0xFFu;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid[s]);
+    uint32_t peers = __match_any_sync(0xffffffffu, valid[s] ? d : 0x100u + lane) & vmask;
+    uint32_t before = 0;
+    if (valid[s]) {
+      before = wc[d];
+      rank[s] = before + __popc(peers & lt);
+    }
+    __syncwarp();
+    if (valid[s] && (peers & lt) == 0) wc[d] = before + __popc(peers);    // group leader
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(SortArgs a) {
+  __shared__ uint32_t wc[RS_WARPS][256];
+  const int epoch = blockIdx.y, tile = blockIdx.x, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wc[0][0])[i] = 0;
+  __syncthreads();
+  uint32_t sub[2] = {0, 0};
+  if (!a.keys_in) {
+    uint32_t kin[2] = {a.key_in_dev[0], a.key_in_dev[1]};
+    round_subkey(kin, a.mode, epoch, a.round, sub);
+  }
+  uint32_t key[RS_ITEMS], rank[RS_ITEMS];
+  bool valid[RS_ITEMS];
+  const uint32_t base = static_cast<uint32_t>(tile) * RS_TILE + warp * (32 * RS_ITEMS) + lane_id();
+#pragma unroll
+  for (int s = 0; s < RS_ITEMS; ++s) {
+    const uint32_t i = base + s * 32;
+    valid[s] = i < a.n;
+    key[s] = valid[s] ? rs_load_key(a, epoch, i, sub) : 0u;
+  }
+  rs_rank(key, valid, a.shift, wc[warp], rank);
+  __syncthreads();
+  for (int d = threadIdx.x; d < 256; d += RS_THREADS) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) c += wc[w][d];
+    a.hist[(static_cast<size_t>(epoch) * 256 + d) * a.tiles + tile] = c;
+  }
+}
+
+// exclusive scan over [256][tiles] (digit-major) per epoch; one block per epoch
+__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* hist, int tiles) {
+  __shared__ uint32_t part[1024];
+  uint32_t* h = hist + static_cast<size_t>(blockIdx.x) * 256 * tiles;
+  const int total = 256 * tiles;
+  const int per = (total + 1023) / 1024;
+  const int b = threadIdx.x * per, e = min(total, b + per);
+  uint32_t s = 0;
+  for (int i = b; i < e; ++i) s += h[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int o = 1; o < 1024; o <<= 1) {
+    uint32_t v = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+  for (int i = b; i < e; ++i) {
+    const uint32_t v = h[i];
+    h[i] = run;
+    run += v;
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(SortArgs a) {
+  __shared__ uint32_t wc[RS_WARPS][256];
+  const int epoch = blockIdx.y, tile = blockIdx.x, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wc[0][0])[i] = 0;
+  __syncthreads();
+  uint32_t sub[2] = {0, 0};
+  if (!a.keys_in) {
+    uint32_t kin[2] = {a.key_in_dev[0], a.key_in_dev[1]};
+    round_subkey(kin, a.mode, epoch, a.round, sub);
+  }
+  uint32_t key[RS_ITEMS], rank[RS_ITEMS];
+  int32_t val[RS_ITEMS];
+  bool valid[RS_ITEMS];
+  const uint32_t base = static_cast<uint32_t>(tile) * RS_TILE + warp * (32 * RS_ITEMS) + lane_id();
+#pragma unroll
+  for (int s = 0; s < RS_ITEMS; ++s) {
+    const uint32_t i = base + s * 32;
+    valid[s] = i < a.n;
+    key[s] = valid[s] ? rs_load_key(a, epoch, i, sub) : 0u;
+    val[s] = valid[s] ? (a.vals_in ? a.vals_in[static_cast<size_t>(epoch) * a.n + i] : static_cast<int32_t>(i)) : 0;
+    rank[s] = 0;
+  }
+  rs_rank(key, valid, a.shift, wc[warp], rank);
+  __syncthreads();
+  // per digit: exclusive prefix over warps, plus the tile's global base
+  for (int d = threadIdx.x; d < 256; d += RS_THREADS) {
+    uint32_t run = a.hist[(static_cast<size_t>(epoch) * 256 + d) * a.tiles + tile];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t c = wc[w][d];
+      wc[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < RS_ITEMS; ++s) {
+    if (valid[s]) {
+      const uint32_t d = (key[s] >> a.shift) & 0xFFu;
+      const size_t pos = static_cast<size_t>(epoch) * a.n + wc[warp][d] + rank[s];
+      a.keys_out[pos] = key[s];
+      a.vals_out[pos] = val[s];
+    }
+  }
+}
+
+size_t perm_workspace_bytes(int epochs, long long B) {
+  const size_t n = static_cast<size_t>(B), E = static_cast<size_t>(epochs);
+  const size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+  // keys ping/pong + vals pong (+ final values go to caller's perm) + histograms
+  return 2 * E * n * 4 + E * n * 4 + E * 256 * tiles * 4 + 1024;
+}
+
+// perm_out: int32 [E][B].  ws as sized above.  key_out (device, [2]) receives the key after E splits.
+int perm_launch(const uint32_t* key_in_dev, uint32_t* key_out_dev, int mode, int epochs, long long B,
+                int32_t* perm_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (B <= 0 || B > 0x7fffffffLL || epochs <= 0) return MINPPO_ERR_ARG;
+  if (ws_bytes < perm_workspace_bytes(epochs, B)) return MINPPO_ERR_WORKSPACE;
+  const size_t n = static_cast<size_t>(B), E = static_cast<size_t>(epochs);
+  const int tiles = static_cast<int>((n + RS_TILE - 1) / RS_TILE);
+  uint32_t* k0 = reinterpret_cast<uint32_t*>(ws);
+  uint32_t* k1 = k0 + E * n;
+  int32_t* v1 = reinterpret_cast<int32_t*>(k1 + E * n);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(v1 + E * n);
+  // rounds = ceil(3 ln B / ln(2^32 - 1))
+  double lr = 3.0 * log(static_cast<double>(B > 1 ? B : 1)) / log(4294967295.0);
+  int rounds = static_cast<int>(ceil(lr));
+  dim3 grid(tiles, epochs);
+  if (rounds == 0) cudaMemsetAsync(perm_out, 0, E * n * 4, stream);   // B == 1: identity
+  // value buffers alternate between perm_out and v1 so that the last pass lands in perm_out
+  const int total_passes = rounds * 4;
+  for (int r = 0; r < rounds; ++r) {
+    for (int pass = 0; pass < 4; ++pass) {
+      const int gp = r * 4 + pass;
+      SortArgs a;
+      a.key_in_dev = key_in_dev;
+      a.mode = mode;
+      a.round = r;
+      a.n = static_cast<uint32_t>(n);
+      a.keys_in = pass == 0 ? nullptr : ((pass & 1) ? k0 : k1);
+      a.keys_out = (pass & 1) ? k1 : k0;
+      const bool out_is_perm = ((total_passes - 1 - gp) % 2) == 0;
+      a.vals_out = out_is_perm ? perm_out : v1;
+      a.vals_in = gp == 0 ? nullptr : (out_is_perm ? v1 : perm_out);
+      a.hist = hist;
+      a.shift = pass * 8;
+      a.tiles = tiles;
+      rs_hist_kernel<<<grid, RS_THREADS, 0, stream>>>(a);
+      rs_scan_kernel<<<epochs, 1024, 0, stream>>>(hist, tiles);
+      rs_scatter_kernel<<<grid, RS_THREADS, 0, stream>>>(a);
+    }
+  }
+  if (key_out_dev) key_advance_kernel<<<1, 32, 0, stream>>>(key_in_dev, key_out_dev, mode, epochs);
+  return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
+}
+
+int perm_launch_count(long long B) {
+  const int rounds = static_cast<int>(ceil(3.0 * log(static_cast<double>(B > 1 ? B : 1)) / log(4294967295.0)));
+  return rounds * 4 * 3;
+}
+
+}  // namespace minppo

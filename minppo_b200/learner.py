@@ -1,0 +1,288 @@
+"""Host-side mirror of the reference's learner seam, over the C ABI.
+
+The reference has no operator / plugin interface for this path: the seam is the span of
+``_update_step`` between the rollout scan and the rebuilt ``RunnerState``
+(/root/reference/minppo/train.py:181-281).  Its logical signature is
+
+    learner_update(params, opt_state{count, mu, nu}, traj{obs, action, value, reward,
+                   log_prob, done}, last_val, rng) -> (params', opt_state', rng', losses[E, M, 4])
+
+``Learner.update`` is that function: same names (``Memory``, ``TrainState``-like state,
+``rng``), same time-major ``[T, N, ...]`` layout as ``jax.lax.scan`` stacks it, same error
+for a batch that does not divide into minibatches (train.py:253-255).  torch is used only for
+device memory, streams and ``torch.distributed`` plumbing; all arithmetic happens in
+libminppo_b200.so (sm_100a kernels).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Any, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import Config, to_c_config
+from .params import leaf_paths, leaf_shapes, param_count
+
+
+class Memory(NamedTuple):
+    """Same fields, order and layout as train.py:26-33 (time-major [T, N, ...])."""
+    done: torch.Tensor       # bool / uint8 [T, N]
+    action: torch.Tensor     # f32 [T, N, A]
+    value: torch.Tensor      # f32 [T, N]
+    reward: torch.Tensor     # f32 [T, N]
+    log_prob: torch.Tensor   # f32 [T, N]
+    obs: torch.Tensor        # f32 [T, N, D]
+    info: Any = None         # EnvMetrics; unused by the loss, passed through (train.py:283)
+
+
+@dataclasses.dataclass
+class TrainState:
+    """What flax's TrainState carries on this path (train.py:126-130): params, the Adam
+    moments and the step count, as flat fp32 arenas on the device."""
+    params: torch.Tensor     # f32 [P]
+    mu: torch.Tensor         # f32 [P]
+    nu: torch.Tensor         # f32 [P]
+    step: torch.Tensor       # i32 [1]  == ScaleByAdamState.count
+
+    @staticmethod
+    def create(flat_params: np.ndarray, device: torch.device) -> "TrainState":
+        p = torch.as_tensor(np.ascontiguousarray(flat_params, np.float32)).to(device)
+        return TrainState(p, torch.zeros_like(p), torch.zeros_like(p), torch.zeros(1, dtype=torch.int32, device=device))
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _as_u8(done: torch.Tensor) -> torch.Tensor:
+    if done.dtype == torch.bool:
+        return done.view(torch.uint8)          # zero-copy: bool is one byte
+    if done.dtype != torch.uint8:
+        raise TypeError(f"done must be bool or uint8, got {done.dtype}")
+    return done
+
+
+def _check(t: torch.Tensor, name: str, dtype: torch.dtype, shape, device: torch.device) -> torch.Tensor:
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    if t.device != device:
+        raise ValueError(f"{name}: expected device {device}, got {t.device}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous (time-major [T, N, ...])")
+    return t
+
+
+# ------------------------------------------------------------------------------------------
+# stateless entry points
+# ------------------------------------------------------------------------------------------
+def calculate_gae(mem_batch: Memory, last_val: torch.Tensor, gamma: float, gae_lambda: float,
+                  chunks: int = 0):
+    """``_calculate_gae(mem_batch, last_val) -> (advantages, targets)`` (train.py:185-207)."""
+    lib = _lib.load()
+    dev = mem_batch.reward.device
+    if dev.type != "cuda":
+        raise ValueError("calculate_gae needs CUDA tensors; there is no CPU path")
+    T, N = mem_batch.reward.shape
+    reward = _check(mem_batch.reward, "reward", torch.float32, (T, N), dev)
+    value = _check(mem_batch.value, "value", torch.float32, (T, N), dev)
+    done = _check(_as_u8(mem_batch.done), "done", torch.uint8, (T, N), dev)
+    last_val = _check(last_val, "last_val", torch.float32, (N,), dev)
+    adv = torch.empty_like(reward)
+    tgt = torch.empty_like(reward)
+    with torch.cuda.device(dev):
+        _lib.check(lib.minppo_gae_chunked(_ptr(reward), _ptr(value), _ptr(done), _ptr(last_val), _ptr(adv), _ptr(tgt),
+                                          T, N, gamma, gae_lambda, chunks, _stream_ptr(dev)))
+    return adv, tgt
+
+
+def permutations(rng: torch.Tensor, batch_size: int, epochs: int, prng_mode: int = _lib.PRNG_LEGACY):
+    """The ``epochs`` successive ``rng, _rng = split(rng); permutation(_rng, batch_size)`` of one
+    update (train.py:252, 258).  rng: uint32-as-int32/uint32 [2] CUDA tensor.
+    Returns (rng_out [2], perms int32 [epochs, batch_size])."""
+    lib = _lib.load()
+    dev = rng.device
+    if dev.type != "cuda":
+        raise ValueError("permutations needs CUDA tensors; there is no CPU path")
+    if rng.numel() != 2 or rng.element_size() != 4:
+        raise ValueError("rng must hold two 32-bit words")
+    perms = torch.empty((epochs, batch_size), dtype=torch.int32, device=dev)
+    rng_out = torch.empty_like(rng)
+    ws_bytes = lib.minppo_permutation_workspace_size(epochs, batch_size)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.minppo_permutation(_ptr(rng), _ptr(rng_out), prng_mode, epochs, batch_size, _ptr(perms),
+                                          _ptr(ws), ws_bytes, _stream_ptr(dev)))
+    return rng_out, perms
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.load().minppo_nccl_unique_id(buf))
+    return buf.raw
+
+
+# ------------------------------------------------------------------------------------------
+# the learner
+# ------------------------------------------------------------------------------------------
+class Learner:
+    """One context per (device, shape).  ``world_size > 1``: env-sharded data parallelism --
+    this rank's trajectory holds envs [rank*N/G, (rank+1)*N/G) of the GLOBAL batch, every rank
+    computes the global permutation, gradients are all-reduced per minibatch."""
+
+    def __init__(self, config: Config, obs_dim: int, act_dim: int, device: Optional[torch.device] = None,
+                 world_size: int = 1, rank: int = 0, nccl_id: Optional[bytes] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("minppo_b200.Learner needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.config = config
+        self.obs_dim, self.act_dim = obs_dim, act_dim
+        self.world_size, self.rank = world_size, rank
+        self.cconf = to_c_config(config, obs_dim, act_dim, world_size, rank)
+        t = config.training
+        self.T, self.N = t.num_steps, t.num_envs
+        self.Nl = self.N // world_size
+        self.E, self.M = t.update_epochs, t.num_minibatches
+        self.P = param_count(obs_dim, act_dim, config.model.hidden_size, config.model.num_layers)
+        batch = self.T * self.N
+        if (batch // self.M) * self.M != batch:
+            raise ValueError("`batch_size` must be equal to `num_steps * num_envs`")      # train.py:254-255
+        handle = C.c_void_p()
+        idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.minppo_ctx_create(C.byref(self.cconf), idbuf, C.byref(handle)))
+        self._h = handle
+        self.use_graph = bool(config.learner.use_graph)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.minppo_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- layout ---------------------------------------------------------------------------
+    def param_layout(self):
+        n = C.c_int32()
+        offs = (C.c_int64 * _lib.MAX_LEAVES)()
+        rows = (C.c_int64 * _lib.MAX_LEAVES)()
+        cols = (C.c_int64 * _lib.MAX_LEAVES)()
+        P = self.lib.minppo_param_layout(C.byref(self.cconf), C.byref(n), offs, rows, cols)
+        paths = leaf_paths(self.config.model.num_layers)
+        return P, [(paths[i], offs[i], rows[i], cols[i]) for i in range(n.value)]
+
+    # -- the update -----------------------------------------------------------------------
+    def update(self, train_state: TrainState, mem_batch: Memory, last_val: torch.Tensor, rng: torch.Tensor,
+               losses: Optional[torch.Tensor] = None, rng_out: Optional[torch.Tensor] = None):
+        """train.py:185-281.  In place on ``train_state``; returns (train_state, rng', losses[E, M, 4])
+        with losses columns (total, value_loss, actor_loss, entropy).  Nothing synchronises."""
+        dev = self.device
+        T, Nl, D, A = self.T, self.Nl, self.obs_dim, self.act_dim
+        obs = _check(mem_batch.obs, "obs", torch.float32, (T, Nl, D), dev)
+        action = _check(mem_batch.action, "action", torch.float32, (T, Nl, A), dev)
+        value = _check(mem_batch.value, "value", torch.float32, (T, Nl), dev)
+        reward = _check(mem_batch.reward, "reward", torch.float32, (T, Nl), dev)
+        log_prob = _check(mem_batch.log_prob, "log_prob", torch.float32, (T, Nl), dev)
+        done = _check(_as_u8(mem_batch.done), "done", torch.uint8, (T, Nl), dev)
+        last_val = _check(last_val, "last_val", torch.float32, (Nl,), dev)
+        _check(train_state.params, "params", torch.float32, (self.P,), dev)
+        _check(train_state.mu, "mu", torch.float32, (self.P,), dev)
+        _check(train_state.nu, "nu", torch.float32, (self.P,), dev)
+        _check(train_state.step, "step", torch.int32, (1,), dev)
+        if rng.numel() != 2 or rng.element_size() != 4 or rng.device != dev:
+            raise ValueError("rng must hold two 32-bit words on the learner's device")
+        if losses is None:
+            losses = torch.empty((self.E, self.M, 4), dtype=torch.float32, device=dev)
+        if rng_out is None:
+            rng_out = torch.empty_like(rng)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.minppo_update(
+                self._h, _ptr(train_state.params), _ptr(train_state.mu), _ptr(train_state.nu), _ptr(train_state.step),
+                _ptr(obs), _ptr(action), _ptr(value), _ptr(reward), _ptr(log_prob), _ptr(done), _ptr(last_val),
+                _ptr(rng), _ptr(rng_out), _ptr(losses), int(self.use_graph), _stream_ptr(dev)))
+        return train_state, rng_out, losses
+
+    def check(self) -> None:
+        """Synchronise and raise if the device-side error flag is set, a row list overflowed
+        or a gradient norm is not finite (the reference has no such guard)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.minppo_ctx_check(self._h, _stream_ptr(self.device)))
+
+    def launches_per_update(self) -> int:
+        return int(self.lib.minppo_update_launch_count(self._h))
+
+    # -- introspection (tests) --------------------------------------------------------------
+    _WHAT = {"advantages": 0, "targets": 1, "perms": 2, "grad": 3, "grad_norms": 4, "counts": 5, "adv_stats": 6}
+
+    def read(self, what: str) -> torch.Tensor:
+        EM, B, Bl = self.E * self.M, self.T * self.N, self.T * self.Nl
+        spec = {
+            "advantages": ((self.T, self.Nl), torch.float32), "targets": ((self.T, self.Nl), torch.float32),
+            "perms": ((self.E, B), torch.int32), "grad": ((self.P + 4,), torch.float32),
+            "grad_norms": ((EM,), torch.float32), "counts": ((EM,), torch.int32),
+            "adv_stats": ((2, EM), torch.float32),
+        }[what]
+        out = torch.empty(spec[0], dtype=spec[1], device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.minppo_ctx_read(self._h, self._WHAT[what], _ptr(out), out.numel() * out.element_size(),
+                                                _stream_ptr(self.device)))
+        return out
+
+    # -- host-buffer entry point (what bench.py's e2e number times) -------------------------
+    def update_host(self, host: "HostBatch") -> np.ndarray:
+        """Full round trip with HOST buffers: pinned H2D copies of the trajectory, params and
+        optimizer state, the update, and D2H of params / moments / step / rng / losses.  Blocks
+        until the results are on the host.  Returns losses[E, M, 4] (a view of pinned memory)."""
+        host.to_device(self.device)
+        ts = TrainState(host.d["params"], host.d["mu"], host.d["nu"], host.d["step"])
+        mem = Memory(host.d["done"], host.d["action"], host.d["value"], host.d["reward"], host.d["log_prob"],
+                     host.d["obs"])
+        self.update(ts, mem, host.d["last_val"], host.d["rng"], host.d["losses"], host.d["rng_out"])
+        host.to_host()
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.h["losses"].numpy()
+
+
+class HostBatch:
+    """Pinned host buffers + their device twins for ``Learner.update_host``."""
+    IN = ("obs", "action", "value", "reward", "log_prob", "done", "last_val", "rng", "params", "mu", "nu", "step")
+    OUT = ("params", "mu", "nu", "step", "rng_out", "losses")
+
+    def __init__(self, learner: Learner):
+        T, Nl, D, A, P = learner.T, learner.Nl, learner.obs_dim, learner.act_dim, learner.P
+        f32, i32, u8 = torch.float32, torch.int32, torch.uint8
+        spec = {
+            "obs": ((T, Nl, D), f32), "action": ((T, Nl, A), f32), "value": ((T, Nl), f32), "reward": ((T, Nl), f32),
+            "log_prob": ((T, Nl), f32), "done": ((T, Nl), u8), "last_val": ((Nl,), f32), "rng": ((2,), i32),
+            "params": ((P,), f32), "mu": ((P,), f32), "nu": ((P,), f32), "step": ((1,), i32),
+            "rng_out": ((2,), i32), "losses": ((learner.E, learner.M, 4), f32),
+        }
+        self.h = {k: torch.zeros(s, dtype=dt).pin_memory() for k, (s, dt) in spec.items()}
+        self.d = {k: torch.empty(s, dtype=dt, device=learner.device) for k, (s, dt) in spec.items()}
+
+    def h2d_bytes(self) -> int:
+        return sum(self.h[k].numel() * self.h[k].element_size() for k in self.IN)
+
+    def d2h_bytes(self) -> int:
+        return sum(self.h[k].numel() * self.h[k].element_size() for k in self.OUT)
+
+    def to_device(self, device) -> None:
+        for k in self.IN:
+            self.d[k].copy_(self.h[k], non_blocking=True)
+
+    def to_host(self) -> None:
+        for k in self.OUT:
+            self.h[k].copy_(self.d[k], non_blocking=True)

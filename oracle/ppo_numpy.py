@@ -189,31 +189,36 @@ def _dact_from_out(h, tanh: bool):
 
 
 def mlp_forward(mlp: Dict, x, num_layers: int, tanh: bool, gemm="exact"):
-    """Returns (out, [a_0 .. a_L]) with a_0 = x (train.py:61-68)."""
-    acts = [x]
-    a = x
+    """Returns (out, [a_0 .. a_L]) with a_0 = x (train.py:61-68).
+
+    gemm="bf16" mirrors the CUDA path's rounding points (DESIGN.md "precision"): the
+    observation and hidden kernels are rounded to bf16 for the tensor-core GEMMs (fp32
+    accumulate), every hidden activation is STORED as bf16 (so all its consumers see the
+    rounded value), the output head runs in fp32 on the stored activation."""
+    a = _q(x, gemm)
+    acts = [a]
     for i in range(num_layers):
         d = mlp[f"Dense_{i}"]
-        a = _act(_q(a, gemm) @ _q(d["kernel"], gemm) + d["bias"], tanh)
+        a = _q(_act(a @ _q(d["kernel"], gemm) + d["bias"], tanh), gemm)
         acts.append(a)
     d = mlp[f"Dense_{num_layers}"]
-    out = _q(a, gemm) @ _q(d["kernel"], gemm) + d["bias"]
+    out = a @ d["kernel"] + d["bias"]
     return out, acts
 
 
 def mlp_backward(mlp: Dict, acts, dout, num_layers: int, tanh: bool, gemm="exact"):
-    """Gradient of sum(out * dout) w.r.t. every kernel / bias of one MLP."""
+    """Gradient of sum(out * dout) w.r.t. every kernel / bias of one MLP.  gemm="bf16": dz of
+    every hidden layer is stored as bf16 once; dW, db and the next dA all see that value."""
     grads: Dict = {}
     d = mlp[f"Dense_{num_layers}"]
-    a = acts[num_layers]
-    grads[f"Dense_{num_layers}"] = {"kernel": _q(a, gemm).T @ _q(dout, gemm), "bias": dout.sum(0)}
-    da = _q(dout, gemm) @ _q(d["kernel"], gemm).T
+    grads[f"Dense_{num_layers}"] = {"kernel": acts[num_layers].T @ dout, "bias": dout.sum(0)}
+    da = dout @ d["kernel"].T
     for i in range(num_layers - 1, -1, -1):
-        dz = da * _dact_from_out(acts[i + 1], tanh)
+        dz = _q(da * _dact_from_out(acts[i + 1], tanh), gemm)
         dd = mlp[f"Dense_{i}"]
-        grads[f"Dense_{i}"] = {"kernel": _q(acts[i], gemm).T @ _q(dz, gemm), "bias": dz.sum(0)}
+        grads[f"Dense_{i}"] = {"kernel": acts[i].T @ dz, "bias": dz.sum(0)}
         if i > 0:
-            da = _q(dz, gemm) @ _q(dd["kernel"], gemm).T
+            da = dz @ _q(dd["kernel"], gemm).T
     return grads
 
 

@@ -153,4 +153,5 @@ def update(params: Dict, opt: Dict, traj: Dict, last_val, rng, hp: Hyper, perms=
             ls, grads = loss_and_grads(params, mb, hp)
             params, opt, _ = clip_adam_step(params, grads, opt, hp)
             losses.append(torch.stack(ls))
-    return params, opt, rng, torch.stack(losses).reshape(E, Mrun, 4), {"advantages": adv, "targets": tgt}
+    out = torch.stack(losses).reshape(E, Mrun, 4) if losses else torch.zeros((E, 0, 4))
+    return params, opt, rng, out, {"advantages": adv, "targets": tgt}

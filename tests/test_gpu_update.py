@@ -1,0 +1,209 @@
+"""One full learner update through the C ABI against the oracle (train.py:181-281).
+
+GEMM precision of the CUDA path (declared): BF16 operands on tcgen05 tensor cores, FP32
+accumulation; hidden activations and dZ stored as BF16; heads, loss, reductions, clip and Adam
+in FP32.  Two comparisons per case:
+
+* vs the oracle with the SAME rounding points emulated (gemm="bf16", float32): isolates
+  algorithmic agreement from precision.  Tolerances: losses 2e-3 * max|loss|, gradient
+  5e-3 * max|g| -- what remains is fp32 summation order and one-bf16-ulp rounding flips.
+* vs the float64 oracle: shows the precision cost.  Tolerances: losses 3e-2 * max|loss|;
+  parameters after the update: max |dp| <= 12 * lr (Adam's normalised step is <= ~lr per
+  update and sign-sensitive where gradients are near zero, so a handful of steps of drift is
+  the natural unit; 128 steps are taken).
+Bit-exact items: permutations, rng key, Adam step count.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ppo_numpy as P
+from oracle import synth, threefry
+from tests.helpers import flat_grads, rel_err, run_gpu_update
+
+pytestmark = pytest.mark.gpu
+
+METRICS = {}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_metrics():
+    yield
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_metrics.json"), "w") as f:
+            json.dump(METRICS, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+CASES = {
+    # config 1 of BASELINE.json: N=16, T=10 -> B=160, M=32 -> mb=5, E=4 (plumbing / parity shape)
+    "c1": dict(hp=dict(num_envs=16, num_steps=10, num_minibatches=32, update_epochs=4, anneal_lr=False), D=225, A=10),
+    # medium: several 128-row tiles per minibatch, annealed LR with the default 1e9 timesteps
+    "medium": dict(hp=dict(num_envs=64, num_steps=32, num_minibatches=4, update_epochs=2, anneal_lr=True), D=225, A=10),
+    # ragged shapes: D not a multiple of 64 below one k-block, small A, narrower net, 1 hidden layer
+    "ragged": dict(hp=dict(num_envs=24, num_steps=16, num_minibatches=3, update_epochs=2, anneal_lr=False,
+                           hidden_size=128, num_layers=1, ent_coef=0.01), D=37, A=3),
+    # 3 hidden layers, relu actor (model.use_tanh=false), aligned D, partitionable PRNG
+    "deep": dict(hp=dict(num_envs=32, num_steps=16, num_minibatches=2, update_epochs=2, anneal_lr=False,
+                         hidden_size=192, num_layers=3, use_tanh=False, prng_mode=threefry.PARTITIONABLE), D=256, A=16),
+}
+
+
+def _oracle(hp, pr, dtype, gemm, perms=None):
+    p0 = P.tree_like(pr["params"], lambda x: x.astype(dtype))
+    return P.update(p0, P.init_opt_state(p0), pr["traj"], pr["last_val"], pr["rng"], hp, dtype=dtype, gemm=gemm,
+                    perms=perms)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_update_parity(name, cuda_device):
+    case = CASES[name]
+    hp = P.Hyper(**case["hp"])
+    pr = synth.make_problem(hp, case["D"], case["A"], seed=7, done_p=0.02)
+    got = run_gpu_update(hp, pr, cuda_device)
+
+    p64, o64, rng64, l64, aux64 = _oracle(hp, pr, np.float64, "exact")
+    pbf, obf, _, lbf, auxbf = _oracle(hp, pr, np.float32, "bf16", perms=aux64["perms"])
+
+    # bit-exact: permutations, key chain, step count
+    assert np.array_equal(got["perms"], aux64["perms"])
+    assert np.array_equal(got["rng"], rng64)
+    assert got["step"] == hp.update_epochs * hp.num_minibatches == o64["count"]
+    # GAE: 1e-5 relative (north_star)
+    assert np.abs(got["advantages"] - aux64["advantages"]).max() <= 1e-5 * np.abs(aux64["advantages"]).max()
+    assert np.abs(got["targets"] - aux64["targets"]).max() <= 1e-5 * np.abs(aux64["targets"]).max()
+
+    lr = hp.opt_lr if not hp.anneal_lr else hp.training_lr
+    flat64 = P.flatten_params(p64, hp.num_layers, np.float64)
+    flatbf = P.flatten_params(pbf, hp.num_layers, np.float64)
+    m = {
+        "loss_vs_bf16_oracle": rel_err(got["losses"], lbf),
+        "loss_vs_fp64_oracle": rel_err(got["losses"], l64),
+        "gnorm_vs_bf16_oracle": rel_err(got["grad_norms"], auxbf["grad_norms"]),
+        "gnorm_vs_fp64_oracle": rel_err(got["grad_norms"], aux64["grad_norms"]),
+        "param_absdiff_vs_bf16_oracle_in_lr": float(np.abs(got["params"] - flatbf).max() / lr),
+        "param_absdiff_vs_fp64_oracle_in_lr": float(np.abs(got["params"] - flat64).max() / lr),
+        "param_rms_vs_fp64_oracle_in_lr": float(np.sqrt(np.mean((got["params"] - flat64) ** 2)) / lr),
+        "first_loss_gpu": [float(x) for x in got["losses"][0, 0]],
+        "first_loss_fp64": [float(x) for x in l64[0, 0]],
+        "launches": got["launches"],
+    }
+    METRICS[name] = m
+    assert np.all(np.isfinite(got["losses"])) and np.all(np.isfinite(got["params"]))
+    assert m["loss_vs_bf16_oracle"] < 2e-3, m
+    assert m["loss_vs_fp64_oracle"] < 3e-2, m
+    assert m["gnorm_vs_bf16_oracle"] < 2e-2, m
+    assert m["param_absdiff_vs_fp64_oracle_in_lr"] < 12.0, m
+    assert m["param_rms_vs_fp64_oracle_in_lr"] < 1.0, m
+
+
+@pytest.mark.parametrize("name", ["medium", "ragged", "deep"])
+def test_single_minibatch_gradient(name, cuda_device):
+    """E = 1, M = 1: the one minibatch is the whole batch, so the gradient the optimizer saw can
+    be read back and compared leaf by leaf with the hand-derived / autograd-checked oracle."""
+    case = CASES[name]
+    kw = dict(case["hp"])
+    kw.update(num_minibatches=1, update_epochs=1)
+    hp = P.Hyper(**kw)
+    pr = synth.make_problem(hp, case["D"], case["A"], seed=9, done_p=0.02)
+    # perturb the policy so that ratio != 1 and both clip branches are exercised
+    g = np.random.default_rng(1)
+    pr["traj"]["log_prob"] = (pr["traj"]["log_prob"] + 0.3 * g.standard_normal(pr["traj"]["log_prob"].shape)).astype(np.float32)
+    pr["traj"]["value"] = (pr["traj"]["value"] + 0.3 * g.standard_normal(pr["traj"]["value"].shape)).astype(np.float32)
+    got = run_gpu_update(hp, pr, cuda_device)
+
+    def oracle_grads(dtype, gemm):
+        p0 = P.tree_like(pr["params"], lambda x: x.astype(dtype))
+        adv, tgt = P.gae(pr["traj"]["reward"], pr["traj"]["value"], pr["traj"]["done"], pr["last_val"], hp.gamma,
+                         hp.gae_lambda, dtype)
+        flat = P.flatten_traj({"obs": pr["traj"]["obs"].astype(dtype), "action": pr["traj"]["action"].astype(dtype),
+                               "value": pr["traj"]["value"].astype(dtype), "log_prob": pr["traj"]["log_prob"].astype(dtype),
+                               "adv": adv, "tgt": tgt})
+        _, sub = threefry.split(pr["rng"], 2, hp.prng_mode)
+        perm = threefry.permutation(sub, hp.batch_size, hp.prng_mode)
+        mb = {k: v[perm] for k, v in flat.items()}
+        ls, gr = P.loss_and_grads(p0, mb, hp, gemm)
+        return ls, flat_grads(gr, hp.num_layers)
+
+    ls64, g64 = oracle_grads(np.float64, "exact")
+    lsbf, gbf = oracle_grads(np.float32, "bf16")
+    ggpu = got["grad"][:g64.size].astype(np.float64)
+    m = {
+        "grad_vs_bf16_oracle": rel_err(ggpu, gbf), "grad_vs_fp64_oracle": rel_err(ggpu, g64),
+        "loss_vs_bf16_oracle": rel_err(got["losses"][0, 0], np.array(lsbf)),
+        "loss_vs_fp64_oracle": rel_err(got["losses"][0, 0], np.array(ls64)),
+        "gnorm_gpu": float(got["grad_norms"][0, 0]), "gnorm_fp64": float(np.linalg.norm(g64)),
+    }
+    # per-leaf relative errors (relative to the leaf's own max) against the emulated oracle
+    off = 0
+    for pth, shp in zip(P.leaf_order(hp.num_layers), P.leaf_shapes(case["D"], case["A"], hp.hidden_size, hp.num_layers)):
+        n = int(np.prod(shp))
+        m["leaf/" + "/".join(pth)] = rel_err(ggpu[off:off + n], gbf[off:off + n])
+        off += n
+    METRICS["grad_" + name] = m
+    assert m["grad_vs_bf16_oracle"] < 5e-3, m
+    assert m["grad_vs_fp64_oracle"] < 5e-2, m
+    assert m["loss_vs_bf16_oracle"] < 2e-3, m
+    assert abs(m["gnorm_gpu"] - m["gnorm_fp64"]) < 3e-2 * m["gnorm_fp64"], m
+
+
+def test_update_deterministic_and_graph_equals_eager(cuda_device):
+    """No atomics anywhere: two runs are bitwise identical, and the CUDA-graph replay equals the
+    directly enqueued kernels."""
+    hp = P.Hyper(**CASES["medium"]["hp"])
+    pr = synth.make_problem(hp, 225, 10, seed=3)
+    a = run_gpu_update(hp, pr, cuda_device, use_graph=True)
+    b = run_gpu_update(hp, pr, cuda_device, use_graph=True)
+    c = run_gpu_update(hp, pr, cuda_device, use_graph=False)
+    for k in ("params", "mu", "nu", "losses", "grad"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], c[k]), k
+
+
+def test_update_resumes_from_optimizer_state(cuda_device):
+    """Second update starting from non-zero mu/nu/count (what RunnerState carries across
+    _update_step calls, train.py:276-281) matches the oracle continuing from the same state."""
+    hp = P.Hyper(**CASES["medium"]["hp"])
+    pr = synth.make_problem(hp, 225, 10, seed=4)
+    p0 = P.tree_like(pr["params"], lambda x: x.astype(np.float32))
+    p1, o1, rng1, _, aux1 = P.update(p0, P.init_opt_state(p0), pr["traj"], pr["last_val"], pr["rng"], hp,
+                                     dtype=np.float32, gemm="bf16")
+    pr2 = dict(pr)
+    pr2["params"], pr2["rng"] = p1, rng1
+    got = run_gpu_update(hp, pr2, cuda_device, opt=o1)
+    p2, o2, rng2, l2, aux2 = P.update(p1, o1, pr["traj"], pr["last_val"], rng1, hp, dtype=np.float32, gemm="bf16")
+    assert got["step"] == o2["count"]
+    assert np.array_equal(got["rng"], rng2)
+    assert np.array_equal(got["perms"], aux2["perms"])
+    assert rel_err(got["losses"], l2) < 2e-3
+    lr = hp.training_lr
+    assert np.abs(got["params"] - P.flatten_params(p2, hp.num_layers, np.float64)).max() < 12 * lr
+
+
+def test_update_rejects_bad_arguments(cuda_device):
+    import torch
+
+    from minppo_b200 import _lib
+    from minppo_b200.learner import Learner
+    from tests.helpers import hyper_to_config
+
+    with pytest.raises(ValueError, match="batch_size"):          # train.py:253-255
+        Learner(hyper_to_config(P.Hyper(num_envs=10, num_steps=3, num_minibatches=4)), 8, 2, cuda_device)
+    with pytest.raises(_lib.MinppoError) as e:
+        Learner(hyper_to_config(P.Hyper(num_envs=16, num_steps=4, num_minibatches=4, hidden_size=100)), 8, 2, cuda_device)
+    assert e.value.code == _lib.ERR_UNSUPPORTED
+    lrn = Learner(hyper_to_config(P.Hyper(num_envs=16, num_steps=4, num_minibatches=4)), 8, 2, cuda_device)
+    from minppo_b200.learner import Memory, TrainState
+
+    ts = TrainState.create(np.zeros(lrn.P, np.float32), cuda_device)
+    z = lambda *s: torch.zeros(*s, device=cuda_device)
+    bad = Memory(done=torch.zeros(4, 16, dtype=torch.bool, device=cuda_device), action=z(4, 16, 2), value=z(4, 16),
+                 reward=z(4, 16), log_prob=z(4, 16), obs=z(4, 16, 9))     # wrong obs dim
+    with pytest.raises(ValueError, match="obs"):
+        lrn.update(ts, bad, z(16), torch.zeros(2, dtype=torch.int32, device=cuda_device))
+    lrn.close()
