@@ -16,9 +16,10 @@
 
 namespace minppo {
 
-constexpr int OPT_THREADS = 256;
+constexpr int OPT_THREADS = 1024;
+constexpr int OPT_EPT = 8;                    // elements per thread per sweep (registers)
 
-MINPPO_DEVINL float block_sum(float v, float* scratch /*[OPT_THREADS/32]*/) {
+MINPPO_DEVINL float block_sum(float v, float* scratch /*[32]*/) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
   __syncthreads();
@@ -49,63 +50,83 @@ MINPPO_DEVINL void grid_barrier(unsigned long long* counter, int* err_flag) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(OPT_THREADS) opt_kernel(const OptArgs a) {
-  __shared__ float scratch[OPT_THREADS / 32];
+// fixed-order sum of `nparts` partials, 8 loads in flight
+MINPPO_DEVINL float sum_partials(const float* __restrict__ src, int nparts, size_t stride) {
+  float acc = 0.f;
+  int p = 0;
+  for (; p + 8 <= nparts; p += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + static_cast<size_t>(p + u) * stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
+  for (; p < nparts; ++p) acc += __ldcg(src + static_cast<size_t>(p) * stride);
+  return acc;
+}
+
+MINPPO_DEVINL int find_leaf_idx(const OptArgs& a, int i) {
+  int l = 0;
+  while (l + 1 < a.nleaves && i >= a.leaf[l + 1].offset) ++l;
+  return l;
+}
+
+__global__ void __launch_bounds__(OPT_THREADS, 1) opt_kernel(const OptArgs a) {
+  __shared__ float scratch[32];
   __shared__ float s_bcast[2];
   const int P = a.P;
   const int gtid = blockIdx.x * OPT_THREADS + threadIdx.x;
   const int gthreads = gridDim.x * OPT_THREADS;
+  const int sweep = gthreads * OPT_EPT;
 
-  if (a.do_reduce) {
-    for (int i = gtid; i < P + 2; i += gthreads) {
-      float g = 0.f;
-      if (i < P) {
-        // locate the leaf (<= MINPPO_MAX_LEAVES entries, ascending offsets)
-        int l = 0;
-        while (l + 1 < a.nleaves && i >= a.leaf[l + 1].offset) ++l;
-        const OptLeaf& L = a.leaf[l];
-        const int e = i - L.offset;
-        const float* src = L.grad_src + L.src_offset + e;
-        for (int p = 0; p < L.nparts; ++p) g += src[static_cast<size_t>(p) * L.part_stride];
-        g += L.grad_bias;                                  // -ent_coef on log_std (rank 0 only)
-      } else {
-        const float* src = a.loss_src + a.loss_src_offset + (i - P);
-        for (int p = 0; p < a.loss_nparts; ++p) g += src[static_cast<size_t>(p) * a.loss_part_stride];
-      }
-      a.gflat[i] = g;
-    }
-    if (!a.do_apply) return;
-    // phase A re-reads gflat written by other threads of the same launch only after the barrier below
+  const int count = a.do_apply ? *a.count : 0;             // Adam step count BEFORE this step
+  float ent = a.entropy_const;                             // A * (0.5 + 0.5 log 2pi) + sum log|scale|
+  if (a.do_apply && blockIdx.x == 0 && threadIdx.x == 0 && a.losses_out) {
+    // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the barrier)
+    for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(a.params[a.off_logstd + j])));
   }
 
-  if (a.do_apply) {
-    const int count = *a.count;                            // Adam step count BEFORE this step
-    float ent = a.entropy_const;                           // A * (0.5 + 0.5 log 2pi) + sum log|scale|
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.losses_out) {
-      // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the barrier)
-      for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(a.params[a.off_logstd + j])));
-    }
+  // P <= sweep in every supported shape except very large nets; loop over sweeps for generality.
+  // Within a sweep every thread owns OPT_EPT elements kept in registers across the grid barrier.
+  for (int base = 0; base < P + 2; base += sweep) {
+    float g[OPT_EPT], pv[OPT_EPT], mv[OPT_EPT], nv[OPT_EPT];
     float ss = 0.f;
-    if (a.do_reduce) {
-      // own elements were just written by this very thread: same index mapping
-      for (int i = gtid; i < P; i += gthreads) { const float g = a.gflat[i]; ss = fmaf(g, g, ss); }
-    } else {
-      for (int i = gtid; i < P; i += gthreads) { const float g = a.gflat[i]; ss = fmaf(g, g, ss); }
+#pragma unroll
+    for (int k = 0; k < OPT_EPT; ++k) {
+      const int i = base + k * gthreads + gtid;
+      g[k] = 0.f; pv[k] = 0.f; mv[k] = 0.f; nv[k] = 0.f;
+      if (i < P) {
+        if (a.do_reduce) {
+          const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
+          g[k] = sum_partials(L.grad_src + L.src_offset + (i - L.offset), L.nparts, L.part_stride) + L.grad_bias;
+          if (!a.do_apply || a.keep_gflat) a.gflat[i] = g[k];
+        } else {
+          g[k] = a.gflat[i];
+        }
+        if (a.do_apply) {                                  // prefetch the optimizer state before the barrier
+          pv[k] = a.params[i]; mv[k] = a.mu[i]; nv[k] = a.nu[i];
+          ss = fmaf(g[k], g[k], ss);
+        }
+      } else if (i < P + 2 && a.do_reduce) {
+        a.gflat[i] = sum_partials(a.loss_src + a.loss_src_offset + (i - P), a.loss_nparts, a.loss_part_stride);
+      }
     }
+    if (!a.do_apply) continue;
+    // NOTE: with P > sweep the global norm needs all sweeps first; handled by the host (opt_launch
+    // sizes the grid so that P + 2 <= sweep, or falls back to two launches).
     const float bs = block_sum(ss, scratch);
     if (threadIdx.x == 0) a.block_ss[blockIdx.x] = bs;
     grid_barrier(a.barrier, a.err_flag);
     if (threadIdx.x < 32) {
       float s = 0.f;
-      for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += 32) s += a.block_ss[b];
+      for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(a.block_ss + b);
       s = warp_sum(s);
       if (threadIdx.x == 0) s_bcast[0] = sqrtf(s);
     }
     __syncthreads();
     const float gnorm = s_bcast[0];
     const bool trigger = gnorm < a.max_norm;               // optax.clip_by_global_norm
-    // learning rate, train.py:98-101 (annealed) or opt.lr
-    float lr;
+    float lr;                                              // train.py:98-101 (annealed) or opt.lr
     if (a.anneal) {
       const float frac = 1.0f - static_cast<float>(count / a.anneal_div) / static_cast<float>(a.num_updates);
       lr = a.lr * frac;
@@ -115,19 +136,20 @@ __global__ void __launch_bounds__(OPT_THREADS) opt_kernel(const OptArgs a) {
     const float cnt1 = static_cast<float>(count + 1);
     const float c1 = 1.0f - powf(a.b1, cnt1);
     const float c2 = 1.0f - powf(a.b2, cnt1);
-    for (int i = gtid; i < P; i += gthreads) {
-      float g = a.gflat[i];
-      if (!trigger) g = (g / gnorm) * a.max_norm;
-      const float mu = a.one_minus_b1 * g + a.b1 * a.mu[i];
-      const float nu = a.one_minus_b2 * (g * g) + a.b2 * a.nu[i];
+#pragma unroll
+    for (int k = 0; k < OPT_EPT; ++k) {
+      const int i = base + k * gthreads + gtid;
+      if (i >= P) continue;
+      float gg = g[k];
+      if (!trigger) gg = (gg / gnorm) * a.max_norm;
+      const float mu = a.one_minus_b1 * gg + a.b1 * mv[k];
+      const float nu = a.one_minus_b2 * (gg * gg) + a.b2 * nv[k];
       const float u = (mu / c1) / (sqrtf(nu / c2 + a.eps_root) + a.eps);
-      const float p = a.params[i] + (-lr) * u;
+      const float p = pv[k] + (-lr) * u;
       a.params[i] = p;
       a.mu[i] = mu;
       a.nu[i] = nu;
-      int l = 0;
-      while (l + 1 < a.nleaves && i >= a.leaf[l + 1].offset) ++l;
-      const OptLeaf& L = a.leaf[l];
+      const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
       if (L.img_t || L.img_n) {
         const int e = i - L.offset;
         const int r = e / L.cols, c = e % L.cols;          // kernel [in=r][out=c]
@@ -140,8 +162,8 @@ __global__ void __launch_bounds__(OPT_THREADS) opt_kernel(const OptArgs a) {
       *a.count = count + 1;
       if (a.losses_out) {
         // gflat[P] = sum max(vl, vlc), gflat[P+1] = sum min(l1, l2) over the global minibatch
-        const float value_loss = 0.5f * a.gflat[P] * a.inv_mb;
-        const float actor_loss = -a.gflat[P + 1] * a.inv_mb;
+        const float value_loss = 0.5f * __ldcg(a.gflat + P) * a.inv_mb;
+        const float actor_loss = -__ldcg(a.gflat + P + 1) * a.inv_mb;
         a.losses_out[0] = actor_loss + a.vf_coef * value_loss - a.ent_coef * ent;
         a.losses_out[1] = value_loss;
         a.losses_out[2] = actor_loss;
@@ -186,7 +208,10 @@ __global__ void weight_images_kernel(const OptArgs a) {
   }
 }
 
+int opt_max_params(int blocks) { return blocks * OPT_THREADS * OPT_EPT - 2; }
+
 int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream) {
+  if (a.do_apply && a.P > opt_max_params(blocks)) return MINPPO_ERR_UNSUPPORTED;   // single-sweep global norm
   opt_kernel<<<blocks, OPT_THREADS, 0, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }

@@ -337,6 +337,7 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
     }
   }
   o->nleaves = n;
+  o->keep_gflat = 1;                         // minppo_ctx_read(what=3) returns the last reduced gradient
   o->P = static_cast<int>(c->P);
   o->A = c->A;
   o->gflat = c->gflat;
@@ -661,6 +662,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     c->S = S;
   }
   c->opt_blocks = c->sm_count;
+  if (c->P > opt_max_params(c->opt_blocks)) { set_error("parameter count %lld exceeds the single-sweep optimizer kernel (%d)", c->P, opt_max_params(c->opt_blocks)); return fail(MINPPO_ERR_UNSUPPORTED); }
   const int H = c->H, L = c->L, A = c->A;
   // head partial layout
   {

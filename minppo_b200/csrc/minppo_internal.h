@@ -78,6 +78,7 @@ struct OptArgs {
   OptLeaf leaf[MINPPO_MAX_LEAVES];
   int nleaves, P, A;
   int do_reduce, do_apply;
+  int keep_gflat;                // also store the reduced gradient when reduce+apply are fused (tests)
   float* gflat;                  // [P + 4]
   const float* loss_src;         // loss partial sums (2 per partial)
   int loss_src_offset, loss_nparts, loss_part_stride;
@@ -94,6 +95,7 @@ struct OptArgs {
   float inv_mb, vf_coef, ent_coef, entropy_const;
 };
 int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream);
+int opt_max_params(int blocks);
 int weight_images_launch(const OptArgs& a, cudaStream_t stream);
 int obs_image_launch(const float* obs, __nv_bfloat16* img, long long rows, int cols, int ld, cudaStream_t stream);
 

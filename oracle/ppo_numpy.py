@@ -255,12 +255,17 @@ def _dclip(x, lo, hi):
     return d + 0.5 * ((x == lo) | (x == hi))
 
 
-def loss_and_grads(params: Dict, mb: Dict, hp: Hyper, gemm="exact"):
+def loss_and_grads(params: Dict, mb: Dict, hp: Hyper, gemm="exact", n_total=None, adv_mean_std=None):
     """mb: obs[mb,D], action[mb,A], value[mb], log_prob[mb], adv[mb], tgt[mb].
-    Returns ((total, value_loss, actor_loss, entropy), grads-tree)."""
+    Returns ((total, value_loss, actor_loss, entropy), grads-tree).
+
+    ``n_total`` / ``adv_mean_std`` describe the env-sharded case: ``mb``
+    holds only this rank's rows of a minibatch of ``n_total`` rows whose advantage mean / std
+    are given; means become sums over local rows divided by ``n_total`` so that SUMMING the
+    returned losses (except entropy) and gradients over ranks gives the global values."""
     obs = mb["obs"]
     dt = obs.dtype.type
-    n = obs.shape[0]
+    n = obs.shape[0] if n_total is None else n_total
     A = mb["action"].shape[1]
     eps = dt(hp.clip_eps)
     mean, log_std, v, (acts_a, acts_c) = actor_critic_forward(params, obs, hp, gemm)
@@ -272,15 +277,16 @@ def loss_and_grads(params: Dict, mb: Dict, hp: Hyper, gemm="exact"):
     v_clip = v_old + np.clip(dv, -eps, eps)
     vl = (v - tgt) ** 2
     vlc = (v_clip - tgt) ** 2
-    value_loss = dt(0.5) * np.maximum(vl, vlc).mean()
+    value_loss = dt(0.5) * np.maximum(vl, vlc).sum() / dt(n)
 
     # actor loss (train.py:234-239); advantage normalised over THIS minibatch (235)
     ratio = np.exp(logp - mb["log_prob"])
     adv = mb["adv"]
-    adv_n = (adv - adv.mean()) / (adv.std() + dt(1e-8))
+    a_mean, a_std = (adv.mean(), adv.std()) if adv_mean_std is None else (dt(adv_mean_std[0]), dt(adv_mean_std[1]))
+    adv_n = (adv - a_mean) / (a_std + dt(1e-8))
     l1 = ratio * adv_n
     l2 = np.clip(ratio, dt(1.0) - eps, dt(1.0) + eps) * adv_n
-    actor_loss = (-np.minimum(l1, l2)).mean()
+    actor_loss = (-np.minimum(l1, l2)).sum() / dt(n)
     entropy = gaussian_entropy(log_std, A)          # batch-independent (train.py:240)
     total = actor_loss + dt(hp.vf_coef) * value_loss - dt(hp.ent_coef) * entropy
 
