@@ -64,6 +64,7 @@ typedef struct minppo_config {
   int32_t rank;              /* this rank owns envs [rank*N/G, (rank+1)*N/G)          */
   int32_t fast_tanh;         /* 1: tanh.approx.f32 (MUFU) in the GEMM epilogue        */
   int32_t dw_splits;         /* split-K factor of the weight-gradient GEMMs (0 = auto) */
+  int32_t disable_fused;     /* 1: always use the layer-wise kernels (default 0: fused step kernel when L == 2) */
   double training_lr;        /* training.lr  (annealed path, train.py:101)            */
   double opt_lr;             /* opt.lr       (constant path, train.py:123)            */
   double max_grad_norm;      /* opt.max_grad_norm                                     */

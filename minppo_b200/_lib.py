@@ -37,6 +37,7 @@ class MinppoConfig(C.Structure):
         ("hidden_size", C.c_int32), ("num_layers", C.c_int32), ("use_tanh", C.c_int32),
         ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("prng_mode", C.c_int32),
         ("world_size", C.c_int32), ("rank", C.c_int32), ("fast_tanh", C.c_int32), ("dw_splits", C.c_int32),
+        ("disable_fused", C.c_int32),
         ("training_lr", C.c_double), ("opt_lr", C.c_double), ("max_grad_norm", C.c_double),
         ("gamma", C.c_double), ("gae_lambda", C.c_double), ("clip_eps", C.c_double),
         ("ent_coef", C.c_double), ("vf_coef", C.c_double),

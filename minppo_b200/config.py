@@ -59,6 +59,7 @@ class LearnerExtras:
     fast_tanh: bool = False              # tanh.approx.f32 in the GEMM epilogue
     use_graph: bool = True               # replay one CUDA graph per update
     dw_splits: int = 0                   # 0 = auto
+    fused: bool = True                   # fused forward+loss+backward kernel (2 hidden layers); False = layer-wise kernels
 
 
 @dataclass
@@ -125,6 +126,7 @@ def to_c_config(cfg: Config, obs_dim: int, act_dim: int, world_size: int = 1, ra
     c.obs_dim, c.act_dim, c.prng_mode = obs_dim, act_dim, mode
     c.world_size, c.rank = world_size, rank
     c.fast_tanh, c.dw_splits = int(cfg.learner.fast_tanh), cfg.learner.dw_splits
+    c.disable_fused = int(not cfg.learner.fused)
     c.training_lr, c.opt_lr, c.max_grad_norm = cfg.training.lr, cfg.opt.lr, cfg.opt.max_grad_norm
     c.gamma, c.gae_lambda, c.clip_eps = cfg.rl.gamma, cfg.rl.gae_lambda, cfg.rl.clip_eps
     c.ent_coef, c.vf_coef = cfg.rl.ent_coef, cfg.rl.vf_coef

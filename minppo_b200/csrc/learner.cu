@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "minppo_internal.h"
 #include "umma_gemm.cuh"
+#include "fused_step.cuh"
 
 namespace minppo {
 
@@ -209,6 +210,8 @@ struct minppo_ctx {
   int T, N, Nl, n0, M, E, L, H, D, Dp, A;
   long long B, Bl, P;
   int mb, cap, M_pad, m_tiles, tiles64, S;
+  bool fused;                 // fused step kernel (L == 2, Dp <= 256, A <= 16)
+  int head_parts;             // head partials per minibatch: m_tiles (fused) or tiles64
   std::vector<LeafInfo> leaves;
   // device buffers
   std::vector<void*> allocs;
@@ -294,6 +297,7 @@ static int init_kernel_attrs() {
   CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_DACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_PARTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   if (head_loss_init()) { set_error("head_loss_init failed"); return MINPPO_ERR_CUDA; }
+  CK(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
   done = true;
   return 0;
 }
@@ -318,10 +322,10 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
     ol.grad_bias = 0.f;
     ol.img_t = nullptr; ol.img_n = nullptr; ol.ld_t = 0; ol.ld_n = 0;
     if (lf.net == 2) {                         // log_std
-      ol.grad_src = c->head_part; ol.src_offset = c->po_logstd; ol.nparts = c->tiles64; ol.part_stride = c->head_stride;
+      ol.grad_src = c->head_part; ol.src_offset = c->po_logstd; ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
       ol.grad_bias = cfg.rank == 0 ? -static_cast<float>(cfg.ent_coef) : 0.f;
     } else if (lf.layer == L) {                // output heads
-      ol.grad_src = c->head_part; ol.nparts = c->tiles64; ol.part_stride = c->head_stride;
+      ol.grad_src = c->head_part; ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
       if (lf.is_kernel) ol.src_offset = lf.net == 0 ? c->po_w3a : c->po_w3c;
       else ol.src_offset = lf.net == 0 ? c->po_b3a : c->po_b3c;
     } else if (lf.is_kernel) {                 // hidden kernels: split-K partials of the dW GEMM
@@ -331,7 +335,7 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
       if (lf.layer >= 1) { ol.img_n = c->net[lf.net].wn[lf.layer]; ol.ld_n = H; }
     } else if (lf.layer == L - 1) {            // bias of the last hidden layer: head kernel column sums
       ol.grad_src = c->head_part; ol.src_offset = lf.net == 0 ? c->po_bh_a : c->po_bh_c;
-      ol.nparts = c->tiles64; ol.part_stride = c->head_stride;
+      ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
     } else {                                   // bias of layer l < L-1: column sums of dz[l+1]
       ol.grad_src = c->net[lf.net].colsum[lf.layer + 1]; ol.src_offset = 0; ol.nparts = c->m_tiles; ol.part_stride = H;
     }
@@ -341,7 +345,7 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
   o->P = static_cast<int>(c->P);
   o->A = c->A;
   o->gflat = c->gflat;
-  o->loss_src = c->head_part; o->loss_src_offset = c->po_loss; o->loss_nparts = c->tiles64; o->loss_part_stride = c->head_stride;
+  o->loss_src = c->head_part; o->loss_src_offset = c->po_loss; o->loss_nparts = c->head_parts; o->loss_part_stride = c->head_stride;
   o->params = u.params; o->mu = u.mu; o->nu = u.nu; o->count = u.count;
   o->block_ss = c->block_ss; o->barrier = c->barrier; o->err_flag = c->err_flag;
   o->off_logstd = static_cast<int>(c->leaves.back().offset);
@@ -370,6 +374,40 @@ static int nccl_allreduce(minppo_ctx* c, float* buf, size_t n, cudaStream_t stre
 static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t stream) {
   const int L = c->L, H = c->H;
   const int32_t* ridx = c->rowidx + static_cast<size_t>(s) * c->cap;
+  if (c->fused) {
+    // forward + heads + loss + backward-to-dZ of both nets in one launch (fused_step.cuh)
+    FusedParams p;
+    memset(&p, 0, sizeof(p));
+    for (int net = 0; net < 2; ++net) {
+      FusedNet& g = p.net[net];
+      NetBufs& nb = c->net[net];
+      g.tm_w0t = nb.m_wt[0]; g.tm_w1t = nb.m_wt[1]; g.tm_w1n = nb.m_wn[1];
+      g.tm_h1 = nb.m_act_k[1]; g.tm_dz2 = nb.m_dz_k[2]; g.tm_dz1 = nb.m_dz_k[1];
+      g.b0 = u.params + find_leaf(c, net, 0, 0).offset;
+      g.b1 = u.params + find_leaf(c, net, 1, 0).offset;
+      g.w2 = u.params + find_leaf(c, net, 2, 1).offset;
+      g.b2 = u.params + find_leaf(c, net, 2, 0).offset;
+      g.colsum = nb.colsum[1];
+      g.act = act_kind(c, net);
+      g.aout = net == 0 ? c->A : 1;
+      g.po_w2 = net == 0 ? c->po_w3a : c->po_w3c;
+      g.po_b2 = net == 0 ? c->po_b3a : c->po_b3c;
+      g.po_bh = net == 0 ? c->po_bh_a : c->po_bh_c;
+      g.po_loss = c->po_loss + (net == 0 ? 1 : 0);          // [0] = sum max(vl, vlc), [1] = sum min(l1, l2)
+    }
+    p.rowidx = ridx; p.obs_img = c->obs_img; p.count = c->counts + s;
+    p.adv_sum = c->stats + s; p.adv_sq = c->stats + c->E * c->M + s;
+    p.action = u.action; p.v_old = u.value; p.logp_old = u.log_prob; p.adv = c->adv; p.tgt = c->tgt;
+    p.log_std = u.params + c->leaves.back().offset;
+    p.part = c->head_part; p.part_stride = c->head_stride; p.po_logstd = c->po_logstd;
+    p.H = H; p.A = c->A; p.Dp = c->Dp; p.m_tiles = c->m_tiles; p.cap = c->cap;
+    p.inv_mb = static_cast<float>(1.0 / c->mb);
+    p.clip_eps = static_cast<float>(c->cfg.clip_eps); p.vf_coef = static_cast<float>(c->cfg.vf_coef);
+    PROF(PC_FWD_GEMM);
+    fused_step_kernel<<<2 * c->m_tiles, FS_THREADS, FS_SMEM_BYTES, stream>>>(p);
+    if (cudaGetLastError() != cudaSuccess) { set_error("fused_step launch failed"); return MINPPO_ERR_CUDA; }
+    c->launches++;
+  } else {
   // forward
   for (int l = 0; l < L; ++l) {
     GemmParams p;
@@ -440,6 +478,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     RET(launch_gemm<EPI_DACT>(p, 2 * c->m_tiles, stream));
     c->launches++;
   }
+  }  // !fused
   // weight gradients: dW_l = act[l]^T dz[l+1], split-K over minibatch rows
   {
     GemmParams p;
@@ -647,6 +686,8 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   c->cap = c->M_pad;                                  // row lists are padded to whole GEMM tiles
   c->m_tiles = c->M_pad / 128;
   c->tiles64 = c->M_pad / 64;
+  c->fused = !cfg->disable_fused && c->L == 2 && c->Dp <= 256 && c->A <= FS_AP;
+  c->head_parts = c->fused ? c->m_tiles : c->tiles64;
   c->P = build_layout(*cfg, &c->leaves);
   // split-K of the dW GEMMs: fill the SMs once
   {

@@ -8,7 +8,7 @@ from oracle import ppo_numpy as P
 from oracle import threefry
 
 
-def hyper_to_config(hp: P.Hyper, fast_tanh: bool = False, use_graph: bool = True, dw_splits: int = 0):
+def hyper_to_config(hp: P.Hyper, fast_tanh: bool = False, use_graph: bool = True, dw_splits: int = 0, fused: bool = True):
     from minppo_b200.config import Config
 
     c = Config()
@@ -21,6 +21,7 @@ def hyper_to_config(hp: P.Hyper, fast_tanh: bool = False, use_graph: bool = True
     c.training.update_epochs, c.training.anneal_lr = hp.update_epochs, hp.anneal_lr
     c.learner.prng_mode = "legacy" if hp.prng_mode == threefry.LEGACY else "partitionable"
     c.learner.fast_tanh, c.learner.use_graph, c.learner.dw_splits = fast_tanh, use_graph, dw_splits
+    c.learner.fused = fused
     return c
 
 

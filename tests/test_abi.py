@@ -52,7 +52,7 @@ def test_struct_layout_matches_header():
             continue
         names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
     assert names == [f[0] for f in _lib.MinppoConfig._fields_]
-    assert C.sizeof(_lib.MinppoConfig) == 4 * 4 + 8 + 11 * 4 + 4 + 12 * 8     # 4 i32, i64, 11 i32 (+4 pad), 12 f64
+    assert C.sizeof(_lib.MinppoConfig) == 4 * 4 + 8 + 12 * 4 + 12 * 8            # 4 i32, i64, 12 i32, 12 f64
 
 
 @pytest.mark.parametrize("D,A,H,L", [(225, 10, 256, 2), (37, 3, 128, 1), (256, 16, 192, 3)])

@@ -167,6 +167,23 @@ def test_update_deterministic_and_graph_equals_eager(cuda_device):
         assert np.array_equal(a[k], c[k]), k
 
 
+@pytest.mark.parametrize("name", ["c1", "medium"])
+def test_fused_step_kernel_equals_layerwise_kernels(name, cuda_device):
+    """The fused forward+loss+backward kernel (L == 2) and the layer-wise GEMM kernels share every
+    rounding point; they differ only in fp32 summation order of the head partials."""
+    case = CASES[name]
+    hp = P.Hyper(**case["hp"])
+    pr = synth.make_problem(hp, case["D"], case["A"], seed=7, done_p=0.02)
+    a = run_gpu_update(hp, pr, cuda_device, fused=True)
+    b = run_gpu_update(hp, pr, cuda_device, fused=False)
+    assert a["launches"] < b["launches"]
+    assert rel_err(a["losses"], b["losses"]) < 2e-4
+    assert rel_err(a["grad"][:-4], b["grad"][:-4]) < 2e-3
+    lr = hp.opt_lr if not hp.anneal_lr else hp.training_lr
+    nsteps = hp.update_epochs * hp.num_minibatches
+    assert np.abs(a["params"] - b["params"]).max() < lr * (0.5 + 0.05 * nsteps)
+
+
 def test_update_resumes_from_optimizer_state(cuda_device):
     """Second update starting from non-zero mu/nu/count (what RunnerState carries across
     _update_step calls, train.py:276-281) matches the oracle continuing from the same state."""
