@@ -420,7 +420,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--fast-tanh", type=int, default=0)
+    ap.add_argument("--fast-tanh", type=int, default=1, help="library default (config.learner.fast_tanh)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

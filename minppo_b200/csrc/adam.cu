@@ -17,7 +17,7 @@
 namespace minppo {
 
 constexpr int OPT_THREADS = 1024;
-constexpr int OPT_EPT = 8;                    // elements per thread per sweep (registers)
+constexpr int OPT_EPT = 8;                    // max elements per thread (registers)
 
 MINPPO_DEVINL float block_sum(float v, float* scratch /*[32]*/) {
   v = warp_sum(v);
@@ -71,13 +71,17 @@ MINPPO_DEVINL int find_leaf_idx(const OptArgs& a, int i) {
   return l;
 }
 
+// EPT elements per thread, kept in registers across the grid barrier.  Elements are dealt to
+// warps in 32-element chunks, round-robin over BLOCKS (chunk = k*G*32 + warp*G + block), so that
+// the few leaves with many partials (output heads) are spread over the whole grid while every
+// warp still reads 128 contiguous bytes per partial.
+template <int EPT>
 __global__ void __launch_bounds__(OPT_THREADS, 1) opt_kernel(const OptArgs a) {
   __shared__ float scratch[32];
-  __shared__ float s_bcast[2];
+  __shared__ float s_bcast[4];
   const int P = a.P;
-  const int gtid = blockIdx.x * OPT_THREADS + threadIdx.x;
-  const int gthreads = gridDim.x * OPT_THREADS;
-  const int sweep = gthreads * OPT_EPT;
+  const int G = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int count = a.do_apply ? *a.count : 0;             // Adam step count BEFORE this step
   float ent = a.entropy_const;                             // A * (0.5 + 0.5 log 2pi) + sum log|scale|
@@ -86,46 +90,40 @@ __global__ void __launch_bounds__(OPT_THREADS, 1) opt_kernel(const OptArgs a) {
     for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(a.params[a.off_logstd + j])));
   }
 
-  // P <= sweep in every supported shape except very large nets; loop over sweeps for generality.
-  // Within a sweep every thread owns OPT_EPT elements kept in registers across the grid barrier.
-  for (int base = 0; base < P + 2; base += sweep) {
-    float g[OPT_EPT], pv[OPT_EPT], mv[OPT_EPT], nv[OPT_EPT];
-    float ss = 0.f;
+  float g[EPT], pv[EPT], mv[EPT], nv[EPT];
+  float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < OPT_EPT; ++k) {
-      const int i = base + k * gthreads + gtid;
-      g[k] = 0.f; pv[k] = 0.f; mv[k] = 0.f; nv[k] = 0.f;
-      if (i < P) {
-        if (a.do_reduce) {
-          const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
-          g[k] = sum_partials(L.grad_src + L.src_offset + (i - L.offset), L.nparts, L.part_stride) + L.grad_bias;
-          if (!a.do_apply || a.keep_gflat) a.gflat[i] = g[k];
-        } else {
-          g[k] = a.gflat[i];
-        }
-        if (a.do_apply) {                                  // prefetch the optimizer state before the barrier
-          pv[k] = a.params[i]; mv[k] = a.mu[i]; nv[k] = a.nu[i];
-          ss = fmaf(g[k], g[k], ss);
-        }
-      } else if (i < P + 2 && a.do_reduce) {
-        a.gflat[i] = sum_partials(a.loss_src + a.loss_src_offset + (i - P), a.loss_nparts, a.loss_part_stride);
+  for (int k = 0; k < EPT; ++k) {
+    const int i = ((k * 32 + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
+    g[k] = 0.f; pv[k] = 0.f; mv[k] = 0.f; nv[k] = 0.f;
+    if (i < P) {
+      if (a.do_reduce) {
+        const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
+        g[k] = sum_partials(L.grad_src + L.src_offset + (i - L.offset), L.nparts, L.part_stride) + L.grad_bias;
+        if (!a.do_apply || a.keep_gflat) a.gflat[i] = g[k];
+      } else {
+        g[k] = a.gflat[i];
       }
+      if (a.do_apply) {                                    // prefetch the optimizer state before the barrier
+        pv[k] = a.params[i]; mv[k] = a.mu[i]; nv[k] = a.nu[i];
+        ss = fmaf(g[k], g[k], ss);
+      }
+    } else if (i < P + 2 && a.do_reduce) {
+      a.gflat[i] = sum_partials(a.loss_src + a.loss_src_offset + (i - P), a.loss_nparts, a.loss_part_stride);
     }
-    if (!a.do_apply) continue;
-    // NOTE: with P > sweep the global norm needs all sweeps first; handled by the host (opt_launch
-    // sizes the grid so that P + 2 <= sweep, or falls back to two launches).
-    const float bs = block_sum(ss, scratch);
-    if (threadIdx.x == 0) a.block_ss[blockIdx.x] = bs;
-    grid_barrier(a.barrier, a.err_flag);
-    if (threadIdx.x < 32) {
-      float s = 0.f;
-      for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(a.block_ss + b);
-      s = warp_sum(s);
-      if (threadIdx.x == 0) s_bcast[0] = sqrtf(s);
-    }
-    __syncthreads();
-    const float gnorm = s_bcast[0];
-    const bool trigger = gnorm < a.max_norm;               // optax.clip_by_global_norm
+  }
+  if (!a.do_apply) return;
+
+  const float bs = block_sum(ss, scratch);
+  if (threadIdx.x == 0) a.block_ss[blockIdx.x] = bs;
+  grid_barrier(a.barrier, a.err_flag);
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+    for (int b = threadIdx.x; b < G; b += 32) s += __ldcg(a.block_ss + b);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) s_bcast[0] = sqrtf(s);
+  }
+  if (threadIdx.x == 32) {                                 // per-step scalars, once per block
     float lr;                                              // train.py:98-101 (annealed) or opt.lr
     if (a.anneal) {
       const float frac = 1.0f - static_cast<float>(count / a.anneal_div) / static_cast<float>(a.num_updates);
@@ -134,42 +132,47 @@ __global__ void __launch_bounds__(OPT_THREADS, 1) opt_kernel(const OptArgs a) {
       lr = a.lr;
     }
     const float cnt1 = static_cast<float>(count + 1);
-    const float c1 = 1.0f - powf(a.b1, cnt1);
-    const float c2 = 1.0f - powf(a.b2, cnt1);
+    s_bcast[1] = lr;
+    s_bcast[2] = 1.0f - powf(a.b1, cnt1);
+    s_bcast[3] = 1.0f - powf(a.b2, cnt1);
+  }
+  __syncthreads();
+  const float gnorm = s_bcast[0];
+  const bool trigger = gnorm < a.max_norm;                 // optax.clip_by_global_norm
+  const float lr = s_bcast[1], c1 = s_bcast[2], c2 = s_bcast[3];
 #pragma unroll
-    for (int k = 0; k < OPT_EPT; ++k) {
-      const int i = base + k * gthreads + gtid;
-      if (i >= P) continue;
-      float gg = g[k];
-      if (!trigger) gg = (gg / gnorm) * a.max_norm;
-      const float mu = a.one_minus_b1 * gg + a.b1 * mv[k];
-      const float nu = a.one_minus_b2 * (gg * gg) + a.b2 * nv[k];
-      const float u = (mu / c1) / (sqrtf(nu / c2 + a.eps_root) + a.eps);
-      const float p = pv[k] + (-lr) * u;
-      a.params[i] = p;
-      a.mu[i] = mu;
-      a.nu[i] = nu;
-      const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
-      if (L.img_t || L.img_n) {
-        const int e = i - L.offset;
-        const int r = e / L.cols, c = e % L.cols;          // kernel [in=r][out=c]
-        const __nv_bfloat16 b = __float2bfloat16_rn(p);
-        if (L.img_t) L.img_t[static_cast<size_t>(c) * L.ld_t + r] = b;
-        if (L.img_n) L.img_n[static_cast<size_t>(r) * L.ld_n + c] = b;
-      }
+  for (int k = 0; k < EPT; ++k) {
+    const int i = ((k * 32 + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
+    if (i >= P) continue;
+    float gg = g[k];
+    if (!trigger) gg = (gg / gnorm) * a.max_norm;
+    const float mu = a.one_minus_b1 * gg + a.b1 * mv[k];
+    const float nu = a.one_minus_b2 * (gg * gg) + a.b2 * nv[k];
+    const float u = (mu / c1) / (sqrtf(nu / c2 + a.eps_root) + a.eps);
+    const float p = pv[k] + (-lr) * u;
+    a.params[i] = p;
+    a.mu[i] = mu;
+    a.nu[i] = nu;
+    const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
+    if (L.img_t || L.img_n) {
+      const int e = i - L.offset;
+      const int r = e / L.cols, c = e % L.cols;            // kernel [in=r][out=c]
+      const __nv_bfloat16 b = __float2bfloat16_rn(p);
+      if (L.img_t) L.img_t[static_cast<size_t>(c) * L.ld_t + r] = b;
+      if (L.img_n) L.img_n[static_cast<size_t>(r) * L.ld_n + c] = b;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      *a.count = count + 1;
-      if (a.losses_out) {
-        // gflat[P] = sum max(vl, vlc), gflat[P+1] = sum min(l1, l2) over the global minibatch
-        const float value_loss = 0.5f * __ldcg(a.gflat + P) * a.inv_mb;
-        const float actor_loss = -__ldcg(a.gflat + P + 1) * a.inv_mb;
-        a.losses_out[0] = actor_loss + a.vf_coef * value_loss - a.ent_coef * ent;
-        a.losses_out[1] = value_loss;
-        a.losses_out[2] = actor_loss;
-        a.losses_out[3] = ent;
-        if (a.gnorm_out) *a.gnorm_out = gnorm;
-      }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *a.count = count + 1;
+    if (a.losses_out) {
+      // gflat[P] = sum max(vl, vlc), gflat[P+1] = sum min(l1, l2) over the global minibatch
+      const float value_loss = 0.5f * __ldcg(a.gflat + P) * a.inv_mb;
+      const float actor_loss = -__ldcg(a.gflat + P + 1) * a.inv_mb;
+      a.losses_out[0] = actor_loss + a.vf_coef * value_loss - a.ent_coef * ent;
+      a.losses_out[1] = value_loss;
+      a.losses_out[2] = actor_loss;
+      a.losses_out[3] = ent;
+      if (a.gnorm_out) *a.gnorm_out = gnorm;
     }
   }
 }
@@ -211,8 +214,12 @@ __global__ void weight_images_kernel(const OptArgs a) {
 int opt_max_params(int blocks) { return blocks * OPT_THREADS * OPT_EPT - 2; }
 
 int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream) {
-  if (a.do_apply && a.P > opt_max_params(blocks)) return MINPPO_ERR_UNSUPPORTED;   // single-sweep global norm
-  opt_kernel<<<blocks, OPT_THREADS, 0, stream>>>(a);
+  if (a.P > opt_max_params(blocks)) return MINPPO_ERR_UNSUPPORTED;   // single sweep: global norm needs all elements
+  const long long per_thread = (static_cast<long long>(a.P) + 2 + static_cast<long long>(blocks) * OPT_THREADS - 1) /
+                               (static_cast<long long>(blocks) * OPT_THREADS);
+  if (per_thread <= 2) opt_kernel<2><<<blocks, OPT_THREADS, 0, stream>>>(a);
+  else if (per_thread <= 4) opt_kernel<4><<<blocks, OPT_THREADS, 0, stream>>>(a);
+  else opt_kernel<OPT_EPT><<<blocks, OPT_THREADS, 0, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }
 

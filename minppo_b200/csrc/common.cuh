@@ -106,6 +106,32 @@ MINPPO_DEVINL void tma_load_2d(uint32_t smem_dst, const CUtensorMap* m, uint64_t
       : "memory");
 }
 
+// TMA stores: shared -> global, bulk-group completion
+MINPPO_DEVINL void tma_store_2d(uint32_t smem_src, const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+MINPPO_DEVINL void tma_store_3d(uint32_t smem_src, const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+MINPPO_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+MINPPO_DEVINL void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+MINPPO_DEVINL void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+MINPPO_DEVINL void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+MINPPO_DEVINL uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 // ------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, loads, fences
 // ------------------------------------------------------------------------------------
@@ -193,9 +219,12 @@ MINPPO_DEVINL float fast_tanh(float x) {            // MUFU.TANH, |rel err| ~ 2^
 }
 // tanh through ex2/rcp (2 MUFU): abs err ~1e-7, well below one bf16 ulp of the stored output
 MINPPO_DEVINL float exp_tanh(float x) {
-  float xc = fminf(fmaxf(x, -15.f), 15.f);
-  float e = exp2f(xc * 2.8853900817779268f);        // exp(2x)
-  return 1.f - __fdividef(2.f, e + 1.f);
+  // 1 - 2 / (1 + exp(2x)): ex2.approx saturates to +inf / 0, rcp.approx(+inf) = 0, so the
+  // limits +-1 come out without clamping.  5 instructions, 2 of them MUFU.
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
 }
 
 MINPPO_DEVINL uint32_t pack_bf16x2(float lo, float hi) {

@@ -77,26 +77,8 @@ struct alignas(64) FusedParams {
   float inv_mb, clip_eps, vf_coef;
 };
 
-MINPPO_DEVINL void tma_store_2d(uint32_t smem_src, const CUtensorMap* m, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_src), "r"(c0), "r"(c1)
-               : "memory");
-}
-MINPPO_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-MINPPO_DEVINL void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-MINPPO_DEVINL void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 MINPPO_DEVINL void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-MINPPO_DEVINL uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-MINPPO_DEVINL void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 MINPPO_DEVINL uint32_t lds_u16(uint32_t addr) {
   uint16_t v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
@@ -109,9 +91,10 @@ MINPPO_DEVINL void sts_u16(uint32_t addr, uint32_t v) {
 MINPPO_DEVINL uint32_t sw_off(int r, int c) {
   return static_cast<uint32_t>((c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4));
 }
-MINPPO_DEVINL float act_apply(float x, int act) {
-  if (act == ACT_RELU) return fmaxf(x, 0.f);
-  if (act == ACT_TANH_FAST) return fast_tanh(x);
+template <int ACT>
+MINPPO_DEVINL float act_apply(float x) {
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == ACT_TANH_FAST) return fast_tanh(x);
   return exp_tanh(x);
 }
 MINPPO_DEVINL float act_deriv(float h, int act) { return act == ACT_RELU ? (h > 0.f ? 1.f : 0.f) : (1.f - h * h); }
@@ -120,26 +103,40 @@ MINPPO_DEVINL float dclip_f(float x, float lo, float hi) {
 }
 
 // accumulator (32 columns per chunk) -> +bias, activation, bf16 -> swizzled smem tile
-MINPPO_DEVINL void epilogue_act(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int act, int row, int q,
-                                int col0, int ncols) {
+template <int ACT>
+MINPPO_DEVINL void epilogue_act_t(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int row, int q, int col0,
+                                  int ncols) {
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
   for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
     float v[32];
     tmem_ld_32x32(taddr + c0, v);
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);     // broadcast LDS.128
+    float4 bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bb[j] = b4[j];
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t w[4];
+      const float bj[8] = {bb[2 * j].x, bb[2 * j].y, bb[2 * j].z, bb[2 * j].w,
+                           bb[2 * j + 1].x, bb[2 * j + 1].y, bb[2 * j + 1].z, bb[2 * j + 1].w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int e = 8 * j + 2 * t;
-        const float x0 = act_apply(v[e] + bias_s[c0 + e], act);
-        const float x1 = act_apply(v[e + 1] + bias_s[c0 + e + 1], act);
+        const float x0 = act_apply<ACT>(v[e] + bj[2 * t]);
+        const float x1 = act_apply<ACT>(v[e + 1] + bj[2 * t + 1]);
         w[t] = pack_bf16x2(x0, x1);
       }
       sts128(dst_base + sw_off(row, c0 + 8 * j), make_uint4(w[0], w[1], w[2], w[3]));
     }
   }
+}
+
+MINPPO_DEVINL void epilogue_act(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int act, int row, int q,
+                                int col0, int ncols) {
+  if (act == ACT_RELU) epilogue_act_t<ACT_RELU>(tmem_acc, dst_base, bias_s, row, q, col0, ncols);
+  else if (act == ACT_TANH_FAST) epilogue_act_t<ACT_TANH_FAST>(tmem_acc, dst_base, bias_s, row, q, col0, ncols);
+  else epilogue_act_t<ACT_TANH>(tmem_acc, dst_base, bias_s, row, q, col0, ncols);
 }
 
 __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_constant__ FusedParams p) {

@@ -85,6 +85,21 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t 
   return 0;
 }
 
+// fp32 3-D tensor [d2][d1][d0] (d0 contiguous), box {32, 128, 1}, 128B swizzle: split-K partial stores
+static int make_tmap_f32_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MINPPO_ERR_CUDA; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (f32 3d) failed (%d)", static_cast<int>(r)); return MINPPO_ERR_CUDA; }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // NCCL, loaded lazily so that single-GPU use never needs the library
 // ------------------------------------------------------------------------------------------
@@ -189,7 +204,7 @@ struct NetBufs {
   std::vector<__nv_bfloat16*> wn;      // wn[l],  l = 1..L-1 [H][H]      (kernel as stored)
   std::vector<float*> dw_part;         // dw_part[l], l = 0..L-1 [S][in_l][H]
   std::vector<float*> colsum;          // colsum[l],  l = 1..L-1 [m_tiles][H]  -> bias grad of layer l-1
-  std::vector<CUtensorMap> m_act_k, m_act_mn, m_dz_k, m_dz_mn, m_wt, m_wn;
+  std::vector<CUtensorMap> m_act_k, m_act_mn, m_dz_k, m_dz_mn, m_wt, m_wn, m_dw;
 };
 
 struct UpdatePtrs {
@@ -495,7 +510,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
         else { g.amode = A_TMA_MN; g.tmA = nb.m_act_mn[l]; }
         g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
         g.kb_total = c->M_pad / 64;
-        g.out = nb.dw_part[l];
+        g.tmC = nb.m_dw[l];
         g.N = H; g.m_tiles = (in_pad + 127) / 128; g.splits = c->S; g.m_store = in_l;
         cta += g.m_tiles * g.splits;
       }
@@ -741,7 +756,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     nb.act.assign(L + 1, nullptr); nb.dz.assign(L + 1, nullptr); nb.wt.assign(L, nullptr); nb.wn.assign(L, nullptr);
     nb.dw_part.assign(L, nullptr); nb.colsum.assign(L, nullptr);
     nb.m_act_k.resize(L + 1); nb.m_act_mn.resize(L + 1); nb.m_dz_k.resize(L + 1); nb.m_dz_mn.resize(L + 1);
-    nb.m_wt.resize(L); nb.m_wn.resize(L);
+    nb.m_wt.resize(L); nb.m_wn.resize(L); nb.m_dw.resize(L);
     for (int l = 1; l <= L; ++l) {
       ALLOC(nb.act[l], static_cast<size_t>(c->M_pad) * H);
       ALLOC(nb.dz[l], static_cast<size_t>(c->M_pad) * H);
@@ -761,6 +776,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
         ALLOC(nb.colsum[l], static_cast<size_t>(c->m_tiles) * H);
       }
       ALLOC(nb.dw_part[l], static_cast<size_t>(c->S) * in_l * H);
+      if ((rc = make_tmap_f32_3d(&nb.m_dw[l], nb.dw_part[l], H, in_l, c->S))) return fail(rc);
     }
   }
 #undef ALLOC
@@ -892,7 +908,8 @@ int minppo_debug_gemm(int32_t mode, const void* a_bf16, const void* b_bf16, cons
   memset(&p, 0, sizeof(p));
   p.ngroups = 1;
   GemmGroup& g = p.g[0];
-  g.cta_begin = 0; g.N = N; g.m_tiles = M / 128; g.splits = splits; g.kb_total = K / 64; g.m_store = M; g.out = cmat;
+  g.cta_begin = 0; g.N = N; g.m_tiles = M / 128; g.splits = splits; g.kb_total = K / 64; g.m_store = M;
+  RET(make_tmap_f32_3d(&g.tmC, cmat, N, M, splits));
   switch (mode) {
     case 0:
       g.amode = A_TMA_K; g.bmode = B_TMA_K;

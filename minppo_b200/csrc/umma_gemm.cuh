@@ -30,7 +30,7 @@ constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_EPI_THREADS = 128;
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 4 * GEMM_MAXN * 4 /*colsum*/ + 256;
-constexpr int GEMM_MAX_GROUPS = 8;
+constexpr int GEMM_MAX_GROUPS = 6;
 
 enum : int { A_TMA_K = 0, A_GATHER_K = 1, A_TMA_MN = 2, A_GATHER_MN = 3 };
 enum : int { B_TMA_K = 0, B_TMA_MN = 2 };
@@ -40,9 +40,10 @@ enum : int { ACT_TANH = 0, ACT_RELU = 1, ACT_TANH_FAST = 2 };
 struct alignas(64) GemmGroup {
   CUtensorMap tmA;                 // A_TMA_*
   CUtensorMap tmB;                 // B_TMA_*
+  CUtensorMap tmC;                 // EPI_PARTIAL: fp32 [splits][m_store][N] store map, box {32, 128, 1}
   const int32_t* rowidx;           // A_GATHER_*: flat row index per minibatch row (all entries valid)
   const __nv_bfloat16* gimage;     // A_GATHER_*: bf16 image [rows][ldg]
-  void* out;                       // EPI_ACT/EPI_DACT: bf16 [M][ldo]; EPI_PARTIAL: fp32 [splits][m_store][N]
+  void* out;                       // EPI_ACT/EPI_DACT: bf16 [M][ldo]
   const float* bias;               // EPI_ACT: fp32 [N]
   const __nv_bfloat16* hprev;      // EPI_DACT: layer output h (for f'(z) from h), bf16 [M][ldh]
   float* colsum;                   // EPI_DACT: fp32 [m_tiles][N] per-tile column sums (bias grads)
@@ -192,34 +193,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
     // ===================== gather producer (optional) + epilogue =====================
     const int et = threadIdx.x - 64;         // 0..127
     if (kGather) {
+      // Row indices are prefetched 8 k-blocks at a time (one dependent global load per batch, not
+      // per k-block) and up to GEMM_STAGES - 1 cp.async groups stay in flight before publishing.
       const int32_t* ridx = G.rowidx;
-      int pending = -1;                      // stage index of the group committed but not yet published
+      constexpr int LAG = GEMM_STAGES - 1;
+      const int c = et >> 6, kr = et & 63;
+      const int row_k = (AMODE == A_GATHER_K) ? ridx[m_tile * GEMM_BM + et] : 0;
+      int rows[8];
       for (int i = 0; i < nkb; ++i) {
+        if ((i & 7) == 0 && AMODE == A_GATHER_MN) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) rows[u] = (i + u < nkb) ? ridx[(kb0 + i + u) * GEMM_BK + kr] : 0;
+        }
         const int s = i % GEMM_STAGES;
         const uint32_t ph = (i / GEMM_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t sa = base + s * GEMM_STAGE_BYTES;
         const int kb = kb0 + i;
         if (AMODE == A_GATHER_K) {
-          const int row = ridx[m_tile * GEMM_BM + et];
-          gather_line(sa, et, G.gimage + static_cast<size_t>(row) * G.ldg + kb * GEMM_BK);
+          gather_line(sa, et, G.gimage + static_cast<size_t>(row_k) * G.ldg + kb * GEMM_BK);
         } else {
-          const int c = et >> 6, kr = et & 63;
-          const int row = ridx[kb * GEMM_BK + kr];
+          int row = rows[0];
+#pragma unroll
+          for (int u = 1; u < 8; ++u) row = ((i & 7) == u) ? rows[u] : row;
           gather_line(sa + c * 8192, kr, G.gimage + static_cast<size_t>(row) * G.ldg + m_tile * GEMM_BM + c * 64);
         }
         cp_async_commit();
-        if (pending >= 0) {
-          cp_async_wait<1>();
+        if (i >= LAG) {
+          cp_async_wait<LAG>();
           fence_proxy_async_smem();
-          mbar_arrive(&full_bar[pending]);
+          mbar_arrive(&full_bar[(i - LAG) % GEMM_STAGES]);
         }
-        pending = s;
       }
-      if (pending >= 0) {
-        cp_async_wait<0>();
+      for (int j = max(0, nkb - LAG); j < nkb; ++j) {          // drain: publish the last groups in order
+        const int left = nkb - 1 - j;                          // groups that may still be in flight
+        if (left >= 2) cp_async_wait<2>();
+        else if (left == 1) cp_async_wait<1>();
+        else cp_async_wait<0>();
         fence_proxy_async_smem();
-        mbar_arrive(&full_bar[pending]);
+        mbar_arrive(&full_bar[j % GEMM_STAGES]);
       }
     }
 
@@ -285,13 +297,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         for (int j = 0; j < 4; ++j) o[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         const float cs = warp_colsum32(v);
         colsum_s[q * GEMM_MAXN + c0 + lane_id()] = cs;
-      } else {  // EPI_PARTIAL
-        if (row < G.m_store) {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(G.out) +
-                                                (static_cast<size_t>(split) * G.m_store + row) * N + c0);
+      } else {  // EPI_PARTIAL: stage the fp32 tile in the (now idle) operand ring, SW128, then TMA-store it
+        const int r = q * 32 + static_cast<int>(lane_id());
+        const uint32_t dst = base + (c0 >> 5) * 16384 + r * 128;      // chunk tile: [128 rows][32 floats]
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
+        for (int j = 0; j < 8; ++j)
+          sts128(dst + ((j ^ (r & 7)) << 4),
+                 make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                            __float_as_uint(v[4 * j + 3])));
+      }
+    }
+    if (EPI == EPI_PARTIAL) {
+      // tmC: fp32 [splits][m_store][N], box {32, 128, 1}: rows >= m_store are clipped by the TMA unit
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        for (int c0 = 0; c0 < N; c0 += 32) tma_store_3d(base + (c0 >> 5) * 16384, &G.tmC, c0, m_tile * GEMM_BM, split);
+        tma_store_commit();
+        tma_store_wait_all0();
       }
     }
     if (EPI == EPI_DACT) {

@@ -8,7 +8,7 @@ from oracle import ppo_numpy as P
 from oracle import threefry
 
 
-def hyper_to_config(hp: P.Hyper, fast_tanh: bool = False, use_graph: bool = True, dw_splits: int = 0, fused: bool = True):
+def hyper_to_config(hp: P.Hyper, fast_tanh: bool = True, use_graph: bool = True, dw_splits: int = 0, fused: bool = True):
     from minppo_b200.config import Config
 
     c = Config()
