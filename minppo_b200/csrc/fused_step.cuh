@@ -2,21 +2,25 @@
 // (the reference's default model.num_layers = 2, /root/reference/minppo/config.py:53).
 //
 // One CTA = one 128-row tile of the minibatch x one net (actor or critic).  Everything between
-// the gathered observation rows and the layer gradients dZ stays on chip:
+// the gathered observation rows and the layer gradients dZ stays on chip; every contraction runs
+// on the tcgen05 tensor cores with accumulators in TMEM:
 //
-//   gather X (cp.async by row index, SW128)          -> smem R1
-//   L1: acc0 = X  W0^T   (tcgen05, B streamed by TMA)  -> epilogue: +b0, act, bf16 -> smem R0 (H1) -> TMA store
-//   L2: acc1 = H1 W1^T                                  -> epilogue: +b1, act, bf16 -> smem R1 (H2)
-//   head (fp32 SIMT): out = H2 W2 + b2; Gaussian log-prob / clipped surrogate (actor CTA) or
-//        clipped value loss (critic CTA) -> g = dL/dout  (train.py:218-243)
-//   dZ2 = (g W2^T) * f'(H2) in place in R1 -> TMA store; dW2 / db2 / db1 / dlog_std / loss partials
-//   dH1: acc0 = dZ2 W1     (tcgen05)                    -> epilogue: * f'(H1), bf16 -> smem R1 (dZ1) -> TMA store
+//   gather X (cp.async by row index, SW128)               -> smem R1
+//   L1   acc0 = X  W0^T  (B streamed by TMA)              -> +b0, act, bf16 -> R0 (H1) -> TMA store
+//   L2   acc1 = H1 W1^T                                   -> +b1, act, bf16 -> R1 (H2)
+//   head out  = H2 W2    (N = 16)                         -> +b2 -> Gaussian log-prob / clipped
+//        surrogate (actor CTA) or clipped value loss (critic CTA), train.py:218-243 -> g = dL/dout
+//   bwd  dA2  = g W2^T   (K = 16),  dW2 = H2^T g (N = 16) -> dZ2 = dA2 * f'(H2) in place -> TMA store
+//   dH1  acc0 = dZ2 W1                                    -> * f'(H1), bf16 -> R1 (dZ1) -> TMA store
+//
+// The output-head operands W2 and g are fp32 quantities: they enter the tensor cores as a bf16
+// hi/lo pair (x = hi + lo to 2^-17), the cross terms hi*hi + hi*lo + lo*hi are accumulated in
+// fp32, so the heads keep fp32-level accuracy while costing a few dozen tiny UMMAs.
 //
 // Warp roles: warp 0 TMA producer (weight k-blocks through a 2-stage ring), warp 1 TMEM
-// allocator + MMA issuer, warps 2..9 workers (gather, epilogues, SIMT head), 2 warps per TMEM
-// lane quadrant so that every scheduler has two epilogue warps in flight.
-// H1, dZ2 and dZ1 are also written to HBM (bf16) because the split-K weight-gradient GEMM
-// (umma_gemm.cuh, EPI_PARTIAL) runs as its own launch over all tiles.
+// allocator + MMA issuer, warps 2..9 workers (gather, epilogues, loss), two per TMEM lane
+// quadrant.  H1, dZ2 and dZ1 are also written to HBM (bf16, TMA stores) for the split-K
+// weight-gradient GEMM (umma_gemm.cuh, EPI_PARTIAL), which runs as its own launch over all tiles.
 #pragma once
 
 #include "common.cuh"
@@ -28,18 +32,18 @@ namespace minppo {
 constexpr int FS_THREADS = 320;
 constexpr int FS_WORKERS = 256;
 constexpr int FS_AP = 16;                               // padded head width (A <= 16)
-constexpr int FS_R0 = 0;                                // H1            64 KB
+constexpr int FS_R0 = 0;                                // H1                  64 KB
 constexpr int FS_R1 = 65536;                            // X / H2 / dZ2 / dZ1  64 KB
 constexpr int FS_RB = 131072;                           // weight ring   2 x 32 KB
 constexpr int FS_BSTAGE = 32768;
-constexpr int FS_MISC = 196608;
-constexpr int FS_W2S = FS_MISC;                         // [256][16] f32
-constexpr int FS_BIAS = FS_W2S + 256 * FS_AP * 4;       // [2][256] f32
-constexpr int FS_GS = FS_BIAS + 2 * 256 * 4;            // [128][16] f32
-constexpr int FS_CS = FS_GS + 128 * FS_AP * 4;          // [4][256] f32
-constexpr int FS_RED = FS_CS + 4 * 256 * 4;             // [8][24] f32
-constexpr int FS_BARS = FS_RED + 8 * 24 * 4;            // mbarriers + tmem slot
-constexpr int FS_SMEM_BYTES = FS_BARS + 128 + 1024;     // + alignment slack
+constexpr int FS_W2T = 196608;                          // head kernel^T bf16 [16][H] SW128: hi (+0), lo (+8192)
+constexpr int FS_GT = FS_W2T + 16384;                   // g^T bf16 [16][128] SW128: hi (+0), lo (+4096)
+constexpr int FS_BIAS = FS_GT + 8192;                   // [2][256] f32
+constexpr int FS_HB = FS_BIAS + 2048;                   // head bias [16], log_std [16] f32
+constexpr int FS_CS = FS_HB + 128;                      // [4][256] f32 column-sum scratch
+constexpr int FS_RED = FS_CS + 4096;                    // [8][40] f32
+constexpr int FS_BARS = FS_RED + 8 * 40 * 4;            // mbarriers + tmem slot
+constexpr int FS_SMEM_BYTES = FS_BARS + 256 + 1024;     // + alignment slack
 
 struct alignas(64) FusedNet {
   CUtensorMap tm_w0t;            // W0^T image [H][Dp]   box {64, H}
@@ -75,21 +79,34 @@ struct alignas(64) FusedParams {
   int part_stride, po_logstd;
   int H, A, Dp, m_tiles, cap;
   float inv_mb, clip_eps, vf_coef;
+  long long* trace;              // debug: [ctas][32] clock64 stamps (null = off)
 };
+
+#define FS_STAMP(slot) do { if (p.trace) p.trace[static_cast<size_t>(blockIdx.x) * 32 + (slot)] = clock64(); } while (0)
 
 MINPPO_DEVINL void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-MINPPO_DEVINL uint32_t lds_u16(uint32_t addr) {
-  uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-  return v;
-}
 MINPPO_DEVINL void sts_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<uint16_t>(v)) : "memory");
+}
+// TMEM -> registers: 32 lanes x 16 consecutive fp32 columns
+MINPPO_DEVINL void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 // byte offset of the 16-byte chunk holding column c of row r inside a [128][H] bf16 SW128 tile set
 MINPPO_DEVINL uint32_t sw_off(int r, int c) {
   return static_cast<uint32_t>((c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4));
+}
+// byte offset of element (j, c) inside a [16][ncols] bf16 SW128 tile set (2 KB per 64 columns)
+MINPPO_DEVINL uint32_t sw16_off(int j, int c) {
+  return static_cast<uint32_t>((c >> 6) * 2048 + j * 128 + ((((c & 63) >> 3) ^ (j & 7)) << 4) + (c & 7) * 2);
 }
 template <int ACT>
 MINPPO_DEVINL float act_apply(float x) {
@@ -97,9 +114,17 @@ MINPPO_DEVINL float act_apply(float x) {
   if (ACT == ACT_TANH_FAST) return fast_tanh(x);
   return exp_tanh(x);
 }
-MINPPO_DEVINL float act_deriv(float h, int act) { return act == ACT_RELU ? (h > 0.f ? 1.f : 0.f) : (1.f - h * h); }
+template <int ACT>
+MINPPO_DEVINL float act_deriv_t(float h) { return ACT == ACT_RELU ? (h > 0.f ? 1.f : 0.f) : (1.f - h * h); }
 MINPPO_DEVINL float dclip_f(float x, float lo, float hi) {
   return (x > lo && x < hi) ? 1.f : ((x == lo || x == hi) ? 0.5f : 0.f);
+}
+// x = hi + lo with hi, lo bf16 (relative error 2^-17)
+MINPPO_DEVINL void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
 }
 
 // accumulator (32 columns per chunk) -> +bias, activation, bf16 -> swizzled smem tile
@@ -131,7 +156,6 @@ MINPPO_DEVINL void epilogue_act_t(uint32_t tmem_acc, uint32_t dst_base, const fl
     }
   }
 }
-
 MINPPO_DEVINL void epilogue_act(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int act, int row, int q,
                                 int col0, int ncols) {
   if (act == ACT_RELU) epilogue_act_t<ACT_RELU>(tmem_acc, dst_base, bias_s, row, q, col0, ncols);
@@ -139,24 +163,67 @@ MINPPO_DEVINL void epilogue_act(uint32_t tmem_acc, uint32_t dst_base, const floa
   else epilogue_act_t<ACT_TANH>(tmem_acc, dst_base, bias_s, row, q, col0, ncols);
 }
 
+// dZ = acc * f'(h): h read from `h_base`, bf16 result written to `dst_base` (may alias h_base:
+// every thread touches only its own 16-byte chunks); column sums of the stored values -> cs.
+template <int ACT>
+MINPPO_DEVINL void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, float* cs, int row, int q,
+                                   int col0, int ncols) {
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+  const int lane = static_cast<int>(lane_id());
+  for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
+    float v[32];
+    tmem_ld_32x32(taddr + c0, v);
+    uint4 hh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hh[j] = lds128(h_base + sw_off(row, c0 + 8 * j));
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t hw[4] = {hh[j].x, hh[j].y, hh[j].z, hh[j].w};
+      uint32_t w[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int e = 8 * j + 2 * t;
+        v[e] *= act_deriv_t<ACT>(bf16_lo(hw[t]));
+        v[e + 1] *= act_deriv_t<ACT>(bf16_hi(hw[t]));
+        w[t] = pack_bf16x2(v[e], v[e + 1]);
+        v[e] = bf16_lo(w[t]); v[e + 1] = bf16_hi(w[t]);          // bias gradient sums the stored (rounded) dZ
+      }
+      sts128(dst_base + sw_off(row, c0 + 8 * j), make_uint4(w[0], w[1], w[2], w[3]));
+    }
+    const float csum = warp_colsum32(v);
+    cs[q * 256 + c0 + lane] = csum;
+  }
+}
+MINPPO_DEVINL void epilogue_dact(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, float* cs, int act, int row,
+                                 int q, int col0, int ncols) {
+  if (act == ACT_RELU) epilogue_dact_t<ACT_RELU>(tmem_acc, h_base, dst_base, cs, row, q, col0, ncols);
+  else epilogue_dact_t<ACT_TANH>(tmem_acc, h_base, dst_base, cs, row, q, col0, ncols);
+}
+
 __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  float* w2s = reinterpret_cast<float*>(sm + FS_W2S);
   float* bias_s = reinterpret_cast<float*>(sm + FS_BIAS);       // [0..256) layer 0, [256..512) layer 1
-  float* gs = reinterpret_cast<float*>(sm + FS_GS);
+  float* hb = reinterpret_cast<float*>(sm + FS_HB);             // [0..16) head bias, [16..32) log_std
   float* cs = reinterpret_cast<float*>(sm + FS_CS);
   float* red = reinterpret_cast<float*>(sm + FS_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + FS_BARS);
   uint64_t* full_bar = bars;            // [2]
   uint64_t* empty_bar = bars + 2;       // [2]
-  uint64_t* accf = bars + 4;            // [2]
-  uint64_t* xfull = bars + 6;
-  uint64_t* h1r = bars + 7;
-  uint64_t* dz2r = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* accf0 = bars + 4;           // L1 accumulator complete
+  uint64_t* accf1 = bars + 5;           // L2 accumulator complete
+  uint64_t* headf = bars + 6;           // head outputs complete
+  uint64_t* bwdf = bars + 7;            // dA2 and dW2 complete
+  uint64_t* dh1f = bars + 8;            // dH1 accumulator complete
+  uint64_t* xfull = bars + 9;           // workers -> MMA: X tile gathered
+  uint64_t* h1r = bars + 10;            // H1 in R0
+  uint64_t* h2r = bars + 11;            // H2 in R1, acc1 drained
+  uint64_t* gr = bars + 12;             // g^T hi/lo written
+  uint64_t* dz2r = bars + 13;           // dZ2 in R1, acc0 drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int net = static_cast<int>(blockIdx.x) / p.m_tiles;
@@ -164,14 +231,15 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   const FusedNet& G = p.net[net];
   const int H = p.H, nkH = H >> 6, nk0 = p.Dp >> 6;
   const uint32_t R0 = base + FS_R0, R1 = base + FS_R1, RB = base + FS_RB;
+  const uint32_t W2T = base + FS_W2T, GT = base + FS_GT;
 
   if (threadIdx.x == 0) {
+    FS_STAMP(16);
     mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
     mbar_init(&empty_bar[0], 1); mbar_init(&empty_bar[1], 1);
-    mbar_init(&accf[0], 1); mbar_init(&accf[1], 1);
+    mbar_init(accf0, 1); mbar_init(accf1, 1); mbar_init(headf, 1); mbar_init(bwdf, 1); mbar_init(dh1f, 1);
     mbar_init(xfull, FS_WORKERS);
-    mbar_init(h1r, 8);
-    mbar_init(dz2r, 8);
+    mbar_init(h1r, 8); mbar_init(h2r, 8); mbar_init(gr, 8); mbar_init(dz2r, 8);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -183,6 +251,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256;
+  const uint32_t acc_head = acc1;               // [256, 272): head outputs (after acc1 is drained)
+  const uint32_t acc_dw = acc1 + 16;            // [272, 272 + 16 * ceil(H/128)): head-kernel gradient
 
   if (warp == 0) {
     // ===================== weight producer: W0^T, W1^T, W1 k-blocks through the ring ==========
@@ -219,18 +289,66 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
           umma_commit(&empty_bar[s]);
         }
       };
+      FS_STAMP(17);
       mbar_wait(xfull, 0);
       tc_fence_after();
+      FS_STAMP(18);
       gemm(R1, nk0, acc0);            // L1: X W0^T
-      umma_commit(&accf[0]);
+      umma_commit(accf0);
+      FS_STAMP(19);
       mbar_wait(h1r, 0);
       tc_fence_after();
+      FS_STAMP(20);
       gemm(R0, nkH, acc1);            // L2: H1 W1^T
-      umma_commit(&accf[1]);
+      umma_commit(accf1);
+      FS_STAMP(21);
+      // ---- head forward: out[128 x 16] = H2 (W2_hi + W2_lo); A = H2 K-major, B = W2^T K-major, N = 16
+      mbar_wait(h2r, 0);
+      tc_fence_after();
+      {
+        const uint32_t idesc_h = umma_idesc_bf16(128, 16u, 0u, 0u);
+        uint32_t accum = 0;
+        for (int part = 0; part < 2; ++part)
+          for (int kb = 0; kb < nkH; ++kb)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              umma_bf16(acc_head, umma_smem_desc(R1 + kb * 16384 + j * 32, 16, 1024),
+                        umma_smem_desc(W2T + part * 8192 + kb * 2048 + j * 32, 16, 1024), idesc_h, accum);
+              accum = 1;
+            }
+        umma_commit(headf);
+      }
+      FS_STAMP(24);
+      // ---- backward through the head --------------------------------------------------------------
+      mbar_wait(gr, 0);
+      tc_fence_after();
+      {
+        // dA2[128 x H] = g W2^T, K = 16: A = g^T (MN-major, 64-row chunks 2 KB apart), B = W2^T (MN-major)
+        const uint32_t idesc_a = umma_idesc_bf16(128, static_cast<uint32_t>(H), 1u, 1u);
+        umma_bf16(acc0, umma_smem_desc(GT, 2048, 1024), umma_smem_desc(W2T, 2048, 1024), idesc_a, 0u);            // hi * hi
+        umma_bf16(acc0, umma_smem_desc(GT, 2048, 1024), umma_smem_desc(W2T + 8192, 2048, 1024), idesc_a, 1u);     // hi * lo
+        umma_bf16(acc0, umma_smem_desc(GT + 4096, 2048, 1024), umma_smem_desc(W2T, 2048, 1024), idesc_a, 1u);     // lo * hi
+        // dW2[c][j] = sum_r H2[r][c] g[r][j]: A = H2 (MN-major: M = c, K = rows), B = g^T (K-major, N = 16)
+        const uint32_t idesc_w = umma_idesc_bf16(128, 16u, 1u, 0u);
+        for (int mh = 0; mh < (H + 127) / 128; ++mh) {
+          uint32_t accum = 0;
+          for (int part = 0; part < 2; ++part)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              umma_bf16(acc_dw + 16 * mh, umma_smem_desc(R1 + 2 * mh * 16384 + t * 2048, 16384, 1024),
+                        umma_smem_desc(GT + part * 4096 + (t >> 2) * 2048 + (t & 3) * 32, 16, 1024), idesc_w, accum);
+              accum = 1;
+            }
+        }
+        umma_commit(bwdf);
+      }
+      FS_STAMP(25);
       mbar_wait(dz2r, 0);
       tc_fence_after();
+      FS_STAMP(22);
       gemm(R1, nkH, acc0);            // dH1: dZ2 W1
-      umma_commit(&accf[0]);
+      umma_commit(dh1f);
+      FS_STAMP(23);
     }
   } else {
     // ===================== workers ==============================================================
@@ -239,49 +357,65 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     const int q = warp & 3, hf = ww >> 2;
     const int erow = q * 32 + lane;                              // epilogue row == TMEM lane
     const int act = G.act, aout = G.aout;
-    const int AQ = (aout + 3) >> 2;
-    const int srow = wt >> 1, shalf = wt & 1;                    // SIMT (row, half) mapping
-    const int grow = tile * 128 + srow;
+    const int srow = wt >> 1, shalf = wt & 1;                    // gather mapping: (row, k-block parity)
+    if (wt == 0) FS_STAMP(0);
 
     // ---- gather the observation rows of this tile into R1 ---------------------------------------
-    const int src = p.rowidx[grow];
-    for (int kb = shalf; kb < nk0; kb += 2)
-      gather_line(R1 + kb * 16384, srow, p.obs_img + static_cast<size_t>(src) * p.Dp + kb * 64);
-    cp_async_commit();
-    // small operands
-    for (int i = wt; i < H * FS_AP; i += FS_WORKERS) {
-      const int k = i >> 4, j = i & 15;
-      w2s[i] = j < aout ? G.w2[k * aout + j] : 0.f;
-    }
-    for (int i = wt; i < H; i += FS_WORKERS) { bias_s[i] = G.b0[i]; bias_s[256 + i] = G.b1[i]; }
-    // per-row loss inputs, prefetched (used after the second epilogue)
+    const int src_g = p.rowidx[tile * 128 + srow];
+    const int lrow = tile * 128 + erow;                          // loss row of this thread (hf == 0 warps)
     const int count = min(*p.count, p.cap);
-    const bool live = (shalf == 0) && (grow < count);
+    const bool live = (hf == 0) && (lrow < count);
+    const int src_l = live ? p.rowidx[lrow] : 0;
+    for (int kb = shalf; kb < nk0; kb += 2)
+      gather_line(R1 + kb * 16384, srow, p.obs_img + static_cast<size_t>(src_g) * p.Dp + kb * 64);
+    cp_async_commit();
+    // ---- small operands: biases, head bias / log_std, head kernel as bf16 hi/lo (transposed) -----
+    for (int i = wt; i < H; i += FS_WORKERS) { bias_s[i] = G.b0[i]; bias_s[256 + i] = G.b1[i]; }
+    if (wt < 16) hb[wt] = wt < aout ? G.b2[wt] : 0.f;
+    else if (wt < 32) hb[wt] = (net == 0 && wt - 16 < aout) ? p.log_std[wt - 16] : 0.f;
+    for (int c = wt; c < H; c += FS_WORKERS) {
+      float wv[FS_AP];
+#pragma unroll
+      for (int j = 0; j < FS_AP; ++j) wv[j] = j < aout ? G.w2[c * aout + j] : 0.f;
+#pragma unroll
+      for (int j = 0; j < FS_AP; ++j) {
+        uint32_t hi, lo;
+        split_bf16(wv[j], hi, lo);
+        const uint32_t off = sw16_off(j, c);
+        sts_u16(W2T + off, hi);
+        sts_u16(W2T + 8192 + off, lo);
+      }
+    }
+    // per-row loss inputs, prefetched (used after the head GEMM)
     float in0 = 0.f, in1 = 0.f, actn[FS_AP];
 #pragma unroll
     for (int j = 0; j < FS_AP; ++j) actn[j] = 0.f;
     if (live) {
       if (net == 0) {
-        in0 = p.logp_old[src]; in1 = p.adv[src];
+        in0 = p.logp_old[src_l]; in1 = p.adv[src_l];
 #pragma unroll
-        for (int j = 0; j < FS_AP; ++j) if (j < aout) actn[j] = p.action[static_cast<size_t>(src) * aout + j];
+        for (int j = 0; j < FS_AP; ++j) if (j < aout) actn[j] = p.action[static_cast<size_t>(src_l) * aout + j];
       } else {
-        in0 = p.v_old[src]; in1 = p.tgt[src];
+        in0 = p.v_old[src_l]; in1 = p.tgt[src_l];
       }
     }
+    const float adv_sum = *p.adv_sum, adv_sq = *p.adv_sq;
     cp_async_wait<0>();
     fence_proxy_async_smem();
     mbar_arrive(xfull);
-    worker_bar();                                                // w2s / bias visible to all workers
+    worker_bar();                                                // biases / hb / W2T visible to all workers
+    if (wt == 0) FS_STAMP(1);
 
     // ---- epilogue 1: H1 = act(acc0 + b0) -> R0, then TMA store to HBM ------------------------------
-    mbar_wait(&accf[0], 0);
+    mbar_wait(accf0, 0);
     tc_fence_after();
+    if (wt == 0) FS_STAMP(2);
     epilogue_act(acc0, R0, bias_s, act, erow, q, hf * (H >> 1), H >> 1);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(h1r);
+    if (wt == 0) FS_STAMP(3);
     if (ww == 0 && lane == 0) {
       mbar_wait(h1r, 0);
       for (int s = 0; s < nkH; ++s) tma_store_2d(R0 + s * 16384, &G.tm_h1, s * 64, tile * 128);
@@ -289,54 +423,28 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     }
 
     // ---- epilogue 2: H2 = act(acc1 + b1) -> R1 -------------------------------------------------------
-    mbar_wait(&accf[1], 0);
+    mbar_wait(accf1, 0);
     tc_fence_after();
+    if (wt == 0) FS_STAMP(4);
     epilogue_act(acc1, R1, bias_s + 256, act, erow, q, hf * (H >> 1), H >> 1);
-    worker_bar();
+    fence_proxy_async_smem();                                    // H2 (and W2T) -> async proxy for the head MMAs
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(h2r);
+    if (wt == 0) FS_STAMP(5);
 
-    // ---- head: out[j] = sum_c H2[row][c] w2[c][j]   (thread = (row, half of the columns)) ----------
-    float acc[FS_AP];
-#pragma unroll
-    for (int j = 0; j < FS_AP; ++j) acc[j] = 0.f;
-    {
-      const int nch = H >> 4;                                    // 16-byte chunks per half row
-      const int cbeg = shalf * (H >> 1);
-      const int rot = (shalf && (((cbeg >> 3) & 4) == 0)) ? 4 : 0;   // keep the two halves on different banks
-      for (int t = 0; t < nch; ++t) {
-        int tt = t + rot;
-        if (tt >= nch) tt -= nch;
-        const int c = cbeg + 8 * tt;
-        const uint4 hv = lds128(R1 + sw_off(srow, c));
-        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float h = (e & 1) ? bf16_hi(hw[e >> 1]) : bf16_lo(hw[e >> 1]);
-          const float4* wr = reinterpret_cast<const float4*>(w2s + (c + e) * FS_AP);
-#pragma unroll
-          for (int jq = 0; jq < FS_AP / 4; ++jq) {
-            if (jq < AQ) {
-              const float4 wv = wr[jq];
-              acc[4 * jq] = fmaf(h, wv.x, acc[4 * jq]);
-              acc[4 * jq + 1] = fmaf(h, wv.y, acc[4 * jq + 1]);
-              acc[4 * jq + 2] = fmaf(h, wv.z, acc[4 * jq + 2]);
-              acc[4 * jq + 3] = fmaf(h, wv.w, acc[4 * jq + 3]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
-    }
-
-    // ---- loss and gradient seed g = dL/dout, one thread per row (half 0) -------------------------
-    float dls[FS_AP];
+    // ---- loss and gradient seed g = dL/dout: thread = row (hf == 0 warps) ---------------------------
+    mbar_wait(headf, 0);
+    tc_fence_after();
+    if (wt == 0) FS_STAMP(6);
+    float dls[FS_AP], g[FS_AP];
     float s_loss = 0.f;
 #pragma unroll
-    for (int j = 0; j < FS_AP; ++j) dls[j] = 0.f;
-    if (shalf == 0) {
-      float g[FS_AP];
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) g[j] = 0.f;
+    for (int j = 0; j < FS_AP; ++j) { dls[j] = 0.f; g[j] = 0.f; }
+    if (hf == 0) {
+      float out[FS_AP];
+      tmem_ld_32x16(acc_head + (static_cast<uint32_t>(q * 32) << 16), out);
+      tmem_ld_wait();
       if (live) {
         const float inv_n = p.inv_mb;
         if (net == 0) {
@@ -347,9 +455,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
           for (int j = 0; j < FS_AP; ++j) {
             z[j] = 0.f; inv_s[j] = 0.f;
             if (j < aout) {
-              const float scale = expf(p.log_std[j]);
+              const float scale = expf(hb[16 + j]);
               inv_s[j] = 1.f / scale;
-              const float mean = acc[j] + G.b2[j];
+              const float mean = out[j] + hb[j];
               z[j] = (actn[j] - mean) * inv_s[j];
               quad += -0.5f * z[j] * z[j] - 0.91893853320467274178f;
               logdet += logf(fabsf(scale));
@@ -357,8 +465,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
           }
           const float logp = quad - logdet;
           const float ratio = expf(logp - in0);
-          const float adv_mean = (*p.adv_sum) * inv_n;
-          const float adv_std = sqrtf((*p.adv_sq) * inv_n);
+          const float adv_mean = adv_sum * inv_n;
+          const float adv_std = sqrtf(adv_sq * inv_n);
           const float adv = (in1 - adv_mean) / (adv_std + 1e-8f);                 // train.py:235
           const float lo = 1.f - p.clip_eps, hi = 1.f + p.clip_eps;
           const float l1 = ratio * adv;
@@ -374,7 +482,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
           }
         } else {
           // clipped value loss, train.py:226-231
-          const float v = acc[0] + G.b2[0];
+          const float v = out[0] + hb[0];
           const float dvv = v - in0;
           const float v_clip = in0 + fminf(fmaxf(dvv, -p.clip_eps), p.clip_eps);
           const float e1 = v - in1, e2 = v_clip - in1;
@@ -384,110 +492,79 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
           g[0] = p.vf_coef * 0.5f * inv_n * (wa * 2.f * e1 + (1.f - wa) * 2.f * e2 * dclip_f(dvv, -p.clip_eps, p.clip_eps));
         }
       }
+      // g^T as bf16 hi/lo, [16 j][128 rows] SW128 (the MN-major A of dA2 and the K-major B of dW2)
 #pragma unroll
-      for (int jq = 0; jq < FS_AP / 4; ++jq)
-        *reinterpret_cast<float4*>(gs + srow * FS_AP + 4 * jq) = make_float4(g[4 * jq], g[4 * jq + 1], g[4 * jq + 2], g[4 * jq + 3]);
+      for (int j = 0; j < FS_AP; ++j) {
+        uint32_t hi, lo;
+        split_bf16(g[j], hi, lo);
+        const uint32_t off = sw16_off(j, erow);
+        sts_u16(GT + off, hi);
+        sts_u16(GT + 4096 + off, lo);
+      }
     }
-    // tile sums of dlog_std and of the loss term (fixed order: lanes, then warps)
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(gr);
+    // tile sums (fixed order: lanes, then warps): dlog_std, head bias gradient, loss term
 #pragma unroll
-    for (int j = 0; j < FS_AP; ++j) dls[j] = warp_sum(dls[j]);
+    for (int j = 0; j < FS_AP; ++j) { dls[j] = warp_sum(dls[j]); g[j] = warp_sum(g[j]); }
     s_loss = warp_sum(s_loss);
     if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < FS_AP; ++j) red[ww * 24 + j] = dls[j];
-      red[ww * 24 + FS_AP] = s_loss;
+      for (int j = 0; j < FS_AP; ++j) { red[ww * 40 + j] = dls[j]; red[ww * 40 + 16 + j] = g[j]; }
+      red[ww * 40 + 32] = s_loss;
     }
     worker_bar();
-
+    if (wt == 0) FS_STAMP(7);
     float* part = p.part + static_cast<size_t>(tile) * p.part_stride;
-    if (wt <= FS_AP) {
+    if (wt <= 32) {
       float s = 0.f;
-      for (int w = 0; w < 8; ++w) s += red[w * 24 + wt];
-      if (wt == FS_AP) part[G.po_loss] = s;
+      for (int w = 0; w < 4; ++w) s += red[w * 40 + wt];         // hf == 0 warps are ww 0..3
+      if (wt == 32) part[G.po_loss] = s;
+      else if (wt >= 16) { if (wt - 16 < aout) part[G.po_b2 + wt - 16] = s; }
       else if (net == 0 && wt < aout) part[p.po_logstd + wt] = s;
     }
-    if (wt >= 32 && wt < 32 + aout) {                              // head bias gradient: sum_r g[r][j]
-      const int j = wt - 32;
-      float s = 0.f;
-      for (int r = 0; r < 128; ++r) s += gs[r * FS_AP + j];
-      part[G.po_b2 + j] = s;
-    }
 
-    // ---- thread = hidden column c: dZ2 in place, dW2 (head kernel grad), db1 ---------------------
-    for (int c = wt; c < H; c += FS_WORKERS) {
-      float w[FS_AP], dw[FS_AP];
+    // ---- dW2 (head kernel gradient) and dZ2 = dA2 * f'(H2) ----------------------------------------
+    mbar_wait(bwdf, 0);
+    tc_fence_after();
+    if (wt == 0) FS_STAMP(8);
+    if (hf * 128 < H) {                                          // warp (q, hf) reads the c-tile mh = hf
+      float dw[FS_AP];
+      tmem_ld_32x16(acc_dw + 16 * hf + (static_cast<uint32_t>(q * 32) << 16), dw);
+      tmem_ld_wait();
+      const int c = hf * 128 + erow;
+      if (c < H) {
 #pragma unroll
-      for (int j = 0; j < FS_AP; ++j) { w[j] = w2s[c * FS_AP + j]; dw[j] = 0.f; }
-      float db = 0.f;
-      const uint32_t cbase = R1 + static_cast<uint32_t>((c >> 6) * 16384 + (c & 7) * 2);
-      const int pos = (c & 63) >> 3;
-#pragma unroll 4
-      for (int r = 0; r < 128; ++r) {
-        const uint32_t addr = cbase + r * 128 + ((pos ^ (r & 7)) << 4);
-        const float h = __uint_as_float(lds_u16(addr) << 16);
-        float da = 0.f;
-#pragma unroll
-        for (int jq = 0; jq < FS_AP / 4; ++jq) {
-          if (jq < AQ) {
-            const float4 gv = *reinterpret_cast<const float4*>(gs + r * FS_AP + 4 * jq);
-            da = fmaf(gv.x, w[4 * jq], da); da = fmaf(gv.y, w[4 * jq + 1], da);
-            da = fmaf(gv.z, w[4 * jq + 2], da); da = fmaf(gv.w, w[4 * jq + 3], da);
-            dw[4 * jq] = fmaf(h, gv.x, dw[4 * jq]); dw[4 * jq + 1] = fmaf(h, gv.y, dw[4 * jq + 1]);
-            dw[4 * jq + 2] = fmaf(h, gv.z, dw[4 * jq + 2]); dw[4 * jq + 3] = fmaf(h, gv.w, dw[4 * jq + 3]);
-          }
-        }
-        const __nv_bfloat16 dz = __float2bfloat16_rn(da * act_deriv(h, act));
-        sts_u16(addr, static_cast<uint32_t>(__bfloat16_as_ushort(dz)));
-        db += __bfloat162float(dz);
+        for (int j = 0; j < FS_AP; ++j) if (j < aout) part[G.po_w2 + c * aout + j] = dw[j];
       }
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) if (j < aout) part[G.po_w2 + c * aout + j] = dw[j];
-      part[G.po_bh + c] = db;
     }
+    epilogue_dact(acc0, R1, R1, cs, act, erow, q, hf * (H >> 1), H >> 1);     // in place: H2 -> dZ2
     fence_proxy_async_smem();
-    tc_fence_before();                                             // acc0 reads of epilogue 1 ordered before the dH1 MMAs
+    tc_fence_before();                                             // acc0 drained before the dH1 MMAs overwrite it
     __syncwarp();
     if (lane == 0) mbar_arrive(dz2r);
+    if (wt == 0) FS_STAMP(9);
     if (ww == 0 && lane == 0) {
       mbar_wait(dz2r, 0);
       for (int s = 0; s < nkH; ++s) tma_store_2d(R1 + s * 16384, &G.tm_dz2, s * 64, tile * 128);
       tma_store_commit();
     }
+    worker_bar();                                                  // cs complete
+    for (int c = wt; c < H; c += FS_WORKERS)
+      part[G.po_bh + c] = (cs[c] + cs[256 + c]) + (cs[512 + c] + cs[768 + c]);      // db1 = colsum(dZ2)
 
     // ---- epilogue 3: dZ1 = acc0 * f'(H1) -> R1 -> TMA store; column sums -> db0 --------------------
-    mbar_wait(&accf[0], 1);                                        // dH1 MMAs done: R1 (dZ2) no longer read by UMMA
+    mbar_wait(dh1f, 0);                                            // dH1 MMAs done: R1 (dZ2) no longer read by UMMA
     tc_fence_after();
+    if (wt == 0) FS_STAMP(10);
     if (ww == 0 && lane == 0) tma_store_wait_read0();              // ... nor by the dZ2 TMA store
-    worker_bar();
-    {
-      const uint32_t taddr = acc0 + (static_cast<uint32_t>(q * 32) << 16);
-      const int col0 = hf * (H >> 1);
-      for (int c0 = col0; c0 < col0 + (H >> 1); c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(taddr + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t off = sw_off(erow, c0 + 8 * j);
-          const uint4 hh = lds128(R0 + off);
-          const uint32_t hw[4] = {hh.x, hh.y, hh.z, hh.w};
-          uint32_t w[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int e = 8 * j + 2 * t;
-            v[e] *= act_deriv(bf16_lo(hw[t]), act);
-            v[e + 1] *= act_deriv(bf16_hi(hw[t]), act);
-            w[t] = pack_bf16x2(v[e], v[e + 1]);
-            v[e] = bf16_lo(w[t]); v[e + 1] = bf16_hi(w[t]);        // bias gradient sums the stored (rounded) dZ
-          }
-          sts128(R1 + off, make_uint4(w[0], w[1], w[2], w[3]));
-        }
-        const float csum = warp_colsum32(v);
-        cs[q * 256 + c0 + lane] = csum;
-      }
-    }
+    worker_bar();                                                  // also: db1 reads of cs are done
+    epilogue_dact(acc0, R0, R1, cs, act, erow, q, hf * (H >> 1), H >> 1);
     fence_proxy_async_smem();
     worker_bar();
+    if (wt == 0) FS_STAMP(11);
     if (ww == 0 && lane == 0) {
       for (int s = 0; s < nkH; ++s) tma_store_2d(R1 + s * 16384, &G.tm_dz1, s * 64, tile * 128);
       tma_store_commit();
@@ -495,6 +572,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     for (int c = wt; c < H; c += FS_WORKERS)
       G.colsum[static_cast<size_t>(tile) * H + c] = (cs[c] + cs[256 + c]) + (cs[512 + c] + cs[768 + c]);
     if (ww == 0 && lane == 0) tma_store_wait_all0();               // all bulk stores complete before the CTA exits
+    if (wt == 0) FS_STAMP(12);
   }
 
   tc_fence_before();

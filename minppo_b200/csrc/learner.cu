@@ -17,6 +17,7 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -231,6 +232,8 @@ struct minppo_ctx {
   // device buffers
   std::vector<void*> allocs;
   float *adv, *tgt, *stats, *gflat, *block_ss, *head_part, *gnorms, *losses_scratch;
+  long long* trace;           // debug cycle stamps of the fused kernel [2*m_tiles][32]
+  bool trace_on;
   int32_t *perms, *rowidx, *counts;
   void* perm_ws;
   size_t perm_ws_bytes;
@@ -418,6 +421,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     p.H = H; p.A = c->A; p.Dp = c->Dp; p.m_tiles = c->m_tiles; p.cap = c->cap;
     p.inv_mb = static_cast<float>(1.0 / c->mb);
     p.clip_eps = static_cast<float>(c->cfg.clip_eps); p.vf_coef = static_cast<float>(c->cfg.vf_coef);
+    p.trace = c->trace_on ? c->trace : nullptr;
     PROF(PC_FWD_GEMM);
     fused_step_kernel<<<2 * c->m_tiles, FS_THREADS, FS_SMEM_BYTES, stream>>>(p);
     if (cudaGetLastError() != cudaSuccess) { set_error("fused_step launch failed"); return MINPPO_ERR_CUDA; }
@@ -743,6 +747,8 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   ALLOC(c->head_part, static_cast<size_t>(c->tiles64) * c->head_stride);
   ALLOC(c->gnorms, static_cast<size_t>(EM));
   ALLOC(c->losses_scratch, 4);
+  ALLOC(c->trace, static_cast<size_t>(2 * c->m_tiles) * 32);
+  c->trace_on = getenv("MINPPO_TRACE") != nullptr;
   ALLOC(c->perms, static_cast<size_t>(c->E) * c->B);
   ALLOC(c->rowidx, static_cast<size_t>(EM) * c->cap);
   ALLOC(c->counts, static_cast<size_t>(EM));
@@ -889,6 +895,7 @@ int minppo_ctx_read(minppo_ctx* c, int32_t what, void* dst, size_t bytes, void* 
     case 4: src = c->gnorms; have = EM * 4; break;
     case 5: src = c->counts; have = EM * 4; break;
     case 6: src = c->stats; have = 2 * EM * 4; break;
+    case 7: src = c->trace; have = static_cast<size_t>(2 * c->m_tiles) * 32 * 8; break;
     default: set_error("minppo_ctx_read: unknown buffer %d", what); return MINPPO_ERR_ARG;
   }
   if (bytes > have) { set_error("minppo_ctx_read: %zu bytes requested, buffer has %zu", bytes, have); return MINPPO_ERR_ARG; }

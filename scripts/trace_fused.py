@@ -1,0 +1,44 @@
+"""Print the cycle timeline of the fused step kernel (MINPPO_TRACE=1) for a few CTAs of the last minibatch step."""
+import os, sys
+os.environ["MINPPO_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+import numpy as np, torch
+import bench
+from minppo_b200 import _lib
+from minppo_b200.learner import Learner, Memory, TrainState
+from oracle import ppo_numpy as P
+from tests.helpers import hyper_to_config
+
+dev = torch.device("cuda:0")
+hp = bench.make_hyper(bench.workload(1))
+learner = Learner(hyper_to_config(hp, use_graph=False), bench.OBS_DIM, bench.ACT_DIM, dev)
+params, traj, last_val = bench.synth_shard(hp, 0, 1)
+t = lambda x: torch.as_tensor(np.ascontiguousarray(x)).to(dev)
+mem = Memory(done=t(traj["done"]), action=t(traj["action"]), value=t(traj["value"]), reward=t(traj["reward"]),
+             log_prob=t(traj["log_prob"]), obs=t(traj["obs"]))
+ts = TrainState.create(P.flatten_params(params, hp.num_layers), dev)
+rng = torch.tensor([0, 1337], dtype=torch.int32, device=dev)
+for _ in range(2):
+    learner.update(ts, mem, t(last_val), rng)
+learner.check()
+n = 2 * (hp.minibatch_size // 128)
+out = torch.empty((n, 32), dtype=torch.int64, device=dev)
+_lib.check(learner.lib.minppo_ctx_read(learner._h, 7, out.data_ptr(), out.numel() * 8, torch.cuda.current_stream(dev).cuda_stream))
+torch.cuda.synchronize()
+tr = out.cpu().numpy()
+names = {16: "kernel start (t0)", 0: "workers start", 1: "gather+stage done, xfull", 17: "mma: start", 18: "mma: xfull seen", 19: "mma: L1 issued",
+         2: "w: acc0 ready", 3: "w: epi1 done (h1r)", 20: "mma: h1r seen", 21: "mma: L2 issued", 4: "w: acc1 ready", 5: "w: epi2 done (h2r)",
+         24: "mma: head fwd issued", 6: "w: head out ready", 7: "w: loss done + tile sums", 25: "mma: dA2/dW2 issued", 8: "w: bwd accs ready",
+         9: "w: dz2 epilogue done (dz2r)", 22: "mma: dz2r seen", 23: "mma: dH1 issued", 10: "w: dh1 acc ready", 11: "w: epi3 done", 12: "w: stores done"}
+order = [16, 0, 17, 1, 18, 19, 2, 3, 20, 21, 4, 5, 24, 6, 7, 25, 8, 9, 22, 23, 10, 11, 12]
+for cta in (0, 1, n // 2, n - 1):
+    t0 = tr[cta, 16]
+    print(f"--- CTA {cta} ({'actor' if cta < n // 2 else 'critic'})")
+    prev = 0
+    for k in order:
+        d = int(tr[cta, k] - t0)
+        print(f"  {names[k]:34s} {d:8d}  (+{d - prev})")
+        prev = d
+tot = tr[:, 12] - tr[:, 16]
+print("total cycles per CTA: actor mean", tot[:n // 2].mean(), "critic mean", tot[n // 2:].mean(), "max", tot.max())
