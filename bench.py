@@ -9,8 +9,9 @@ over the [T x N] trajectory, E epochs x M minibatches of shuffle/gather + ActorC
 forward/backward + PPO loss + global-norm clip + Adam.
 
   N == 1 : BASELINE.json configs[1]: 2048 envs x 128 steps, 256x256 MLPs, 4 epochs x 32 minibatches.
-  N  > 1 : configs[3]: 16384 envs x 64 steps (GLOBAL batch fixed), env-sharded over N GPUs with a
-           per-minibatch NCCL gradient all-reduce -> "scaling": "strong".
+  N  > 1 : the same shard on EVERY GPU (2048 envs x 128 steps per GPU, global batch 2048*N envs, env-sharded,
+           global permutation, per-minibatch gradient all-reduce) -> "scaling": "weak"; at N = 8 this is
+           configs[3]'s 16384 envs.  `--workload c4` runs configs[3] literally (16384 x 64 global, strong).
 
 `value`  = unique transitions per second = T*N / t_update, inputs resident in HBM, CUDA-graph replay.
 `e2e`    = same metric through Learner.update_host: pinned HOST buffers, H2D of the trajectory +
@@ -40,12 +41,20 @@ METRIC = "learner transitions/sec (GAE+PPO epochs)"
 UNIT = "transitions/s"
 
 
-def workload(n_gpus: int):
+def workload(n_gpus: int, which: str = "auto"):
+    """auto: configs[1] on every GPU (2048 envs x 128 steps PER GPU, env-sharded: the global batch and the
+    global minibatch grow with N -> weak scaling; at N = 8 this is configs[3]'s 16384 envs).
+    c4: configs[3] literally (16384 envs x 64 steps GLOBAL, strong scaling)."""
+    if which == "c4":
+        return dict(name=f"configs[3]: 16384 envs x 64 steps env-sharded over {n_gpus} GPU(s), 256x256 MLPs, "
+                         "4 epochs x 32 minibatches", num_envs=16384, num_steps=64, num_minibatches=32,
+                    update_epochs=4, scaling="strong")
     if n_gpus == 1:
         return dict(name="configs[1]: 2048 envs x 128 steps, 256x256 MLPs, 4 epochs x 32 minibatches",
-                    num_envs=2048, num_steps=128, num_minibatches=32, update_epochs=4)
-    return dict(name="configs[3]: 16384 envs x 64 steps env-sharded, 256x256 MLPs, 4 epochs x 32 minibatches",
-                num_envs=16384, num_steps=64, num_minibatches=32, update_epochs=4)
+                    num_envs=2048, num_steps=128, num_minibatches=32, update_epochs=4, scaling="weak")
+    return dict(name=f"configs[1] per GPU, env-sharded: {2048 * n_gpus} envs x 128 steps over {n_gpus} GPUs "
+                     "(2048 envs per GPU), 256x256 MLPs, 4 epochs x 32 minibatches, per-minibatch gradient all-reduce",
+                num_envs=2048 * n_gpus, num_steps=128, num_minibatches=32, update_epochs=4, scaling="weak")
 
 
 def make_hyper(w):
@@ -184,7 +193,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = workload(args.gpus)
+    w = workload(args.gpus, args.workload)
     hp = make_hyper(w)
     B = hp.batch_size
     sample = 4 if B >= (1 << 20) else 8
@@ -201,7 +210,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_upd * 1e3, "higher_is_better": True,
-        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "obs_dim": OBS_DIM, "act_dim": ACT_DIM, "shape_note": "D/A are a declared stand-in"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample_desc + "; CPU restatement (PyTorch fp32), not JAX"},
@@ -237,7 +246,7 @@ def run_ours(args):
         dist.broadcast_object_list(ids, src=0)
         nccl_id = ids[0]
 
-    w = workload(world)
+    w = workload(world, args.workload)
     hp = make_hyper(w)
     B = hp.batch_size
     cfg = hyper_to_config(hp, fast_tanh=bool(args.fast_tanh), use_graph=True)
@@ -285,6 +294,14 @@ def run_ours(args):
     ms_per_step = float(tt.item()) / args.steps
     value = B / (ms_per_step * 1e-3)
     final_losses = losses.cpu().numpy()
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_per_step, "value": value, "n_gpus": world,
+                              "skip": os.environ.get("MINPPO_SKIP", "0"), "clocks": clocks}), flush=True)
+        learner.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end-to-end through host buffers --------------------------------------------------------
     hb = HostBatch(learner)
@@ -341,21 +358,38 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        # dominant kernel = the GEMM class with the most time; algorithmic FLOPs per launch
+        # dominant kernel = the tensor-core class with the most time; ALGORITHMIC FLOPs per launch
+        # (F MACs forward, F - 2DH for dX, F for dW per transition; D unpadded)
         H, L, D, A = hp.hidden_size, hp.num_layers, OBS_DIM, ACT_DIM
         rows = hp.minibatch_size / world
-        flops = {
-            "fwd_gemm": 2 * rows * 2 * (D * H + (L - 1) * H * H) / L,         # per launch (one layer, both nets), averaged
-            "bwd_gemm": 2 * rows * 2 * H * H,                                 # per launch (one layer, both nets)
-            "dw_gemm": 2 * rows * 2 * (D * H + (L - 1) * H * H),              # one launch covers all layers, both nets
-        }
+        F_hidden = 2 * D * H + 2 * (L - 1) * H * H            # MACs per row, hidden-layer contractions, both nets
+        F_heads = H * A + H
+        fused_path = prof["head_loss"]["scopes"] == 0           # fused step kernel: fwd + heads + loss + dX in one launch
+        if fused_path:
+            flops = {"fwd_gemm": 2 * rows * ((F_hidden + F_heads) + (F_hidden - 2 * D * H + F_heads) + F_heads),
+                     "dw_gemm": 2 * rows * F_hidden}
+            names = {"fwd_gemm": "fused_step_kernel (forward + heads + PPO loss + backward-to-dZ, both nets)",
+                     "dw_gemm": "umma_gemm_kernel<EPI_PARTIAL> (split-K weight gradients, all layers, both nets)"}
+        else:
+            flops = {"fwd_gemm": 2 * rows * F_hidden / L, "bwd_gemm": 2 * rows * 2 * H * H, "dw_gemm": 2 * rows * F_hidden}
+            names = {k: f"umma_gemm_kernel ({k})" for k in flops}
         dom = max(flops, key=lambda k: prof[k]["ms_per_update"])
         launches = max(prof[dom]["scopes"], 1)
         dur_s = prof[dom]["ms_per_update"] * 1e-3 / launches
         achieved = flops[dom] / dur_s / 1e12 if dur_s > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": f"umma_gemm_kernel ({dom})", "achieved": achieved, "peak": tf_peak,
-                    "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
-                    "flops_per_launch": flops[dom], "avg_launch_us": dur_s * 1e6, "peak_source": peak_src + ", sustained bf16"}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(dom)          # dram bytes per launch from the committed ncu --set full capture
+        except (OSError, ValueError):
+            pass
+        step_flops = 2 * rows * (3 * (F_hidden + F_heads) - 2 * D * H)
+        roofline = {"bound": "tensor", "kernel": names[dom], "achieved": achieved, "peak": tf_peak,
+                    "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
+                    "flops_per_launch": flops[dom], "avg_launch_us": dur_s * 1e6, "peak_source": peak_src + ", sustained bf16",
+                    "whole_step": {"flops_per_minibatch_step": step_flops,
+                                   "achieved_tflops": step_flops * hp.update_epochs * hp.num_minibatches / (ms_per_step * 1e-3) / 1e12,
+                                   "note": "all kernels of one update (graph replay) against the same peak"}}
         # GAE against the HBM roofline at a bandwidth-relevant size (config 3 scale: 128 x 1M)
         Tg, Ng = 128, 1 << 20
         gg = torch.Generator(device=dev).manual_seed(0)
@@ -391,7 +425,7 @@ def run_ours(args):
                              "extrapolated to the full update; CPU restatement (PyTorch fp32), not JAX"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "bf16 tensor-core GEMMs (fp32 accumulate), fp32 elsewhere", "data": "synthetic",
             "config": {"workload": w["name"], "obs_dim": OBS_DIM, "act_dim": ACT_DIM,
                        "shape_note": "D=225/A=10 are a declared stand-in for stompy_pro (SURVEY.md F9)",
@@ -422,6 +456,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fast-tanh", type=int, default=1, help="library default (config.learner.fast_tanh)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c4"],
+                    help="auto: configs[1] per GPU (weak scaling); c4: configs[3] global batch (strong scaling)")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (development)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -16,7 +16,7 @@
 
 namespace minppo {
 
-constexpr int OPT_THREADS = 1024;
+constexpr int OPT_THREADS = 512;                 // 512 x <= 42 regs: co-resident with a fused-step CTA under PDL
 constexpr int OPT_EPT = 8;                    // max elements per thread (registers)
 
 MINPPO_DEVINL float block_sum(float v, float* scratch /*[32]*/) {
@@ -76,38 +76,45 @@ MINPPO_DEVINL int find_leaf_idx(const OptArgs& a, int i) {
 // the few leaves with many partials (output heads) are spread over the whole grid while every
 // warp still reads 128 contiguous bytes per partial.
 template <int EPT>
-__global__ void __launch_bounds__(OPT_THREADS, 1) opt_kernel(const OptArgs a) {
+__global__ void __launch_bounds__(OPT_THREADS, 3) opt_kernel(const OptArgs a) {
   __shared__ float scratch[32];
   __shared__ float s_bcast[4];
   const int P = a.P;
   const int G = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int count = a.do_apply ? *a.count : 0;             // Adam step count BEFORE this step
+  const int count = a.do_apply ? __ldcg(a.count) : 0;            // Adam step count BEFORE this step
   float ent = a.entropy_const;                             // A * (0.5 + 0.5 log 2pi) + sum log|scale|
   if (a.do_apply && blockIdx.x == 0 && threadIdx.x == 0 && a.losses_out) {
     // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the barrier)
-    for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(a.params[a.off_logstd + j])));
+    for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(__ldcg(a.params + a.off_logstd + j))));
   }
 
   float g[EPT], pv[EPT], mv[EPT], nv[EPT];
   float ss = 0.f;
+  // optimizer state of this thread's elements: independent of the gradient producers, so it is
+  // fetched before the PDL wait (nothing else writes params / mu / nu between two optimizer steps)
 #pragma unroll
   for (int k = 0; k < EPT; ++k) {
     const int i = ((k * 32 + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
-    g[k] = 0.f; pv[k] = 0.f; mv[k] = 0.f; nv[k] = 0.f;
+    pv[k] = 0.f; mv[k] = 0.f; nv[k] = 0.f;
+    if (i < P && a.do_apply) { pv[k] = __ldcg(a.params + i); mv[k] = __ldcg(a.mu + i); nv[k] = __ldcg(a.nu + i); }
+  }
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch();
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int i = ((k * 32 + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
+    g[k] = 0.f;
     if (i < P) {
       if (a.do_reduce) {
         const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
         g[k] = sum_partials(L.grad_src + L.src_offset + (i - L.offset), L.nparts, L.part_stride) + L.grad_bias;
         if (!a.do_apply || a.keep_gflat) a.gflat[i] = g[k];
       } else {
-        g[k] = a.gflat[i];
+        g[k] = __ldcg(a.gflat + i);
       }
-      if (a.do_apply) {                                    // prefetch the optimizer state before the barrier
-        pv[k] = a.params[i]; mv[k] = a.mu[i]; nv[k] = a.nu[i];
-        ss = fmaf(g[k], g[k], ss);
-      }
+      if (a.do_apply) ss = fmaf(g[k], g[k], ss);
     } else if (i < P + 2 && a.do_reduce) {
       a.gflat[i] = sum_partials(a.loss_src + a.loss_src_offset + (i - P), a.loss_nparts, a.loss_part_stride);
     }
@@ -213,14 +220,15 @@ __global__ void weight_images_kernel(const OptArgs a) {
 
 int opt_max_params(int blocks) { return blocks * OPT_THREADS * OPT_EPT - 2; }
 
-int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream) {
+int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream, bool pdl) {
   if (a.P > opt_max_params(blocks)) return MINPPO_ERR_UNSUPPORTED;   // single sweep: global norm needs all elements
   const long long per_thread = (static_cast<long long>(a.P) + 2 + static_cast<long long>(blocks) * OPT_THREADS - 1) /
                                (static_cast<long long>(blocks) * OPT_THREADS);
-  if (per_thread <= 2) opt_kernel<2><<<blocks, OPT_THREADS, 0, stream>>>(a);
-  else if (per_thread <= 4) opt_kernel<4><<<blocks, OPT_THREADS, 0, stream>>>(a);
-  else opt_kernel<OPT_EPT><<<blocks, OPT_THREADS, 0, stream>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
+  cudaError_t e;
+  if (per_thread <= 2) e = launch_kernel(opt_kernel<2>, blocks, OPT_THREADS, 0, stream, pdl, a);
+  else if (per_thread <= 4) e = launch_kernel(opt_kernel<4>, blocks, OPT_THREADS, 0, stream, pdl, a);
+  else e = launch_kernel(opt_kernel<OPT_EPT>, blocks, OPT_THREADS, 0, stream, pdl, a);
+  return e == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }
 
 int weight_images_launch(const OptArgs& a, cudaStream_t stream) {

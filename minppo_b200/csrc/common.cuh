@@ -38,6 +38,17 @@ MINPPO_DEVINL float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL).  Protocol used by the per-minibatch kernels:
+//   prologue + reads of update-static data;  griddep_wait();  griddep_launch();  main body.
+// Triggering only AFTER the own wait keeps completion transitive: when kernel K+1 starts, K has
+// passed its wait, hence K-1 has completed.  Both are no-ops for a launch without the attribute.
+// Data another kernel of the chain rewrites (params, partials) is read with ld.global.cg after
+// the wait: with PDL the L1 invalidate of the launch boundary may precede those writes.
+// ------------------------------------------------------------------------------------
+MINPPO_DEVINL void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+MINPPO_DEVINL void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------
 MINPPO_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     // ===================== weight producer: W0^T, W1^T, W1 k-blocks through the ring ==========
     if (elect_one()) {
       tma_prefetch_desc(&G.tm_w0t); tma_prefetch_desc(&G.tm_w1t); tma_prefetch_desc(&G.tm_w1n);
+      griddep_wait();                 // the weight images are rewritten by the previous optimizer step
       const uint32_t bytes = static_cast<uint32_t>(H) * 128u;
       const int total = nk0 + 2 * nkH;
       for (int i = 0; i < total; ++i) {
@@ -369,24 +370,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     for (int kb = shalf; kb < nk0; kb += 2)
       gather_line(R1 + kb * 16384, srow, p.obs_img + static_cast<size_t>(src_g) * p.Dp + kb * 64);
     cp_async_commit();
-    // ---- small operands: biases, head bias / log_std, head kernel as bf16 hi/lo (transposed) -----
-    for (int i = wt; i < H; i += FS_WORKERS) { bias_s[i] = G.b0[i]; bias_s[256 + i] = G.b1[i]; }
-    if (wt < 16) hb[wt] = wt < aout ? G.b2[wt] : 0.f;
-    else if (wt < 32) hb[wt] = (net == 0 && wt - 16 < aout) ? p.log_std[wt - 16] : 0.f;
-    for (int c = wt; c < H; c += FS_WORKERS) {
-      float wv[FS_AP];
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) wv[j] = j < aout ? G.w2[c * aout + j] : 0.f;
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) {
-        uint32_t hi, lo;
-        split_bf16(wv[j], hi, lo);
-        const uint32_t off = sw16_off(j, c);
-        sts_u16(W2T + off, hi);
-        sts_u16(W2T + 8192 + off, lo);
-      }
-    }
-    // per-row loss inputs, prefetched (used after the head GEMM)
+    // per-row loss inputs, prefetched (used after the head GEMM); static within one update
     float in0 = 0.f, in1 = 0.f, actn[FS_AP];
 #pragma unroll
     for (int j = 0; j < FS_AP; ++j) actn[j] = 0.f;
@@ -400,6 +384,26 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       }
     }
     const float adv_sum = *p.adv_sum, adv_sq = *p.adv_sq;
+    // ---- everything below reads what the previous optimizer step wrote (PDL: see common.cuh) -------
+    griddep_wait();
+    if (wt == 0) griddep_launch();
+    // ---- small operands: biases, head bias / log_std, head kernel as bf16 hi/lo (transposed) -----
+    for (int i = wt; i < H; i += FS_WORKERS) { bias_s[i] = __ldcg(G.b0 + i); bias_s[256 + i] = __ldcg(G.b1 + i); }
+    if (wt < 16) hb[wt] = wt < aout ? __ldcg(G.b2 + wt) : 0.f;
+    else if (wt < 32) hb[wt] = (net == 0 && wt - 16 < aout) ? __ldcg(p.log_std + wt - 16) : 0.f;
+    for (int c = wt; c < H; c += FS_WORKERS) {
+      float wv[FS_AP];
+#pragma unroll
+      for (int j = 0; j < FS_AP; ++j) wv[j] = j < aout ? __ldcg(G.w2 + c * aout + j) : 0.f;
+#pragma unroll
+      for (int j = 0; j < FS_AP; ++j) {
+        uint32_t hi, lo;
+        split_bf16(wv[j], hi, lo);
+        const uint32_t off = sw16_off(j, c);
+        sts_u16(W2T + off, hi);
+        sts_u16(W2T + 8192 + off, lo);
+      }
+    }
     cp_async_wait<0>();
     fence_proxy_async_smem();
     mbar_arrive(xfull);

@@ -234,6 +234,8 @@ struct minppo_ctx {
   float *adv, *tgt, *stats, *gflat, *block_ss, *head_part, *gnorms, *losses_scratch;
   long long* trace;           // debug cycle stamps of the fused kernel [2*m_tiles][32]
   bool trace_on;
+  bool pdl;                   // programmatic dependent launch between step kernels (MINPPO_PDL=0 disables)
+  int skip_mask;              // debug (MINPPO_SKIP): 1 = no fused step, 2 = no dW GEMM, 4 = no optimizer (timing ablation only)
   int32_t *perms, *rowidx, *counts;
   void* perm_ws;
   size_t perm_ws_bytes;
@@ -321,9 +323,9 @@ static int init_kernel_attrs() {
 }
 
 template <int EPI>
-static int launch_gemm(const GemmParams& p, int ctas, cudaStream_t stream) {
-  umma_gemm_kernel<EPI><<<ctas, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
-  if (cudaGetLastError() != cudaSuccess) { set_error("umma_gemm launch failed"); return MINPPO_ERR_CUDA; }
+static int launch_gemm(const GemmParams& p, int ctas, cudaStream_t stream, bool pdl = false) {
+  const cudaError_t e = launch_kernel(umma_gemm_kernel<EPI>, ctas, GEMM_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
+  if (e != cudaSuccess) { set_error("umma_gemm launch failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
   return 0;
 }
 
@@ -392,7 +394,10 @@ static int nccl_allreduce(minppo_ctx* c, float* buf, size_t n, cudaStream_t stre
 static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t stream) {
   const int L = c->L, H = c->H;
   const int32_t* ridx = c->rowidx + static_cast<size_t>(s) * c->cap;
-  if (c->fused) {
+  // programmatic dependent launch between the per-minibatch kernels (fused path only; common.cuh)
+  const bool pdl = c->pdl && c->fused && !c->profiling;
+  if (c->fused && (c->skip_mask & 1)) {
+  } else if (c->fused) {
     // forward + heads + loss + backward-to-dZ of both nets in one launch (fused_step.cuh)
     FusedParams p;
     memset(&p, 0, sizeof(p));
@@ -423,8 +428,8 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     p.clip_eps = static_cast<float>(c->cfg.clip_eps); p.vf_coef = static_cast<float>(c->cfg.vf_coef);
     p.trace = c->trace_on ? c->trace : nullptr;
     PROF(PC_FWD_GEMM);
-    fused_step_kernel<<<2 * c->m_tiles, FS_THREADS, FS_SMEM_BYTES, stream>>>(p);
-    if (cudaGetLastError() != cudaSuccess) { set_error("fused_step launch failed"); return MINPPO_ERR_CUDA; }
+    const cudaError_t e = launch_kernel(fused_step_kernel, 2 * c->m_tiles, FS_THREADS, FS_SMEM_BYTES, stream, pdl, p);
+    if (e != cudaSuccess) { set_error("fused_step launch failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
     c->launches++;
   } else {
   // forward
@@ -499,7 +504,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
   }
   }  // !fused
   // weight gradients: dW_l = act[l]^T dz[l+1], split-K over minibatch rows
-  {
+  if (!(c->skip_mask & 2)) {
     GemmParams p;
     memset(&p, 0, sizeof(p));
     int ng = 0, cta = 0;
@@ -521,11 +526,11 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     }
     p.ngroups = ng;
     PROF(PC_DW_GEMM);
-    RET(launch_gemm<EPI_PARTIAL>(p, cta, stream));
+    RET(launch_gemm<EPI_PARTIAL>(p, cta, stream, pdl));
     c->launches++;
   }
   // optimizer
-  {
+  if (!(c->skip_mask & 4)) {
     OptArgs o;
     fill_opt_args(c, u, &o);
     o.losses_out = u.losses_out ? u.losses_out + static_cast<size_t>(s) * 4 : c->losses_scratch;
@@ -533,11 +538,11 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     if (c->cfg.world_size == 1) {
       o.do_reduce = 1; o.do_apply = 1;
       PROF(PC_OPT);
-      RET(opt_launch(o, c->opt_blocks, stream));
+      RET(opt_launch(o, c->opt_blocks, stream, pdl));
       c->launches++;
     } else {
       o.do_reduce = 1; o.do_apply = 0;
-      { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream)); }
+      { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream, pdl)); }
       { PROF(PC_ALLREDUCE); RET(nccl_allreduce(c, c->gflat, static_cast<size_t>(c->P) + 2, stream)); }
       o.do_reduce = 0; o.do_apply = 1;
       { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream)); }
@@ -749,6 +754,8 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   ALLOC(c->losses_scratch, 4);
   ALLOC(c->trace, static_cast<size_t>(2 * c->m_tiles) * 32);
   c->trace_on = getenv("MINPPO_TRACE") != nullptr;
+  c->pdl = !(getenv("MINPPO_PDL") && atoi(getenv("MINPPO_PDL")) == 0);
+  c->skip_mask = getenv("MINPPO_SKIP") ? atoi(getenv("MINPPO_SKIP")) : 0;
   ALLOC(c->perms, static_cast<size_t>(c->E) * c->B);
   ALLOC(c->rowidx, static_cast<size_t>(EM) * c->cap);
   ALLOC(c->counts, static_cast<size_t>(EM));

@@ -94,10 +94,27 @@ struct OptArgs {
   float lr, max_norm, b1, b2, one_minus_b1, one_minus_b2, eps, eps_root;
   float inv_mb, vf_coef, ent_coef, entropy_const;
 };
-int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream);
+int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream, bool pdl = false);
 int opt_max_params(int blocks);
 int weight_images_launch(const OptArgs& a, cudaStream_t stream);
 int obs_image_launch(const float* obs, __nv_bfloat16* img, long long rows, int cols, int ld, cudaStream_t stream);
+
+// ---- launch helper: optional programmatic-dependent-launch edge to the preceding kernel ------
+template <typename Kern, typename Arg>
+inline cudaError_t launch_kernel(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t stream, bool pdl,
+                                 const Arg& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, arg);
+}
 
 // ---- error plumbing (learner.cu) -----------------------------------------------------------
 void set_error(const char* fmt, ...);

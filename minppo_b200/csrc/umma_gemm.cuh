@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
     if (elect_one()) {
       if (kTmaA) tma_prefetch_desc(&G.tmA);
       tma_prefetch_desc(&G.tmB);
+      griddep_wait();                  // PDL (common.cuh): operands are written by the preceding kernel
+      griddep_launch();
       const uint32_t a_bytes = kTmaA ? GEMM_A_BYTES : 0;
       const uint32_t b_bytes = static_cast<uint32_t>(N) * GEMM_BK * 2;
       for (int i = 0; i < nkb; ++i) {
