@@ -369,7 +369,8 @@ def run_ours(args):
             flops = {"fwd_gemm": 2 * rows * ((F_hidden + F_heads) + (F_hidden - 2 * D * H + F_heads) + F_heads),
                      "dw_gemm": 2 * rows * F_hidden}
             names = {"fwd_gemm": "fused_step_kernel (forward + heads + PPO loss + backward-to-dZ, both nets)",
-                     "dw_gemm": "umma_gemm_kernel<EPI_PARTIAL> (split-K weight gradients, all layers, both nets)"}
+                     "dw_gemm": "dwopt_kernel (split-K weight gradients of all layers and both nets + gradient "
+                                "reduction + global-norm clip + Adam, one launch)"}
         else:
             flops = {"fwd_gemm": 2 * rows * F_hidden / L, "bwd_gemm": 2 * rows * 2 * H * H, "dw_gemm": 2 * rows * F_hidden}
             names = {k: f"umma_gemm_kernel ({k})" for k in flops}

@@ -13,63 +13,9 @@
 // Single GPU runs R+A in one launch; with env-sharded ranks R, NCCL all-reduce(gflat), A.
 #include "common.cuh"
 #include "minppo_internal.h"
+#include "opt_common.cuh"
 
 namespace minppo {
-
-constexpr int OPT_THREADS = 512;                 // 512 x <= 42 regs: co-resident with a fused-step CTA under PDL
-constexpr int OPT_EPT = 8;                    // max elements per thread (registers)
-
-MINPPO_DEVINL float block_sum(float v, float* scratch /*[32]*/) {
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float s = 0.f;
-  if (threadIdx.x < 32) {
-    s = threadIdx.x < (OPT_THREADS / 32) ? scratch[threadIdx.x] : 0.f;
-    s = warp_sum(s);
-  }
-  __syncthreads();
-  return s;                                   // valid in warp 0
-}
-
-// Sense-free grid barrier on a monotonically increasing 64-bit counter.  All blocks of the
-// grid are co-resident (grid <= #SMs, one block per SM).  A bounded spin turns a scheduling
-// surprise into an error flag instead of a hung GPU.
-MINPPO_DEVINL void grid_barrier(unsigned long long* counter, int* err_flag) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long old = atomicAdd(counter, 1ULL);
-    const unsigned long long target = (old / gridDim.x + 1ULL) * gridDim.x;
-    const long long t0 = clock64();
-    while (*reinterpret_cast<volatile unsigned long long*>(counter) < target) {
-      if (clock64() - t0 > 4000000000LL) { atomicExch(err_flag, MINPPO_ERR_BARRIER); break; }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// fixed-order sum of `nparts` partials, 8 loads in flight
-MINPPO_DEVINL float sum_partials(const float* __restrict__ src, int nparts, size_t stride) {
-  float acc = 0.f;
-  int p = 0;
-  for (; p + 8 <= nparts; p += 8) {
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + static_cast<size_t>(p + u) * stride);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc += v[u];
-  }
-  for (; p < nparts; ++p) acc += __ldcg(src + static_cast<size_t>(p) * stride);
-  return acc;
-}
-
-MINPPO_DEVINL int find_leaf_idx(const OptArgs& a, int i) {
-  int l = 0;
-  while (l + 1 < a.nleaves && i >= a.leaf[l + 1].offset) ++l;
-  return l;
-}
 
 // EPT elements per thread, kept in registers across the grid barrier.  Elements are dealt to
 // warps in 32-element chunks, round-robin over BLOCKS (chunk = k*G*32 + warp*G + block), so that
@@ -96,7 +42,7 @@ __global__ void __launch_bounds__(OPT_THREADS, 3) opt_kernel(const OptArgs a) {
   // fetched before the PDL wait (nothing else writes params / mu / nu between two optimizer steps)
 #pragma unroll
   for (int k = 0; k < EPT; ++k) {
-    const int i = ((k * 32 + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
+    const int i = ((k * (OPT_THREADS / 32) + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
     pv[k] = 0.f; mv[k] = 0.f; nv[k] = 0.f;
     if (i < P && a.do_apply) { pv[k] = __ldcg(a.params + i); mv[k] = __ldcg(a.mu + i); nv[k] = __ldcg(a.nu + i); }
   }
@@ -104,7 +50,7 @@ __global__ void __launch_bounds__(OPT_THREADS, 3) opt_kernel(const OptArgs a) {
   if (threadIdx.x == 0) griddep_launch();
 #pragma unroll
   for (int k = 0; k < EPT; ++k) {
-    const int i = ((k * 32 + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
+    const int i = ((k * (OPT_THREADS / 32) + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
     g[k] = 0.f;
     if (i < P) {
       if (a.do_reduce) {
@@ -149,7 +95,7 @@ __global__ void __launch_bounds__(OPT_THREADS, 3) opt_kernel(const OptArgs a) {
   const float lr = s_bcast[1], c1 = s_bcast[2], c2 = s_bcast[3];
 #pragma unroll
   for (int k = 0; k < EPT; ++k) {
-    const int i = ((k * 32 + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
+    const int i = ((k * (OPT_THREADS / 32) + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
     if (i >= P) continue;
     float gg = g[k];
     if (!trigger) gg = (gg / gnorm) * a.max_norm;
@@ -160,14 +106,7 @@ __global__ void __launch_bounds__(OPT_THREADS, 3) opt_kernel(const OptArgs a) {
     a.params[i] = p;
     a.mu[i] = mu;
     a.nu[i] = nu;
-    const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
-    if (L.img_t || L.img_n) {
-      const int e = i - L.offset;
-      const int r = e / L.cols, c = e % L.cols;            // kernel [in=r][out=c]
-      const __nv_bfloat16 b = __float2bfloat16_rn(p);
-      if (L.img_t) L.img_t[static_cast<size_t>(c) * L.ld_t + r] = b;
-      if (L.img_n) L.img_n[static_cast<size_t>(r) * L.ld_n + c] = b;
-    }
+    write_images(a.leaf[find_leaf_idx(a, i)], i, p);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *a.count = count + 1;
@@ -207,14 +146,7 @@ __global__ void weight_images_kernel(const OptArgs a) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.P; i += gthreads) {
     int l = 0;
     while (l + 1 < a.nleaves && i >= a.leaf[l + 1].offset) ++l;
-    const OptLeaf& L = a.leaf[l];
-    if (L.img_t || L.img_n) {
-      const int e = i - L.offset;
-      const int r = e / L.cols, c = e % L.cols;
-      const __nv_bfloat16 b = __float2bfloat16_rn(a.params[i]);
-      if (L.img_t) L.img_t[static_cast<size_t>(c) * L.ld_t + r] = b;
-      if (L.img_n) L.img_n[static_cast<size_t>(r) * L.ld_n + c] = b;
-    }
+    write_images(a.leaf[l], i, a.params[i]);
   }
 }
 

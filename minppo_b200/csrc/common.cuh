@@ -133,6 +133,9 @@ MINPPO_DEVINL void tma_store_3d(uint32_t smem_src, const CUtensorMap* m, int c0,
 MINPPO_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 MINPPO_DEVINL void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 MINPPO_DEVINL void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// async-proxy (TMA) global writes -> ordered before later generic-proxy operations of this thread
+// (release to other CTAs of the same grid through a grid barrier)
+MINPPO_DEVINL void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 MINPPO_DEVINL void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -241,6 +244,17 @@ MINPPO_DEVINL float exp_tanh(float x) {
 MINPPO_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// x = hi + lo with hi, lo bf16 (relative error 2^-17)
+MINPPO_DEVINL void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+// byte offset of element (j, c) inside a [16][ncols] bf16 SW128 tile set (2 KB per 64 columns)
+MINPPO_DEVINL uint32_t sw16_off(int j, int c) {
+  return static_cast<uint32_t>((c >> 6) * 2048 + j * 128 + ((((c & 63) >> 3) ^ (j & 7)) << 4) + (c & 7) * 2);
 }
 MINPPO_DEVINL float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 MINPPO_DEVINL float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }

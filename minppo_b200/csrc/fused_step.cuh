@@ -11,7 +11,7 @@
 //   head out  = H2 W2    (N = 16)                         -> +b2 -> Gaussian log-prob / clipped
 //        surrogate (actor CTA) or clipped value loss (critic CTA), train.py:218-243 -> g = dL/dout
 //   bwd  dA2  = g W2^T   (K = 16),  dW2 = H2^T g (N = 16) -> dZ2 = dA2 * f'(H2) in place -> TMA store
-//   dH1  acc0 = dZ2 W1                                    -> * f'(H1), bf16 -> R1 (dZ1) -> TMA store
+//   dH1  acc1 = dZ2 W1                                    -> * f'(H1), bf16 -> R1 (dZ1) -> TMA store
 //
 // The output-head operands W2 and g are fp32 quantities: they enter the tensor cores as a bf16
 // hi/lo pair (x = hi + lo to 2^-17), the cross terms hi*hi + hi*lo + lo*hi are accumulated in
@@ -54,7 +54,7 @@ struct alignas(64) FusedNet {
   CUtensorMap tm_dz1;            // dz[1]
   const float* b0;               // arena pointers
   const float* b1;
-  const float* w2;               // head kernel [H][aout]
+  const uint4* w2img;            // head kernel^T as bf16 hi / lo, the 16 KB smem image of FS_W2T (written by the optimizer)
   const float* b2;               // head bias [aout]
   float* colsum;                 // [m_tiles][H] column sums of dZ1 (bias gradient of layer 0)
   int act;                       // ACT_*
@@ -104,10 +104,6 @@ MINPPO_DEVINL void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
 MINPPO_DEVINL uint32_t sw_off(int r, int c) {
   return static_cast<uint32_t>((c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4));
 }
-// byte offset of element (j, c) inside a [16][ncols] bf16 SW128 tile set (2 KB per 64 columns)
-MINPPO_DEVINL uint32_t sw16_off(int j, int c) {
-  return static_cast<uint32_t>((c >> 6) * 2048 + j * 128 + ((((c & 63) >> 3) ^ (j & 7)) << 4) + (c & 7) * 2);
-}
 template <int ACT>
 MINPPO_DEVINL float act_apply(float x) {
   if (ACT == ACT_RELU) return fmaxf(x, 0.f);
@@ -119,14 +115,6 @@ MINPPO_DEVINL float act_deriv_t(float h) { return ACT == ACT_RELU ? (h > 0.f ? 1
 MINPPO_DEVINL float dclip_f(float x, float lo, float hi) {
   return (x > lo && x < hi) ? 1.f : ((x == lo || x == hi) ? 0.5f : 0.f);
 }
-// x = hi + lo with hi, lo bf16 (relative error 2^-17)
-MINPPO_DEVINL void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-  hi = __bfloat16_as_ushort(h);
-  lo = __bfloat16_as_ushort(l);
-}
-
 // accumulator (32 columns per chunk) -> +bias, activation, bf16 -> swizzled smem tile
 template <int ACT>
 MINPPO_DEVINL void epilogue_act_t(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int row, int q, int col0,
@@ -219,11 +207,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   uint64_t* bwdf = bars + 7;            // dA2 and dW2 complete
   uint64_t* dh1f = bars + 8;            // dH1 accumulator complete
   uint64_t* xfull = bars + 9;           // workers -> MMA: X tile gathered
-  uint64_t* h1r = bars + 10;            // H1 in R0
-  uint64_t* h2r = bars + 11;            // H2 in R1, acc1 drained
-  uint64_t* gr = bars + 12;             // g^T hi/lo written
-  uint64_t* dz2r = bars + 13;           // dZ2 in R1, acc0 drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* h2r = bars + 10;            // H2 in R1, acc1 drained
+  uint64_t* gr = bars + 11;             // g^T hi/lo written
+  uint64_t* h1r = bars + 12;            // [4] H1 columns [64 b, 64 b + 64) in R0 (k-block b of the L2 GEMM)
+  uint64_t* dz2r = bars + 16;           // [4] dZ2 columns [64 b, 64 b + 64) in R1 (k-block b of the dH1 GEMM)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int net = static_cast<int>(blockIdx.x) / p.m_tiles;
@@ -239,7 +227,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     mbar_init(&empty_bar[0], 1); mbar_init(&empty_bar[1], 1);
     mbar_init(accf0, 1); mbar_init(accf1, 1); mbar_init(headf, 1); mbar_init(bwdf, 1); mbar_init(dh1f, 1);
     mbar_init(xfull, FS_WORKERS);
-    mbar_init(h1r, 8); mbar_init(h2r, 8); mbar_init(gr, 8); mbar_init(dz2r, 8);
+    mbar_init(h2r, 8); mbar_init(gr, 8);
+    for (int b = 0; b < 4; ++b) { mbar_init(&h1r[b], 8); mbar_init(&dz2r[b], 8); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -276,10 +265,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(H), 0u, 0u);
       int i = 0;
-      auto gemm = [&](uint32_t a_base, int nk, uint32_t acc) {
+      // a_ready: per-k-block barriers of the A operand (the epilogue that produces A publishes it in
+      // 64-column blocks, so this GEMM starts while the previous epilogue is still running)
+      auto gemm = [&](uint32_t a_base, int nk, uint32_t acc, uint64_t* a_ready) {
         for (int kb = 0; kb < nk; ++kb, ++i) {
           const int s = i & 1;
           const uint32_t ph = (i >> 1) & 1;
+          if (a_ready) mbar_wait(&a_ready[kb], 0);
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = a_base + kb * 16384, sb = RB + s * FS_BSTAGE;
@@ -294,13 +286,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       mbar_wait(xfull, 0);
       tc_fence_after();
       FS_STAMP(18);
-      gemm(R1, nk0, acc0);            // L1: X W0^T
+      gemm(R1, nk0, acc0, nullptr);   // L1: X W0^T
       umma_commit(accf0);
       FS_STAMP(19);
-      mbar_wait(h1r, 0);
-      tc_fence_after();
       FS_STAMP(20);
-      gemm(R0, nkH, acc1);            // L2: H1 W1^T
+      gemm(R0, nkH, acc1, h1r);       // L2: H1 W1^T
       umma_commit(accf1);
       FS_STAMP(21);
       // ---- head forward: out[128 x 16] = H2 (W2_hi + W2_lo); A = H2 K-major, B = W2^T K-major, N = 16
@@ -344,10 +334,10 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
         umma_commit(bwdf);
       }
       FS_STAMP(25);
-      mbar_wait(dz2r, 0);
-      tc_fence_after();
       FS_STAMP(22);
-      gemm(R1, nkH, acc0);            // dH1: dZ2 W1
+      // accumulates into acc1: every worker warp has read the head / dW2 columns of acc1 before its first
+      // arrival on dz2r[0], while acc0 (dA2) is still being drained by the dZ2 epilogue
+      gemm(R1, nkH, acc1, dz2r);      // dH1: dZ2 W1
       umma_commit(dh1f);
       FS_STAMP(23);
     }
@@ -387,23 +377,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     // ---- everything below reads what the previous optimizer step wrote (PDL: see common.cuh) -------
     griddep_wait();
     if (wt == 0) griddep_launch();
-    // ---- small operands: biases, head bias / log_std, head kernel as bf16 hi/lo (transposed) -----
+    // ---- small operands: biases, head bias / log_std, head kernel^T image (bf16 hi / lo, swizzled) --
     for (int i = wt; i < H; i += FS_WORKERS) { bias_s[i] = __ldcg(G.b0 + i); bias_s[256 + i] = __ldcg(G.b1 + i); }
     if (wt < 16) hb[wt] = wt < aout ? __ldcg(G.b2 + wt) : 0.f;
     else if (wt < 32) hb[wt] = (net == 0 && wt - 16 < aout) ? __ldcg(p.log_std + wt - 16) : 0.f;
-    for (int c = wt; c < H; c += FS_WORKERS) {
-      float wv[FS_AP];
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) wv[j] = j < aout ? __ldcg(G.w2 + c * aout + j) : 0.f;
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) {
-        uint32_t hi, lo;
-        split_bf16(wv[j], hi, lo);
-        const uint32_t off = sw16_off(j, c);
-        sts_u16(W2T + off, hi);
-        sts_u16(W2T + 8192 + off, lo);
-      }
-    }
+    for (int i = wt; i < 1024; i += FS_WORKERS) sts128(W2T + i * 16, __ldcg(G.w2img + i));
     cp_async_wait<0>();
     fence_proxy_async_smem();
     mbar_arrive(xfull);
@@ -414,15 +392,19 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     mbar_wait(accf0, 0);
     tc_fence_after();
     if (wt == 0) FS_STAMP(2);
-    epilogue_act(acc0, R0, bias_s, act, erow, q, hf * (H >> 1), H >> 1);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(h1r);
+    for (int b = 0; b < nkH; ++b) {
+      epilogue_act(acc0, R0, bias_s, act, erow, q, b * 64 + hf * 32, 32);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h1r[b]);
+    }
     if (wt == 0) FS_STAMP(3);
     if (ww == 0 && lane == 0) {
-      mbar_wait(h1r, 0);
-      for (int s = 0; s < nkH; ++s) tma_store_2d(R0 + s * 16384, &G.tm_h1, s * 64, tile * 128);
+      for (int b = 0; b < nkH; ++b) {
+        mbar_wait(&h1r[b], 0);
+        tma_store_2d(R0 + b * 16384, &G.tm_h1, b * 64, tile * 128);
+      }
       tma_store_commit();
     }
 
@@ -544,15 +526,19 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
         for (int j = 0; j < FS_AP; ++j) if (j < aout) part[G.po_w2 + c * aout + j] = dw[j];
       }
     }
-    epilogue_dact(acc0, R1, R1, cs, act, erow, q, hf * (H >> 1), H >> 1);     // in place: H2 -> dZ2
-    fence_proxy_async_smem();
-    tc_fence_before();                                             // acc0 drained before the dH1 MMAs overwrite it
-    __syncwarp();
-    if (lane == 0) mbar_arrive(dz2r);
+    for (int b = 0; b < nkH; ++b) {
+      epilogue_dact(acc0, R1, R1, cs, act, erow, q, b * 64 + hf * 32, 32);        // in place: H2 -> dZ2
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dz2r[b]);
+    }
     if (wt == 0) FS_STAMP(9);
     if (ww == 0 && lane == 0) {
-      mbar_wait(dz2r, 0);
-      for (int s = 0; s < nkH; ++s) tma_store_2d(R1 + s * 16384, &G.tm_dz2, s * 64, tile * 128);
+      for (int b = 0; b < nkH; ++b) {
+        mbar_wait(&dz2r[b], 0);
+        tma_store_2d(R1 + b * 16384, &G.tm_dz2, b * 64, tile * 128);
+      }
       tma_store_commit();
     }
     worker_bar();                                                  // cs complete
@@ -565,7 +551,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     if (wt == 0) FS_STAMP(10);
     if (ww == 0 && lane == 0) tma_store_wait_read0();              // ... nor by the dZ2 TMA store
     worker_bar();                                                  // also: db1 reads of cs are done
-    epilogue_dact(acc0, R0, R1, cs, act, erow, q, hf * (H >> 1), H >> 1);
+    epilogue_dact(acc1, R0, R1, cs, act, erow, q, hf * (H >> 1), H >> 1);
     fence_proxy_async_smem();
     worker_bar();
     if (wt == 0) FS_STAMP(11);
@@ -575,7 +561,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     }
     for (int c = wt; c < H; c += FS_WORKERS)
       G.colsum[static_cast<size_t>(tile) * H + c] = (cs[c] + cs[256 + c]) + (cs[512 + c] + cs[768 + c]);
-    if (ww == 0 && lane == 0) tma_store_wait_all0();               // all bulk stores complete before the CTA exits
+    if (ww == 0 && lane == 0) tma_store_wait_read0();              // smem may be released once the bulk stores have read it;
+                                                                   // their global writes complete with the grid
     if (wt == 0) FS_STAMP(12);
   }
 

@@ -26,6 +26,7 @@
 #include "minppo_internal.h"
 #include "umma_gemm.cuh"
 #include "fused_step.cuh"
+#include "dwopt.cuh"
 
 namespace minppo {
 
@@ -204,6 +205,7 @@ struct NetBufs {
   std::vector<__nv_bfloat16*> wt;      // wt[l],  l = 0..L-1 [H][Kp_l]   (kernel^T)
   std::vector<__nv_bfloat16*> wn;      // wn[l],  l = 1..L-1 [H][H]      (kernel as stored)
   std::vector<float*> dw_part;         // dw_part[l], l = 0..L-1 [S][in_l][H]
+  uint8_t* w2img;                      // head kernel^T bf16 hi / lo image (16 KB, fused path)
   std::vector<float*> colsum;          // colsum[l],  l = 1..L-1 [m_tiles][H]  -> bias grad of layer l-1
   std::vector<CUtensorMap> m_act_k, m_act_mn, m_dz_k, m_dz_mn, m_wt, m_wn, m_dw;
 };
@@ -235,6 +237,7 @@ struct minppo_ctx {
   long long* trace;           // debug cycle stamps of the fused kernel [2*m_tiles][32]
   bool trace_on;
   bool pdl;                   // programmatic dependent launch between step kernels (MINPPO_PDL=0 disables)
+  bool merged_opt;            // dW GEMM + reduction + Adam in one launch (MINPPO_SPLIT_OPT=1 disables)
   int skip_mask;              // debug (MINPPO_SKIP): 1 = no fused step, 2 = no dW GEMM, 4 = no optimizer (timing ablation only)
   int32_t *perms, *rowidx, *counts;
   void* perm_ws;
@@ -318,6 +321,9 @@ static int init_kernel_attrs() {
   CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_PARTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   if (head_loss_init()) { set_error("head_loss_init failed"); return MINPPO_ERR_CUDA; }
   CK(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(dwopt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(dwopt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(dwopt_kernel<DWOPT_MAX_EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   done = true;
   return 0;
 }
@@ -340,13 +346,13 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
     ol.offset = static_cast<int>(lf.offset);
     ol.cols = static_cast<int>(lf.cols);
     ol.grad_bias = 0.f;
-    ol.img_t = nullptr; ol.img_n = nullptr; ol.ld_t = 0; ol.ld_n = 0;
+    ol.img_t = nullptr; ol.img_n = nullptr; ol.ld_t = 0; ol.ld_n = 0; ol.img_w2 = nullptr;
     if (lf.net == 2) {                         // log_std
       ol.grad_src = c->head_part; ol.src_offset = c->po_logstd; ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
       ol.grad_bias = cfg.rank == 0 ? -static_cast<float>(cfg.ent_coef) : 0.f;
     } else if (lf.layer == L) {                // output heads
       ol.grad_src = c->head_part; ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
-      if (lf.is_kernel) ol.src_offset = lf.net == 0 ? c->po_w3a : c->po_w3c;
+      if (lf.is_kernel) { ol.src_offset = lf.net == 0 ? c->po_w3a : c->po_w3c; ol.img_w2 = c->fused ? c->net[lf.net].w2img : nullptr; }
       else ol.src_offset = lf.net == 0 ? c->po_b3a : c->po_b3c;
     } else if (lf.is_kernel) {                 // hidden kernels: split-K partials of the dW GEMM
       const int in_l = lf.layer == 0 ? c->D : H;
@@ -408,7 +414,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
       g.tm_h1 = nb.m_act_k[1]; g.tm_dz2 = nb.m_dz_k[2]; g.tm_dz1 = nb.m_dz_k[1];
       g.b0 = u.params + find_leaf(c, net, 0, 0).offset;
       g.b1 = u.params + find_leaf(c, net, 1, 0).offset;
-      g.w2 = u.params + find_leaf(c, net, 2, 1).offset;
+      g.w2img = reinterpret_cast<const uint4*>(nb.w2img);
       g.b2 = u.params + find_leaf(c, net, 2, 0).offset;
       g.colsum = nb.colsum[1];
       g.act = act_kind(c, net);
@@ -503,11 +509,15 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     c->launches++;
   }
   }  // !fused
-  // weight gradients: dW_l = act[l]^T dz[l+1], split-K over minibatch rows
-  if (!(c->skip_mask & 2)) {
-    GemmParams p;
-    memset(&p, 0, sizeof(p));
-    int ng = 0, cta = 0;
+  // weight gradients dW_l = act[l]^T dz[l+1] (split-K over minibatch rows), then the optimizer.
+  // Default: ONE launch (dwopt.cuh).  MINPPO_SPLIT_OPT=1, a grid that does not fit one CTA per SM or
+  // the timing ablation fall back to the two-launch sequence (GEMM kernel, opt_kernel).
+  DwOptParams dp;
+  memset(&dp, 0, sizeof(dp));
+  GemmParams& p = dp.gemm;
+  int cta = 0;
+  {
+    int ng = 0;
     for (int net = 0; net < 2; ++net) {
       NetBufs& nb = c->net[net];
       for (int l = 0; l < L; ++l) {
@@ -525,17 +535,37 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
       }
     }
     p.ngroups = ng;
+  }
+  OptArgs& o = dp.opt;
+  fill_opt_args(c, u, &o);
+  o.losses_out = u.losses_out ? u.losses_out + static_cast<size_t>(s) * 4 : c->losses_scratch;
+  o.gnorm_out = c->gnorms + s;
+  const bool sharded = c->cfg.world_size > 1;
+  const bool merged = c->merged_opt && c->skip_mask == 0 && cta <= c->sm_count && c->P <= dwopt_max_params(c->sm_count);
+  if (merged) {
+    dp.gemm_ctas = cta;
+    o.do_reduce = 1; o.do_apply = sharded ? 0 : 1;
+    {
+      PROF(PC_DW_GEMM);
+      const cudaError_t e = dwopt_launch(dp, c->sm_count, stream, pdl);
+      if (e != cudaSuccess) { set_error("dwopt launch failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
+      c->launches++;
+    }
+    if (sharded) {
+      { PROF(PC_ALLREDUCE); RET(nccl_allreduce(c, c->gflat, static_cast<size_t>(c->P) + 2, stream)); }
+      o.do_reduce = 0; o.do_apply = 1;
+      { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream, pdl)); }
+      c->launches += 2;
+    }
+    return 0;
+  }
+  if (!(c->skip_mask & 2)) {
     PROF(PC_DW_GEMM);
     RET(launch_gemm<EPI_PARTIAL>(p, cta, stream, pdl));
     c->launches++;
   }
-  // optimizer
   if (!(c->skip_mask & 4)) {
-    OptArgs o;
-    fill_opt_args(c, u, &o);
-    o.losses_out = u.losses_out ? u.losses_out + static_cast<size_t>(s) * 4 : c->losses_scratch;
-    o.gnorm_out = c->gnorms + s;
-    if (c->cfg.world_size == 1) {
+    if (!sharded) {
       o.do_reduce = 1; o.do_apply = 1;
       PROF(PC_OPT);
       RET(opt_launch(o, c->opt_blocks, stream, pdl));
@@ -545,7 +575,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
       { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream, pdl)); }
       { PROF(PC_ALLREDUCE); RET(nccl_allreduce(c, c->gflat, static_cast<size_t>(c->P) + 2, stream)); }
       o.do_reduce = 0; o.do_apply = 1;
-      { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream)); }
+      { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream, pdl)); }
       c->launches += 3;
     }
   }
@@ -755,6 +785,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   ALLOC(c->trace, static_cast<size_t>(2 * c->m_tiles) * 32);
   c->trace_on = getenv("MINPPO_TRACE") != nullptr;
   c->pdl = !(getenv("MINPPO_PDL") && atoi(getenv("MINPPO_PDL")) == 0);
+  c->merged_opt = !(getenv("MINPPO_SPLIT_OPT") && atoi(getenv("MINPPO_SPLIT_OPT")) != 0);
   c->skip_mask = getenv("MINPPO_SKIP") ? atoi(getenv("MINPPO_SKIP")) : 0;
   ALLOC(c->perms, static_cast<size_t>(c->E) * c->B);
   ALLOC(c->rowidx, static_cast<size_t>(EM) * c->cap);
@@ -768,6 +799,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     NetBufs& nb = c->net[net];
     nb.act.assign(L + 1, nullptr); nb.dz.assign(L + 1, nullptr); nb.wt.assign(L, nullptr); nb.wn.assign(L, nullptr);
     nb.dw_part.assign(L, nullptr); nb.colsum.assign(L, nullptr);
+    ALLOC(nb.w2img, 16384);
     nb.m_act_k.resize(L + 1); nb.m_act_mn.resize(L + 1); nb.m_dz_k.resize(L + 1); nb.m_dz_mn.resize(L + 1);
     nb.m_wt.resize(L); nb.m_wn.resize(L); nb.m_dw.resize(L);
     for (int l = 1; l <= L; ++l) {

@@ -73,6 +73,8 @@ struct OptLeaf {
   __nv_bfloat16* img_t;          // bf16 image [out][ld_t] (transposed; forward GEMM B operand) or null
   __nv_bfloat16* img_n;          // bf16 image [in][ld_n]  (dX GEMM B operand) or null
   int ld_t, ld_n;
+  uint8_t* img_w2;               // output-head kernels: 16 KB bf16 hi / lo image of kernel^T in the fused kernel's
+                                 // shared-memory layout (fused_step.cuh FS_W2T), or null
 };
 struct OptArgs {
   OptLeaf leaf[MINPPO_MAX_LEAVES];

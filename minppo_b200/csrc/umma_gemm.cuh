@@ -88,9 +88,9 @@ MINPPO_DEVINL float warp_colsum32(float (&v)[32]) {
   return v[0];   // column index == lane (bit b of lane selected the upper half at step b)
 }
 
+// The whole CTA (GEMM_THREADS threads) calls this; it returns after the TMEM columns are released.
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
+MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B: 1024-B aligned tiles
   uint8_t* aligned = smem_raw + (base - raw);
@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
         for (int c0 = 0; c0 < N; c0 += 32) tma_store_3d(base + (c0 >> 5) * 16384, &G.tmC, c0, m_tile * GEMM_BM, split);
         tma_store_commit();
         tma_store_wait_all0();
+        fence_proxy_async_global();
       }
     }
     if (EPI == EPI_DACT) {
@@ -331,6 +332,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  umma_gemm_body<EPI>(p, smem_raw);
 }
 
 }  // namespace minppo

@@ -19,8 +19,8 @@ if has tests; then
 fi
 if has ablate; then
   : > gpurun_out/ablate.log
-  for cfg in "MINPPO_PDL=1" "MINPPO_PDL=0" "MINPPO_PDL=0 MINPPO_SKIP=6" "MINPPO_PDL=0 MINPPO_SKIP=5" "MINPPO_PDL=0 MINPPO_SKIP=3" \
-             "MINPPO_PDL=1 MINPPO_SKIP=6" "MINPPO_PDL=1 MINPPO_SKIP=4" "MINPPO_PDL=1 MINPPO_SKIP=2" $EXTRA_ABLATE; do
+  for cfg in "MINPPO_PDL=1" "MINPPO_PDL=0" "MINPPO_PDL=1 MINPPO_SPLIT_OPT=1" "MINPPO_PDL=1 MINPPO_SKIP=6" \
+             "MINPPO_PDL=1 MINPPO_SKIP=5" "MINPPO_PDL=1 MINPPO_SKIP=3" $EXTRA_ABLATE; do
     echo "## $cfg" >> gpurun_out/ablate.log
     env $cfg timeout 600 python bench.py --quick --steps 10 --warmup 3 2>&1 | tail -n 2 >> gpurun_out/ablate.log
   done
@@ -45,7 +45,7 @@ if has ncu; then
 fi
 if has ncufull; then
   timeout 1500 ncu --set full --clock-control none --import-source on \
-    -k regex:"umma_gemm_kernel|opt_kernel|fused_step_kernel" -s 60 -c 6 -f -o gpurun_out/prof_full \
+    -k regex:"umma_gemm_kernel|opt_kernel|fused_step_kernel" -s 40 -c 4 -f -o gpurun_out/prof_full \
     python bench.py --quick --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
   echo "exit $?" >> gpurun_out/ncu_full.log
   tail -n 3 gpurun_out/ncu_full.log
