@@ -17,57 +17,39 @@
 
 namespace minppo {
 
-// EPT elements per thread, kept in registers across the grid barrier.  Elements are dealt to
-// warps in 32-element chunks, round-robin over BLOCKS (chunk = k*G*32 + warp*G + block), so that
-// the few leaves with many partials (output heads) are spread over the whole grid while every
-// warp still reads 128 contiguous bytes per partial.
-template <int EPT>
-__global__ void __launch_bounds__(OPT_THREADS, 3) opt_kernel(const OptArgs a) {
+// Stand-alone optimizer launch: used when the merged dW + optimizer kernel (dwopt.cuh) does not apply --
+// env-sharded ranks (apply only, after the all-reduce of gflat) and the two-launch fallback.
+// Plain strided loops: the gradient lives in gflat between the phases.
+__global__ void __launch_bounds__(OPT_THREADS, 2) opt_kernel(const OptArgs a) {
   __shared__ float scratch[32];
   __shared__ float s_bcast[4];
+  __shared__ LeafTab T;
   const int P = a.P;
   const int G = gridDim.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  leaf_tab_build(T, a, threadIdx.x, OPT_THREADS);
+  __syncthreads();
+  const int first = static_cast<int>(blockIdx.x) * OPT_THREADS + static_cast<int>(threadIdx.x);
+  const int stride = G * OPT_THREADS;
 
-  const int count = a.do_apply ? __ldcg(a.count) : 0;            // Adam step count BEFORE this step
+  const int count = a.do_apply ? __ldcg(a.count) : 0;      // Adam step count BEFORE this step
   float ent = a.entropy_const;                             // A * (0.5 + 0.5 log 2pi) + sum log|scale|
   if (a.do_apply && blockIdx.x == 0 && threadIdx.x == 0 && a.losses_out) {
     // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the barrier)
     for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(__ldcg(a.params + a.off_logstd + j))));
   }
-
-  float g[EPT], pv[EPT], mv[EPT], nv[EPT];
-  float ss = 0.f;
-  // optimizer state of this thread's elements: independent of the gradient producers, so it is
-  // fetched before the PDL wait (nothing else writes params / mu / nu between two optimizer steps)
-#pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int i = ((k * (OPT_THREADS / 32) + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
-    pv[k] = 0.f; mv[k] = 0.f; nv[k] = 0.f;
-    if (i < P && a.do_apply) { pv[k] = __ldcg(a.params + i); mv[k] = __ldcg(a.mu + i); nv[k] = __ldcg(a.nu + i); }
-  }
   griddep_wait();
   if (threadIdx.x == 0) griddep_launch();
-#pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int i = ((k * (OPT_THREADS / 32) + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
-    g[k] = 0.f;
-    if (i < P) {
-      if (a.do_reduce) {
-        const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
-        g[k] = sum_partials(L.grad_src + L.src_offset + (i - L.offset), L.nparts, L.part_stride) + L.grad_bias;
-        if (!a.do_apply || a.keep_gflat) a.gflat[i] = g[k];
-      } else {
-        g[k] = __ldcg(a.gflat + i);
-      }
-      if (a.do_apply) ss = fmaf(g[k], g[k], ss);
-    } else if (i < P + 2 && a.do_reduce) {
-      a.gflat[i] = sum_partials(a.loss_src + a.loss_src_offset + (i - P), a.loss_nparts, a.loss_part_stride);
-    }
+  float ss = 0.f;
+  if (a.do_reduce) {
+    ss = reduce_leaves<false>(a, T, first, stride);
+    ss += reduce_leaves<true>(a, T, first, stride);
+  } else {
+#pragma unroll 1
+    for (int i = first; i < P; i += stride) { const float g = __ldcg(a.gflat + i); ss = fmaf(g, g, ss); }
   }
   if (!a.do_apply) return;
 
-  const float bs = block_sum(ss, scratch);
+  const float bs = block_sum<OPT_THREADS>(ss, scratch);
   if (threadIdx.x == 0) a.block_ss[blockIdx.x] = bs;
   grid_barrier(a.barrier, a.err_flag);
   if (threadIdx.x < 32) {
@@ -76,38 +58,12 @@ __global__ void __launch_bounds__(OPT_THREADS, 3) opt_kernel(const OptArgs a) {
     s = warp_sum(s);
     if (threadIdx.x == 0) s_bcast[0] = sqrtf(s);
   }
-  if (threadIdx.x == 32) {                                 // per-step scalars, once per block
-    float lr;                                              // train.py:98-101 (annealed) or opt.lr
-    if (a.anneal) {
-      const float frac = 1.0f - static_cast<float>(count / a.anneal_div) / static_cast<float>(a.num_updates);
-      lr = a.lr * frac;
-    } else {
-      lr = a.lr;
-    }
-    const float cnt1 = static_cast<float>(count + 1);
-    s_bcast[1] = lr;
-    s_bcast[2] = 1.0f - powf(a.b1, cnt1);
-    s_bcast[3] = 1.0f - powf(a.b2, cnt1);
-  }
+  if (threadIdx.x == 32) step_scalars(a, count, s_bcast[1], s_bcast[2], s_bcast[3]);
   __syncthreads();
-  const float gnorm = s_bcast[0];
-  const bool trigger = gnorm < a.max_norm;                 // optax.clip_by_global_norm
-  const float lr = s_bcast[1], c1 = s_bcast[2], c2 = s_bcast[3];
-#pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int i = ((k * (OPT_THREADS / 32) + warp) * G + static_cast<int>(blockIdx.x)) * 32 + lane;
-    if (i >= P) continue;
-    float gg = g[k];
-    if (!trigger) gg = (gg / gnorm) * a.max_norm;
-    const float mu = a.one_minus_b1 * gg + a.b1 * mv[k];
-    const float nu = a.one_minus_b2 * (gg * gg) + a.b2 * nv[k];
-    const float u = (mu / c1) / (sqrtf(nu / c2 + a.eps_root) + a.eps);
-    const float p = pv[k] + (-lr) * u;
-    a.params[i] = p;
-    a.mu[i] = mu;
-    a.nu[i] = nu;
-    write_images(a.leaf[find_leaf_idx(a, i)], i, p);
-  }
+  AdamScalars sc;
+  sc.gnorm = s_bcast[0]; sc.lr = s_bcast[1]; sc.c1 = s_bcast[2]; sc.c2 = s_bcast[3];
+  sc.trigger = sc.gnorm < a.max_norm;                      // optax.clip_by_global_norm
+  apply_adam(a, T, sc, first, stride);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *a.count = count + 1;
     if (a.losses_out) {
@@ -118,7 +74,7 @@ __global__ void __launch_bounds__(OPT_THREADS, 3) opt_kernel(const OptArgs a) {
       a.losses_out[1] = value_loss;
       a.losses_out[2] = actor_loss;
       a.losses_out[3] = ent;
-      if (a.gnorm_out) *a.gnorm_out = gnorm;
+      if (a.gnorm_out) *a.gnorm_out = sc.gnorm;
     }
   }
 }
@@ -150,16 +106,10 @@ __global__ void weight_images_kernel(const OptArgs a) {
   }
 }
 
-int opt_max_params(int blocks) { return blocks * OPT_THREADS * OPT_EPT - 2; }
+int opt_max_params(int) { return 0x7fffffff - 2; }      // strided loops: no per-launch limit
 
 int opt_launch(const OptArgs& a, int blocks, cudaStream_t stream, bool pdl) {
-  if (a.P > opt_max_params(blocks)) return MINPPO_ERR_UNSUPPORTED;   // single sweep: global norm needs all elements
-  const long long per_thread = (static_cast<long long>(a.P) + 2 + static_cast<long long>(blocks) * OPT_THREADS - 1) /
-                               (static_cast<long long>(blocks) * OPT_THREADS);
-  cudaError_t e;
-  if (per_thread <= 2) e = launch_kernel(opt_kernel<2>, blocks, OPT_THREADS, 0, stream, pdl, a);
-  else if (per_thread <= 4) e = launch_kernel(opt_kernel<4>, blocks, OPT_THREADS, 0, stream, pdl, a);
-  else e = launch_kernel(opt_kernel<OPT_EPT>, blocks, OPT_THREADS, 0, stream, pdl, a);
+  const cudaError_t e = launch_kernel(opt_kernel, blocks, OPT_THREADS, 0, stream, pdl, a);
   return e == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }
 

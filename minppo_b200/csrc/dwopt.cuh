@@ -8,10 +8,12 @@
 //            CTAs [gemm_ctas, grid): meanwhile sum the per-tile partials of the SMALL leaves (biases, output
 //            heads, log_std: one partial per 128-row tile of the fused step kernel) and the loss sums -> gflat.
 //   barrier
-//   phase 2  every thread owns <= EPT arena elements: fixed-order sum of the split-K partials (bitwise
-//            reproducible, no atomics), optimizer state fetched alongside, sum of squares -> per-block partial.
+//   phase 2  fixed-order sum of the split-K partials of the hidden kernels -> gflat (bitwise reproducible, no
+//            atomics; 16-byte loads, 16 partials in flight per thread), sum of squares -> per-block partial.
 //   barrier
 //   phase 3  clip scale, Adam, params / mu / nu in place, bf16 weight images for the next step's GEMMs.
+// The phases are plain strided loops (no per-element unrolling): an earlier fully unrolled version was
+// 15k SASS instructions and spent a third of its time on instruction-cache misses.
 // With env-sharded ranks (do_apply == 0) the kernel stops after phase 2 with the local gradient SUM in gflat;
 // the all-reduce and opt_kernel (adam.cu, apply only) follow.
 #pragma once
@@ -27,55 +29,19 @@ struct alignas(64) DwOptParams {
   int gemm_ctas;                 // CTAs [0, gemm_ctas) run the GEMM; the others pre-reduce the small leaves
 };
 
-MINPPO_DEVINL bool leaf_is_big(const OptLeaf& L) { return L.img_t != nullptr || L.img_n != nullptr; }   // hidden kernels
-
-// fixed-order sum of `nparts` partials, 16 loads in flight
-MINPPO_DEVINL float sum_partials16(const float* __restrict__ src, int nparts, size_t stride) {
-  float acc = 0.f;
-  int p = 0;
-  for (; p + 16 <= nparts; p += 16) {
-    float v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + static_cast<size_t>(p + u) * stride);
-#pragma unroll
-    for (int u = 0; u < 16; ++u) acc += v[u];
-  }
-  for (; p < nparts; ++p) acc += __ldcg(src + static_cast<size_t>(p) * stride);
-  return acc;
-}
-
-// Job list of the extra CTAs: every element of every small leaf, then the two loss sums.
-MINPPO_DEVINL void reduce_small_leaves(const OptArgs& a, int first, int stride) {
-  int n_small = 2;
-  for (int l = 0; l < a.nleaves; ++l)
-    if (!leaf_is_big(a.leaf[l])) n_small += (l + 1 < a.nleaves ? a.leaf[l + 1].offset : a.P) - a.leaf[l].offset;
-  for (int j = first; j < n_small; j += stride) {
-    int x = j, l = 0;
-    for (; l < a.nleaves; ++l) {
-      if (leaf_is_big(a.leaf[l])) continue;
-      const int n = (l + 1 < a.nleaves ? a.leaf[l + 1].offset : a.P) - a.leaf[l].offset;
-      if (x < n) break;
-      x -= n;
-    }
-    if (l < a.nleaves) {
-      const OptLeaf& L = a.leaf[l];
-      a.gflat[L.offset + x] = sum_partials16(L.grad_src + L.src_offset + x, L.nparts, L.part_stride) + L.grad_bias;
-    } else {
-      a.gflat[a.P + x] = sum_partials16(a.loss_src + a.loss_src_offset + x, a.loss_nparts, a.loss_part_stride);
-    }
-  }
-}
-
-template <int EPT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_constant__ DwOptParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float scratch[32];
   __shared__ float s_bcast[4];
+  __shared__ LeafTab T;
   const OptArgs& a = p.opt;
   const int P = a.P;
   const int G = static_cast<int>(gridDim.x), NT = GEMM_THREADS;
   const int b = static_cast<int>(blockIdx.x), t = static_cast<int>(threadIdx.x);
   const bool has_extra = p.gemm_ctas < G;
+  float ss = 0.f;
+  leaf_tab_build(T, a, t, NT);
+  __syncthreads();
 
   // ---- phase 1 ----------------------------------------------------------------------------------
   if (b < p.gemm_ctas) {
@@ -83,7 +49,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
   } else {
     griddep_wait();                                      // the small-leaf partials come from the fused step kernel
     if (t == 0) griddep_launch();
-    reduce_small_leaves(a, (b - p.gemm_ctas) * NT + t, (G - p.gemm_ctas) * NT);
+    ss = reduce_leaves<false>(a, T, (b - p.gemm_ctas) * NT + t, (G - p.gemm_ctas) * NT);
   }
   const int count = a.do_apply ? __ldcg(a.count) : 0;   // Adam step count BEFORE this step
   float ent = a.entropy_const;                           // A * (0.5 + 0.5 log 2pi) + sum log|scale|
@@ -94,33 +60,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
   grid_barrier(a.barrier, a.err_flag);
 
   // ---- phase 2 ----------------------------------------------------------------------------------
-  float g[EPT], pv[EPT], mv[EPT], nv[EPT];
-  float ss = 0.f;
-#pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int i = (k * G + b) * NT + t;
-    pv[k] = 0.f; mv[k] = 0.f; nv[k] = 0.f;
-    if (i < P && a.do_apply) { pv[k] = __ldcg(a.params + i); mv[k] = __ldcg(a.mu + i); nv[k] = __ldcg(a.nu + i); }
-  }
-#pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int i = (k * G + b) * NT + t;
-    g[k] = 0.f;
-    if (i < P) {
-      const OptLeaf& L = a.leaf[find_leaf_idx(a, i)];
-      if (leaf_is_big(L) || !has_extra) {
-        g[k] = sum_partials16(L.grad_src + L.src_offset + (i - L.offset), L.nparts, L.part_stride) + L.grad_bias;
-        if (!a.do_apply || a.keep_gflat) a.gflat[i] = g[k];
-      } else {
-        g[k] = __ldcg(a.gflat + i);
-      }
-      ss = fmaf(g[k], g[k], ss);
-    } else if (i < P + 2 && !has_extra) {
-      a.gflat[i] = sum_partials16(a.loss_src + a.loss_src_offset + (i - P), a.loss_nparts, a.loss_part_stride);
-    }
-  }
+  if (!has_extra) ss += reduce_leaves<false>(a, T, b * NT + t, G * NT);
+  ss += reduce_leaves<true>(a, T, b * NT + t, G * NT);
   if (!a.do_apply) return;
-
   const float bs = block_sum<GEMM_THREADS>(ss, scratch);
   if (t == 0) a.block_ss[b] = bs;
   grid_barrier(a.barrier, a.err_flag);
@@ -137,16 +79,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
   AdamScalars sc;
   sc.gnorm = s_bcast[0]; sc.lr = s_bcast[1]; sc.c1 = s_bcast[2]; sc.c2 = s_bcast[3];
   sc.trigger = sc.gnorm < a.max_norm;                    // optax.clip_by_global_norm
-#pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int i = (k * G + b) * NT + t;
-    if (i >= P) continue;
-    adam_element(a, sc, g[k], pv[k], mv[k], nv[k]);
-    a.params[i] = pv[k];
-    a.mu[i] = mv[k];
-    a.nu[i] = nv[k];
-    write_images(a.leaf[find_leaf_idx(a, i)], i, pv[k]);
-  }
+  apply_adam(a, T, sc, b * NT + t, G * NT);
   if (b == 0 && t == 0) {
     *a.count = count + 1;
     if (a.losses_out) {
@@ -162,15 +95,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
   }
 }
 
-constexpr int DWOPT_MAX_EPT = 12;
-inline long long dwopt_max_params(int grid) { return static_cast<long long>(grid) * GEMM_THREADS * DWOPT_MAX_EPT - 2; }
-
 inline cudaError_t dwopt_launch(const DwOptParams& p, int grid, cudaStream_t stream, bool pdl) {
-  const long long per_thread = (static_cast<long long>(p.opt.P) + 2 + static_cast<long long>(grid) * GEMM_THREADS - 1) /
-                               (static_cast<long long>(grid) * GEMM_THREADS);
-  if (per_thread <= 4) return launch_kernel(dwopt_kernel<4>, grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
-  if (per_thread <= 8) return launch_kernel(dwopt_kernel<8>, grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
-  return launch_kernel(dwopt_kernel<DWOPT_MAX_EPT>, grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
+  return launch_kernel(dwopt_kernel, grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
 }
 
 }  // namespace minppo

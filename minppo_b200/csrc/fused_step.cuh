@@ -39,9 +39,8 @@ constexpr int FS_BSTAGE = 32768;
 constexpr int FS_W2T = 196608;                          // head kernel^T bf16 [16][H] SW128: hi (+0), lo (+8192)
 constexpr int FS_GT = FS_W2T + 16384;                   // g^T bf16 [16][128] SW128: hi (+0), lo (+4096)
 constexpr int FS_BIAS = FS_GT + 8192;                   // [2][256] f32
-constexpr int FS_HB = FS_BIAS + 2048;                   // head bias [16], log_std [16] f32
-constexpr int FS_CS = FS_HB + 128;                      // [4][256] f32 column-sum scratch
-constexpr int FS_RED = FS_CS + 4096;                    // [8][40] f32
+constexpr int FS_HB = FS_BIAS + 2048;                   // f32: head bias [16], log_std [16], 1/scale [16], log-det [1]
+constexpr int FS_RED = FS_HB + 256;                     // [8][40] f32
 constexpr int FS_BARS = FS_RED + 8 * 40 * 4;            // mbarriers + tmem slot
 constexpr int FS_SMEM_BYTES = FS_BARS + 256 + 1024;     // + alignment slack
 
@@ -56,10 +55,9 @@ struct alignas(64) FusedNet {
   const float* b1;
   const uint4* w2img;            // head kernel^T as bf16 hi / lo, the 16 KB smem image of FS_W2T (written by the optimizer)
   const float* b2;               // head bias [aout]
-  float* colsum;                 // [m_tiles][H] column sums of dZ1 (bias gradient of layer 0)
   int act;                       // ACT_*
   int aout;                      // A (actor) or 1 (critic)
-  int po_w2, po_b2, po_bh, po_loss;   // offsets of this net's fields inside a head partial
+  int po_w2, po_b2, po_loss;     // offsets of this net's fields inside a head partial
 };
 
 struct alignas(64) FusedParams {
@@ -152,12 +150,12 @@ MINPPO_DEVINL void epilogue_act(uint32_t tmem_acc, uint32_t dst_base, const floa
 }
 
 // dZ = acc * f'(h): h read from `h_base`, bf16 result written to `dst_base` (may alias h_base:
-// every thread touches only its own 16-byte chunks); column sums of the stored values -> cs.
+// every thread touches only its own 16-byte chunks).  The bias gradients (column sums of dZ) are
+// not formed here: the weight-gradient GEMM gets them from the tensor core as ones x dZ.
 template <int ACT>
-MINPPO_DEVINL void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, float* cs, int row, int q,
-                                   int col0, int ncols) {
+MINPPO_DEVINL void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, int row, int q, int col0,
+                                   int ncols) {
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-  const int lane = static_cast<int>(lane_id());
   for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
     float v[32];
     tmem_ld_32x32(taddr + c0, v);
@@ -172,21 +170,16 @@ MINPPO_DEVINL void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base, uint32_t 
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int e = 8 * j + 2 * t;
-        v[e] *= act_deriv_t<ACT>(bf16_lo(hw[t]));
-        v[e + 1] *= act_deriv_t<ACT>(bf16_hi(hw[t]));
-        w[t] = pack_bf16x2(v[e], v[e + 1]);
-        v[e] = bf16_lo(w[t]); v[e + 1] = bf16_hi(w[t]);          // bias gradient sums the stored (rounded) dZ
+        w[t] = pack_bf16x2(v[e] * act_deriv_t<ACT>(bf16_lo(hw[t])), v[e + 1] * act_deriv_t<ACT>(bf16_hi(hw[t])));
       }
       sts128(dst_base + sw_off(row, c0 + 8 * j), make_uint4(w[0], w[1], w[2], w[3]));
     }
-    const float csum = warp_colsum32(v);
-    cs[q * 256 + c0 + lane] = csum;
   }
 }
-MINPPO_DEVINL void epilogue_dact(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, float* cs, int act, int row,
-                                 int q, int col0, int ncols) {
-  if (act == ACT_RELU) epilogue_dact_t<ACT_RELU>(tmem_acc, h_base, dst_base, cs, row, q, col0, ncols);
-  else epilogue_dact_t<ACT_TANH>(tmem_acc, h_base, dst_base, cs, row, q, col0, ncols);
+MINPPO_DEVINL void epilogue_dact(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, int act, int row, int q,
+                                 int col0, int ncols) {
+  if (act == ACT_RELU) epilogue_dact_t<ACT_RELU>(tmem_acc, h_base, dst_base, row, q, col0, ncols);
+  else epilogue_dact_t<ACT_TANH>(tmem_acc, h_base, dst_base, row, q, col0, ncols);
 }
 
 __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_constant__ FusedParams p) {
@@ -195,8 +188,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
   float* bias_s = reinterpret_cast<float*>(sm + FS_BIAS);       // [0..256) layer 0, [256..512) layer 1
-  float* hb = reinterpret_cast<float*>(sm + FS_HB);             // [0..16) head bias, [16..32) log_std
-  float* cs = reinterpret_cast<float*>(sm + FS_CS);
+  float* hb = reinterpret_cast<float*>(sm + FS_HB);             // [0..16) head bias, [16..32) log_std,
+                                                                // [32..48) 1 / scale, [48] sum log|scale|
   float* red = reinterpret_cast<float*>(sm + FS_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + FS_BARS);
   uint64_t* full_bar = bars;            // [2]
@@ -378,10 +371,27 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     griddep_wait();
     if (wt == 0) griddep_launch();
     // ---- small operands: biases, head bias / log_std, head kernel^T image (bf16 hi / lo, swizzled) --
-    for (int i = wt; i < H; i += FS_WORKERS) { bias_s[i] = __ldcg(G.b0 + i); bias_s[256 + i] = __ldcg(G.b1 + i); }
-    if (wt < 16) hb[wt] = wt < aout ? __ldcg(G.b2 + wt) : 0.f;
-    else if (wt < 32) hb[wt] = (net == 0 && wt - 16 < aout) ? __ldcg(p.log_std + wt - 16) : 0.f;
-    for (int i = wt; i < 1024; i += FS_WORKERS) sts128(W2T + i * 16, __ldcg(G.w2img + i));
+    // (all global loads first: the st.shared wrappers are ordering barriers for the compiler)
+    const float b0v = wt < H ? __ldcg(G.b0 + wt) : 0.f;             // H <= 256 == FS_WORKERS
+    const float b1v = wt < H ? __ldcg(G.b1 + wt) : 0.f;
+    float hbv = 0.f;
+    if (wt < 16) hbv = wt < aout ? __ldcg(G.b2 + wt) : 0.f;
+    else if (wt < 32) hbv = (net == 0 && wt - 16 < aout) ? __ldcg(p.log_std + wt - 16) : 0.f;
+    float logdet = 0.f;
+    if (wt == 32 && net == 0) {
+      // distrax: log|det| = sum log|scale|, scale = exp(log_std); summed in index order (train.py:223)
+      float ls[FS_AP];
+#pragma unroll
+      for (int j = 0; j < FS_AP; ++j) ls[j] = j < aout ? __ldcg(p.log_std + j) : 0.f;
+#pragma unroll
+      for (int j = 0; j < FS_AP; ++j) if (j < aout) logdet += logf(fabsf(expf(ls[j])));
+    }
+    for (int i = wt; i < 1024; i += FS_WORKERS) cp_async_16(W2T + i * 16, G.w2img + i);
+    cp_async_commit();
+    if (wt < H) { bias_s[wt] = b0v; bias_s[256 + wt] = b1v; }
+    if (wt < 32) hb[wt] = hbv;
+    if (wt >= 16 && wt < 32) hb[16 + wt] = 1.f / expf(hbv);          // 1 / scale (unused columns: 1)
+    if (wt == 32) hb[48] = logdet;
     cp_async_wait<0>();
     fence_proxy_async_smem();
     mbar_arrive(xfull);
@@ -436,19 +446,18 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
         if (net == 0) {
           // distrax MultivariateNormalDiag: z = (a - loc) * (1/scale); train.py:223, 234-239
           float z[FS_AP], inv_s[FS_AP];
-          float quad = 0.f, logdet = 0.f;
+          float quad = 0.f;
 #pragma unroll
           for (int j = 0; j < FS_AP; ++j) {
             z[j] = 0.f; inv_s[j] = 0.f;
             if (j < aout) {
-              const float scale = expf(hb[16 + j]);
-              inv_s[j] = 1.f / scale;
+              inv_s[j] = hb[32 + j];
               const float mean = out[j] + hb[j];
               z[j] = (actn[j] - mean) * inv_s[j];
               quad += -0.5f * z[j] * z[j] - 0.91893853320467274178f;
-              logdet += logf(fabsf(scale));
             }
           }
+          const float logdet = hb[48];
           const float logp = quad - logdet;
           const float ratio = expf(logp - in0);
           const float adv_mean = adv_sum * inv_n;
@@ -527,7 +536,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       }
     }
     for (int b = 0; b < nkH; ++b) {
-      epilogue_dact(acc0, R1, R1, cs, act, erow, q, b * 64 + hf * 32, 32);        // in place: H2 -> dZ2
+      epilogue_dact(acc0, R1, R1, act, erow, q, b * 64 + hf * 32, 32);            // in place: H2 -> dZ2
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -541,28 +550,24 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       }
       tma_store_commit();
     }
-    worker_bar();                                                  // cs complete
-    for (int c = wt; c < H; c += FS_WORKERS)
-      part[G.po_bh + c] = (cs[c] + cs[256 + c]) + (cs[512 + c] + cs[768 + c]);      // db1 = colsum(dZ2)
 
-    // ---- epilogue 3: dZ1 = acc0 * f'(H1) -> R1 -> TMA store; column sums -> db0 --------------------
+    // ---- epilogue 3: dZ1 = acc1 * f'(H1) -> R1 -> TMA store ------------------------------------------
     mbar_wait(dh1f, 0);                                            // dH1 MMAs done: R1 (dZ2) no longer read by UMMA
     tc_fence_after();
     if (wt == 0) FS_STAMP(10);
     if (ww == 0 && lane == 0) tma_store_wait_read0();              // ... nor by the dZ2 TMA store
-    worker_bar();                                                  // also: db1 reads of cs are done
-    epilogue_dact(acc1, R0, R1, cs, act, erow, q, hf * (H >> 1), H >> 1);
-    fence_proxy_async_smem();
     worker_bar();
+    for (int b = 0; b < nkH; ++b) {                                // 64-column blocks, each stored as soon as it is complete
+      epilogue_dact(acc1, R0, R1, act, erow, q, b * 64 + hf * 32, 32);
+      fence_proxy_async_smem();
+      worker_bar();
+      if (ww == 0 && lane == 0) tma_store_2d(R1 + b * 16384, &G.tm_dz1, b * 64, tile * 128);
+    }
     if (wt == 0) FS_STAMP(11);
     if (ww == 0 && lane == 0) {
-      for (int s = 0; s < nkH; ++s) tma_store_2d(R1 + s * 16384, &G.tm_dz1, s * 64, tile * 128);
       tma_store_commit();
-    }
-    for (int c = wt; c < H; c += FS_WORKERS)
-      G.colsum[static_cast<size_t>(tile) * H + c] = (cs[c] + cs[256 + c]) + (cs[512 + c] + cs[768 + c]);
-    if (ww == 0 && lane == 0) tma_store_wait_read0();              // smem may be released once the bulk stores have read it;
-                                                                   // their global writes complete with the grid
+      tma_store_wait_read0();                                      // smem may be released once the bulk stores have read it;
+    }                                                              // their global writes complete with the grid
     if (wt == 0) FS_STAMP(12);
   }
 

@@ -206,6 +206,7 @@ struct NetBufs {
   std::vector<__nv_bfloat16*> wn;      // wn[l],  l = 1..L-1 [H][H]      (kernel as stored)
   std::vector<float*> dw_part;         // dw_part[l], l = 0..L-1 [S][in_l][H]
   uint8_t* w2img;                      // head kernel^T bf16 hi / lo image (16 KB, fused path)
+  std::vector<float*> dbias;           // dbias[l], l = 0..L-1 [S][H]: bias-gradient partials from the dW GEMM (ones x dz[l+1])
   std::vector<float*> colsum;          // colsum[l],  l = 1..L-1 [m_tiles][H]  -> bias grad of layer l-1
   std::vector<CUtensorMap> m_act_k, m_act_mn, m_dz_k, m_dz_mn, m_wt, m_wn, m_dw;
 };
@@ -321,9 +322,7 @@ static int init_kernel_attrs() {
   CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_PARTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   if (head_loss_init()) { set_error("head_loss_init failed"); return MINPPO_ERR_CUDA; }
   CK(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(dwopt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(dwopt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(dwopt_kernel<DWOPT_MAX_EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(dwopt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   done = true;
   return 0;
 }
@@ -346,7 +345,7 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
     ol.offset = static_cast<int>(lf.offset);
     ol.cols = static_cast<int>(lf.cols);
     ol.grad_bias = 0.f;
-    ol.img_t = nullptr; ol.img_n = nullptr; ol.ld_t = 0; ol.ld_n = 0; ol.img_w2 = nullptr;
+    ol.img_t = nullptr; ol.img_n = nullptr; ol.ld_t = 0; ol.ld_n = 0; ol.img_w2 = nullptr; ol.late = 0;
     if (lf.net == 2) {                         // log_std
       ol.grad_src = c->head_part; ol.src_offset = c->po_logstd; ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
       ol.grad_bias = cfg.rank == 0 ? -static_cast<float>(cfg.ent_coef) : 0.f;
@@ -356,14 +355,11 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
       else ol.src_offset = lf.net == 0 ? c->po_b3a : c->po_b3c;
     } else if (lf.is_kernel) {                 // hidden kernels: split-K partials of the dW GEMM
       const int in_l = lf.layer == 0 ? c->D : H;
-      ol.grad_src = c->net[lf.net].dw_part[lf.layer]; ol.src_offset = 0; ol.nparts = c->S; ol.part_stride = in_l * H;
+      ol.grad_src = c->net[lf.net].dw_part[lf.layer]; ol.src_offset = 0; ol.nparts = c->S; ol.part_stride = in_l * H; ol.late = 1;
       ol.img_t = c->net[lf.net].wt[lf.layer]; ol.ld_t = lf.layer == 0 ? c->Dp : H;
       if (lf.layer >= 1) { ol.img_n = c->net[lf.net].wn[lf.layer]; ol.ld_n = H; }
-    } else if (lf.layer == L - 1) {            // bias of the last hidden layer: head kernel column sums
-      ol.grad_src = c->head_part; ol.src_offset = lf.net == 0 ? c->po_bh_a : c->po_bh_c;
-      ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
-    } else {                                   // bias of layer l < L-1: column sums of dz[l+1]
-      ol.grad_src = c->net[lf.net].colsum[lf.layer + 1]; ol.src_offset = 0; ol.nparts = c->m_tiles; ol.part_stride = H;
+    } else {                                   // hidden biases: column sums of dz[l+1], computed by the dW GEMM (ones x dz)
+      ol.grad_src = c->net[lf.net].dbias[lf.layer]; ol.src_offset = 0; ol.nparts = c->S; ol.part_stride = H; ol.late = 1;
     }
   }
   o->nleaves = n;
@@ -416,12 +412,10 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
       g.b1 = u.params + find_leaf(c, net, 1, 0).offset;
       g.w2img = reinterpret_cast<const uint4*>(nb.w2img);
       g.b2 = u.params + find_leaf(c, net, 2, 0).offset;
-      g.colsum = nb.colsum[1];
       g.act = act_kind(c, net);
       g.aout = net == 0 ? c->A : 1;
       g.po_w2 = net == 0 ? c->po_w3a : c->po_w3c;
       g.po_b2 = net == 0 ? c->po_b3a : c->po_b3c;
-      g.po_bh = net == 0 ? c->po_bh_a : c->po_bh_c;
       g.po_loss = c->po_loss + (net == 0 ? 1 : 0);          // [0] = sum max(vl, vlc), [1] = sum min(l1, l2)
     }
     p.rowidx = ridx; p.obs_img = c->obs_img; p.count = c->counts + s;
@@ -530,6 +524,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
         g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
         g.kb_total = c->M_pad / 64;
         g.tmC = nb.m_dw[l];
+        g.colsum_out = nb.dbias[l];
         g.N = H; g.m_tiles = (in_pad + 127) / 128; g.splits = c->S; g.m_store = in_l;
         cta += g.m_tiles * g.splits;
       }
@@ -541,7 +536,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
   o.losses_out = u.losses_out ? u.losses_out + static_cast<size_t>(s) * 4 : c->losses_scratch;
   o.gnorm_out = c->gnorms + s;
   const bool sharded = c->cfg.world_size > 1;
-  const bool merged = c->merged_opt && c->skip_mask == 0 && cta <= c->sm_count && c->P <= dwopt_max_params(c->sm_count);
+  const bool merged = c->merged_opt && c->skip_mask == 0 && cta <= c->sm_count;
   if (merged) {
     dp.gemm_ctas = cta;
     o.do_reduce = 1; o.do_apply = sharded ? 0 : 1;
@@ -798,7 +793,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   for (int net = 0; net < 2; ++net) {
     NetBufs& nb = c->net[net];
     nb.act.assign(L + 1, nullptr); nb.dz.assign(L + 1, nullptr); nb.wt.assign(L, nullptr); nb.wn.assign(L, nullptr);
-    nb.dw_part.assign(L, nullptr); nb.colsum.assign(L, nullptr);
+    nb.dw_part.assign(L, nullptr); nb.colsum.assign(L, nullptr); nb.dbias.assign(L, nullptr);
     ALLOC(nb.w2img, 16384);
     nb.m_act_k.resize(L + 1); nb.m_act_mn.resize(L + 1); nb.m_dz_k.resize(L + 1); nb.m_dz_mn.resize(L + 1);
     nb.m_wt.resize(L); nb.m_wn.resize(L); nb.m_dw.resize(L);
@@ -821,6 +816,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
         ALLOC(nb.colsum[l], static_cast<size_t>(c->m_tiles) * H);
       }
       ALLOC(nb.dw_part[l], static_cast<size_t>(c->S) * in_l * H);
+      ALLOC(nb.dbias[l], static_cast<size_t>(c->S) * H);
       if ((rc = make_tmap_f32_3d(&nb.m_dw[l], nb.dw_part[l], H, in_l, c->S))) return fail(rc);
     }
   }

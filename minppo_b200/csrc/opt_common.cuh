@@ -7,7 +7,7 @@
 namespace minppo {
 
 constexpr int OPT_THREADS = 512;                 // 512 x <= 42 regs: co-resident with a fused-step CTA under PDL
-constexpr int OPT_EPT = 8;                    // max elements per thread (registers)
+
 
 template <int NTHREADS = 512>
 MINPPO_DEVINL float block_sum(float v, float* scratch /*[32]*/) {
@@ -102,6 +102,129 @@ MINPPO_DEVINL void write_images(const OptLeaf& L, int i, float p) {
     const uint32_t off = sw16_off(j, r);
     *reinterpret_cast<uint16_t*>(L.img_w2 + off) = static_cast<uint16_t>(hi);
     *reinterpret_cast<uint16_t*>(L.img_w2 + 8192 + off) = static_cast<uint16_t>(lo);
+  }
+}
+
+// ---- leaf table in shared memory ---------------------------------------------------------------
+// Kernel parameters live in the constant bank; indexing them with a run-time leaf index costs one
+// dependent LDC per field (the first merged kernel spent most of its optimizer phases there).  Every
+// CTA copies the table to shared memory once and the strided loops below walk it monotonically.
+struct LeafTab {
+  OptLeaf leaf[MINPPO_MAX_LEAVES];
+  int size[MINPPO_MAX_LEAVES];
+  int nleaves;
+};
+MINPPO_DEVINL void leaf_tab_build(LeafTab& T, const OptArgs& a, int tid, int nthreads) {
+  constexpr int WORDS = sizeof(OptLeaf) / 4;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(a.leaf);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(T.leaf);
+  for (int w = tid; w < a.nleaves * WORDS; w += nthreads) dst[w] = src[w];
+  for (int l = tid; l < a.nleaves; l += nthreads)
+    T.size[l] = (l + 1 < a.nleaves ? a.leaf[l + 1].offset : a.P) - a.leaf[l].offset;
+  if (tid == 0) T.nleaves = a.nleaves;
+}
+
+// fixed-order sum of `nparts` partials, 16 loads in flight
+MINPPO_DEVINL float sum_partials16(const float* __restrict__ src, int nparts, size_t stride) {
+  float acc = 0.f;
+  int p = 0;
+#pragma unroll 1
+  for (; p + 16 <= nparts; p += 16) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + static_cast<size_t>(p + u) * stride);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc += v[u];
+  }
+#pragma unroll 1
+  for (; p < nparts; ++p) acc += __ldcg(src + static_cast<size_t>(p) * stride);
+  return acc;
+}
+// same, four consecutive elements at once (16-byte loads; src 16-byte aligned, stride % 4 == 0)
+MINPPO_DEVINL float4 sum_partials16_v4(const float* __restrict__ src, int nparts, size_t stride) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int p = 0;
+#pragma unroll 1
+  for (; p + 16 <= nparts; p += 16) {
+    float4 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(p + u) * stride));
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+  }
+#pragma unroll 1
+  for (; p < nparts; ++p) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(p) * stride));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  return acc;
+}
+
+// Gradient reduction of one class of leaves -> gflat; returns this thread's sum of squares.
+//   LATE == false: leaves whose partials the fused step kernel wrote (biases of the output heads, head
+//                  kernels, log_std, ...): one element per job, then the two loss sums.
+//   LATE == true : leaves whose partials the dW GEMM of the SAME launch writes (hidden kernels): four
+//                  elements per job (sizes and partial strides are multiples of 4, partial buffers 16-byte
+//                  aligned; gflat itself is only 4-byte aligned at a leaf offset).
+// Jobs are dealt round-robin (job = first + k * stride); the leaf walk is monotonic in k.
+template <bool LATE>
+MINPPO_DEVINL float reduce_leaves(const OptArgs& a, const LeafTab& T, int first, int stride) {
+  const int nl = T.nleaves;
+  int l = -1, base = 0, n = 0;
+  float ss = 0.f;
+#pragma unroll 1
+  for (int j = first;; j += stride) {
+    while (l < nl && j >= base + n) {
+      base += n;
+      n = 0;
+      do { ++l; } while (l < nl && (T.leaf[l].late != 0) != LATE);
+      if (l < nl) n = LATE ? (T.size[l] >> 2) : T.size[l];
+    }
+    if (l >= nl) {
+      if (!LATE && j - base < 2)          // the loss sums ride behind the early leaves
+        a.gflat[a.P + (j - base)] = sum_partials16(a.loss_src + a.loss_src_offset + (j - base), a.loss_nparts, a.loss_part_stride);
+      break;
+    }
+    const OptLeaf& L = T.leaf[l];
+    const int x = j - base;
+    if (LATE) {
+      const float4 g = sum_partials16_v4(L.grad_src + L.src_offset + 4 * x, L.nparts, L.part_stride);
+      float* dst = a.gflat + L.offset + 4 * x;
+      dst[0] = g.x; dst[1] = g.y; dst[2] = g.z; dst[3] = g.w;
+      ss = fmaf(g.x, g.x, ss); ss = fmaf(g.y, g.y, ss); ss = fmaf(g.z, g.z, ss); ss = fmaf(g.w, g.w, ss);
+    } else {
+      const float g = sum_partials16(L.grad_src + L.src_offset + x, L.nparts, L.part_stride) + L.grad_bias;
+      a.gflat[L.offset + x] = g;
+      ss = fmaf(g, g, ss);
+    }
+  }
+  return ss;
+}
+
+// clip + Adam over the arena, three elements in flight per thread; gradient from gflat
+MINPPO_DEVINL void apply_adam(const OptArgs& a, const LeafTab& T, const AdamScalars& sc, int first, int stride) {
+  const int P = a.P;
+  int l = 0;
+#pragma unroll 1
+  for (int i0 = first; i0 < P; i0 += 3 * stride) {
+    float g[3], pv[3], mv[3], nv[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int i = i0 + u * stride;
+      if (i < P) { g[u] = __ldcg(a.gflat + i); pv[u] = __ldcg(a.params + i); mv[u] = __ldcg(a.mu + i); nv[u] = __ldcg(a.nu + i); }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int i = i0 + u * stride;
+      if (i < P) {
+        adam_element(a, sc, g[u], pv[u], mv[u], nv[u]);
+        a.params[i] = pv[u];
+        a.mu[i] = mv[u];
+        a.nu[i] = nv[u];
+        while (l + 1 < T.nleaves && i >= T.leaf[l + 1].offset) ++l;
+        write_images(T.leaf[l], i, pv[u]);
+      }
+    }
   }
 }
 

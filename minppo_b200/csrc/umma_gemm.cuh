@@ -29,7 +29,8 @@ constexpr int GEMM_B_BYTES = GEMM_MAXN * GEMM_BK * 2;    // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_EPI_THREADS = 128;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 4 * GEMM_MAXN * 4 /*colsum*/ + 256;
+constexpr int GEMM_ONES_BYTES = 16384;                   // all-ones bf16 [128][64] tile: A operand of the bias-gradient MMAs
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_ONES_BYTES + 1024 /*align*/ + 4 * GEMM_MAXN * 4 /*colsum*/ + 256;
 constexpr int GEMM_MAX_GROUPS = 6;
 
 enum : int { A_TMA_K = 0, A_GATHER_K = 1, A_TMA_MN = 2, A_GATHER_MN = 3 };
@@ -47,6 +48,8 @@ struct alignas(64) GemmGroup {
   const float* bias;               // EPI_ACT: fp32 [N]
   const __nv_bfloat16* hprev;      // EPI_DACT: layer output h (for f'(z) from h), bf16 [M][ldh]
   float* colsum;                   // EPI_DACT: fp32 [m_tiles][N] per-tile column sums (bias grads)
+  float* colsum_out;               // EPI_PARTIAL + B_TMA_MN: fp32 [splits][N] column sums of B over this CTA's K range
+                                   // (= bias gradient partials), computed on the tensor core as ones x B; or null
   int ldg, ldo, ldh;
   int amode, bmode;                // A_* / B_* operand modes
   int cta_begin;                   // first blockIdx.x of this group
@@ -94,8 +97,9 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B: 1024-B aligned tiles
   uint8_t* aligned = smem_raw + (base - raw);
-  float* colsum_s = reinterpret_cast<float*>(aligned + GEMM_STAGES * GEMM_STAGE_BYTES);   // [4][MAXN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aligned + GEMM_STAGES * GEMM_STAGE_BYTES + 4 * GEMM_MAXN * 4);
+  const uint32_t ones = base + GEMM_STAGES * GEMM_STAGE_BYTES;                             // 1024-byte aligned
+  float* colsum_s = reinterpret_cast<float*>(aligned + GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_ONES_BYTES);   // [4][MAXN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aligned + GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_ONES_BYTES + 4 * GEMM_MAXN * 4);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + GEMM_STAGES;        // [STAGES]
   uint64_t* tmem_full_bar = bars + 2 * GEMM_STAGES;
@@ -116,6 +120,18 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
   const int N = G.N;
   const bool kGather = (AMODE == A_GATHER_K || AMODE == A_GATHER_MN);
   const bool kTmaA = !kGather;
+  // bias-gradient columns of this CTA: the m-tiles of one (group, split) share the N columns between them when
+  // the shares are whole 64-column panels, otherwise m-tile 0 takes all of them
+  const bool cs_even = (N % G.m_tiles) == 0 && ((N / G.m_tiles) % 64) == 0;
+  const int cs_nc = cs_even ? N / G.m_tiles : (m_tile == 0 ? N : 0);
+  const int cs_c0 = cs_even ? m_tile * cs_nc : 0;
+  const bool kColsum = EPI == EPI_PARTIAL && G.colsum_out != nullptr && BMODE == B_TMA_MN && cs_nc > 0;
+  constexpr uint32_t kTmemCols = EPI == EPI_PARTIAL ? 512 : 256;
+  if (kColsum) {
+    for (int i = threadIdx.x; i < GEMM_ONES_BYTES / 16; i += GEMM_THREADS)
+      sts128(ones + i * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));       // bf16 1.0
+    fence_proxy_async_smem();
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) {
@@ -126,7 +142,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -186,6 +202,10 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
           if (BMODE == B_TMA_K) db = umma_smem_desc(sb + j * 32, 16, 1024);
           else db = umma_smem_desc(sb + j * 2048, 8192, 1024);
           umma_bf16(tmem_base, da, db, idesc, (i > 0 || j > 0) ? 1u : 0u);
+          if (kColsum)         // D[:, c] += sum_k 1 * B[k][c]: every accumulator row holds the column sums
+            umma_bf16(tmem_base + 256, umma_smem_desc(ones + j * 32, 16, 1024),
+                      umma_smem_desc(sb + j * 2048 + (cs_c0 >> 6) * 8192, 8192, 1024),
+                      umma_idesc_bf16(GEMM_BM, static_cast<uint32_t>(cs_nc), 0u, 1u), (i > 0 || j > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
       }
@@ -309,6 +329,23 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
                             __float_as_uint(v[4 * j + 3])));
       }
     }
+    if (kColsum) {
+      // all 128 accumulator rows are equal: warp q picks 32-column chunks q, q + 4, ..., lane i keeps column i
+      for (int ch = q; ch < cs_nc / 32; ch += 4) {
+        float v[32];
+        if (nkb > 0) {
+          tmem_ld_32x32(taddr + 256 + ch * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        float out = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) out = (static_cast<int>(lane_id()) == j) ? v[j] : out;
+        G.colsum_out[static_cast<size_t>(split) * N + cs_c0 + ch * 32 + lane_id()] = out;
+      }
+    }
     if (EPI == EPI_PARTIAL) {
       // tmC: fp32 [splits][m_store][N], box {32, 128, 1}: rows >= m_store are clipped by the TMA unit
       fence_proxy_async_smem();
@@ -331,7 +368,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 template <int EPI>
