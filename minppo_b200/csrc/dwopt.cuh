@@ -27,7 +27,60 @@ struct alignas(64) DwOptParams {
   GemmParams gemm;
   OptArgs opt;
   int gemm_ctas;                 // CTAs [0, gemm_ctas) run the GEMM; the others pre-reduce the small leaves
+  long long* trace;              // debug: [grid][8] clock64 stamps (null = off)
+  // bias gradients on the otherwise idle extra CTAs: column sums of dz (bf16 [cs_rows][cs_n]) of GEMM group i
+  // -> cs_out[i] as [cs_chunks][cs_n] partials (row chunk c of extra CTA e = c * ngroups + i)
+  const __nv_bfloat16* cs_src[GEMM_MAX_GROUPS];
+  float* cs_out[GEMM_MAX_GROUPS];
+  int cs_rows, cs_n, cs_chunks;  // cs_chunks == 0: the GEMM CTAs form them on the tensor core instead
+  // L2 prefetch of the NEXT minibatch's observation rows (the fused step kernel gathers them first thing)
+  const int32_t* next_ridx;      // [next_rows] or null
+  const __nv_bfloat16* obs_img;  // [Bl][obs_ld]
+  int next_rows, obs_ld;
 };
+
+// column sums of rows [r0, r1) of a bf16 [rows][n] matrix (n <= 256): one warp per row, 16-byte loads,
+// fixed summation order (rows within a warp, then warps)
+MINPPO_DEVINL void colsum_rows(const __nv_bfloat16* __restrict__ src, int n, int r0, int r1, float* __restrict__ out,
+                               float* scratch /* [GEMM_THREADS / 32][256] */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = GEMM_THREADS / 32;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const bool on = lane * 8 < n;
+  int r = r0 + warp;
+#pragma unroll 1
+  for (; r + 7 * NW < r1; r += 8 * NW) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = on ? __ldcg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + u * NW) * n) + lane) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[2 * j] += bf16_lo(w[j]); acc[2 * j + 1] += bf16_hi(w[j]); }
+    }
+  }
+#pragma unroll 1
+  for (; r < r1; r += NW) {
+    const uint4 v = on ? __ldcg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * n) + lane) : make_uint4(0, 0, 0, 0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[2 * j] += bf16_lo(w[j]); acc[2 * j + 1] += bf16_hi(w[j]); }
+  }
+  __syncthreads();                       // scratch reuse across calls
+#pragma unroll
+  for (int j = 0; j < 8; ++j) scratch[warp * 256 + lane * 8 + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < n; c += GEMM_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += scratch[w * 256 + c];
+    out[c] = s;
+  }
+}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_constant__ DwOptParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -39,7 +92,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
   const int G = static_cast<int>(gridDim.x), NT = GEMM_THREADS;
   const int b = static_cast<int>(blockIdx.x), t = static_cast<int>(threadIdx.x);
   const bool has_extra = p.gemm_ctas < G;
+#define DW_STAMP(slot) do { if (p.trace && t == 0) p.trace[static_cast<size_t>(b) * 8 + (slot)] = clock64(); } while (0)
   float ss = 0.f;
+  DW_STAMP(0);
   leaf_tab_build(T, a, t, NT);
   __syncthreads();
 
@@ -49,7 +104,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
   } else {
     griddep_wait();                                      // the small-leaf partials come from the fused step kernel
     if (t == 0) griddep_launch();
-    ss = reduce_leaves<false>(a, T, (b - p.gemm_ctas) * NT + t, (G - p.gemm_ctas) * NT);
+    const int e = b - p.gemm_ctas, ne = G - p.gemm_ctas;
+    ss = reduce_leaves<false>(a, T, e * NT + t, ne * NT);
+    if (p.cs_chunks > 0 && e < p.cs_chunks * p.gemm.ngroups) {
+      const int i = e % p.gemm.ngroups, c = e / p.gemm.ngroups;
+      const int per = (p.cs_rows + p.cs_chunks - 1) / p.cs_chunks;
+      colsum_rows(p.cs_src[i], p.cs_n, min(p.cs_rows, c * per), min(p.cs_rows, (c + 1) * per),
+                  p.cs_out[i] + static_cast<size_t>(c) * p.cs_n, reinterpret_cast<float*>(smem_raw));
+    }
+    if (p.next_ridx) {                                   // warm L2 for the next step's gather
+      const int lines = (p.obs_ld * 2) >> 7;
+      for (int j = e * NT + t; j < p.next_rows * lines; j += ne * NT) {
+        const char* row = reinterpret_cast<const char*>(p.obs_img + static_cast<size_t>(p.next_ridx[j / lines]) * p.obs_ld);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (j % lines) * 128));
+      }
+    }
   }
   const int count = a.do_apply ? __ldcg(a.count) : 0;   // Adam step count BEFORE this step
   float ent = a.entropy_const;                           // A * (0.5 + 0.5 log 2pi) + sum log|scale|
@@ -57,7 +126,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
     // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the second barrier)
     for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(__ldcg(a.params + a.off_logstd + j))));
   }
+  DW_STAMP(1);
   grid_barrier(a.barrier, a.err_flag);
+  DW_STAMP(2);
 
   // ---- phase 2 ----------------------------------------------------------------------------------
   if (!has_extra) ss += reduce_leaves<false>(a, T, b * NT + t, G * NT);
@@ -65,7 +136,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
   if (!a.do_apply) return;
   const float bs = block_sum<GEMM_THREADS>(ss, scratch);
   if (t == 0) a.block_ss[b] = bs;
+  DW_STAMP(3);
   grid_barrier(a.barrier, a.err_flag);
+  DW_STAMP(4);
 
   // ---- phase 3 ----------------------------------------------------------------------------------
   if (t < 32) {
@@ -80,6 +153,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
   sc.gnorm = s_bcast[0]; sc.lr = s_bcast[1]; sc.c1 = s_bcast[2]; sc.c2 = s_bcast[3];
   sc.trigger = sc.gnorm < a.max_norm;                    // optax.clip_by_global_norm
   apply_adam(a, T, sc, b * NT + t, G * NT);
+  __syncthreads();
+  DW_STAMP(5);
   if (b == 0 && t == 0) {
     *a.count = count + 1;
     if (a.losses_out) {

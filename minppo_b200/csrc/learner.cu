@@ -229,6 +229,7 @@ struct minppo_ctx {
   int T, N, Nl, n0, M, E, L, H, D, Dp, A;
   long long B, Bl, P;
   int mb, cap, M_pad, m_tiles, tiles64, S;
+  int cs_chunks;              // > 0: bias-gradient column sums on the spare CTAs of the dwopt launch, in this many row chunks
   bool fused;                 // fused step kernel (L == 2, Dp <= 256, A <= 16)
   int head_parts;             // head partials per minibatch: m_tiles (fused) or tiles64
   std::vector<LeafInfo> leaves;
@@ -236,6 +237,7 @@ struct minppo_ctx {
   std::vector<void*> allocs;
   float *adv, *tgt, *stats, *gflat, *block_ss, *head_part, *gnorms, *losses_scratch;
   long long* trace;           // debug cycle stamps of the fused kernel [2*m_tiles][32]
+  long long* trace2;          // debug cycle stamps of the dwopt kernel [sm_count][8]
   bool trace_on;
   bool pdl;                   // programmatic dependent launch between step kernels (MINPPO_PDL=0 disables)
   bool merged_opt;            // dW GEMM + reduction + Adam in one launch (MINPPO_SPLIT_OPT=1 disables)
@@ -359,7 +361,8 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
       ol.img_t = c->net[lf.net].wt[lf.layer]; ol.ld_t = lf.layer == 0 ? c->Dp : H;
       if (lf.layer >= 1) { ol.img_n = c->net[lf.net].wn[lf.layer]; ol.ld_n = H; }
     } else {                                   // hidden biases: column sums of dz[l+1], computed by the dW GEMM (ones x dz)
-      ol.grad_src = c->net[lf.net].dbias[lf.layer]; ol.src_offset = 0; ol.nparts = c->S; ol.part_stride = H; ol.late = 1;
+      ol.grad_src = c->net[lf.net].dbias[lf.layer]; ol.src_offset = 0; ol.nparts = c->cs_chunks > 0 ? c->cs_chunks : c->S;
+      ol.part_stride = H; ol.late = 1;
     }
   }
   o->nleaves = n;
@@ -524,7 +527,8 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
         g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
         g.kb_total = c->M_pad / 64;
         g.tmC = nb.m_dw[l];
-        g.colsum_out = nb.dbias[l];
+        g.colsum_out = c->cs_chunks > 0 ? nullptr : nb.dbias[l];
+        dp.cs_src[ng - 1] = nb.dz[l + 1]; dp.cs_out[ng - 1] = nb.dbias[l];
         g.N = H; g.m_tiles = (in_pad + 127) / 128; g.splits = c->S; g.m_store = in_l;
         cta += g.m_tiles * g.splits;
       }
@@ -539,6 +543,9 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
   const bool merged = c->merged_opt && c->skip_mask == 0 && cta <= c->sm_count;
   if (merged) {
     dp.gemm_ctas = cta;
+    dp.cs_rows = c->M_pad; dp.cs_n = H; dp.cs_chunks = c->cs_chunks;
+    if (s + 1 < c->E * c->M) { dp.next_ridx = ridx + c->cap; dp.obs_img = c->obs_img; dp.next_rows = c->cap; dp.obs_ld = c->Dp; }
+    dp.trace = c->trace_on ? c->trace2 : nullptr;
     o.do_reduce = 1; o.do_apply = sharded ? 0 : 1;
     {
       PROF(PC_DW_GEMM);
@@ -750,6 +757,10 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     // no empty splits: ceil(kb_total / S) * (S - 1) < kb_total
     while (S > 1 && ((kb_total + S - 1) / S) * (S - 1) >= kb_total) --S;
     c->S = S;
+    // spare CTAs of the one-CTA-per-SM dwopt grid: >= one per GEMM group -> they form the bias gradients
+    const int spare = c->sm_count - per_split * S;
+    const bool merged_ok = !(getenv("MINPPO_SPLIT_OPT") && atoi(getenv("MINPPO_SPLIT_OPT")) != 0) && !getenv("MINPPO_SKIP");
+    c->cs_chunks = (merged_ok && spare >= 2 * c->L && !getenv("MINPPO_TC_COLSUM")) ? spare / (2 * c->L) : 0;
   }
   c->opt_blocks = c->sm_count;
   if (c->P > opt_max_params(c->opt_blocks)) { set_error("parameter count %lld exceeds the single-sweep optimizer kernel (%d)", c->P, opt_max_params(c->opt_blocks)); return fail(MINPPO_ERR_UNSUPPORTED); }
@@ -778,6 +789,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   ALLOC(c->gnorms, static_cast<size_t>(EM));
   ALLOC(c->losses_scratch, 4);
   ALLOC(c->trace, static_cast<size_t>(2 * c->m_tiles) * 32);
+  ALLOC(c->trace2, static_cast<size_t>(c->sm_count) * 8);
   c->trace_on = getenv("MINPPO_TRACE") != nullptr;
   c->pdl = !(getenv("MINPPO_PDL") && atoi(getenv("MINPPO_PDL")) == 0);
   c->merged_opt = !(getenv("MINPPO_SPLIT_OPT") && atoi(getenv("MINPPO_SPLIT_OPT")) != 0);
@@ -816,7 +828,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
         ALLOC(nb.colsum[l], static_cast<size_t>(c->m_tiles) * H);
       }
       ALLOC(nb.dw_part[l], static_cast<size_t>(c->S) * in_l * H);
-      ALLOC(nb.dbias[l], static_cast<size_t>(c->S) * H);
+      ALLOC(nb.dbias[l], static_cast<size_t>(c->S > c->cs_chunks ? c->S : c->cs_chunks) * H);
       if ((rc = make_tmap_f32_3d(&nb.m_dw[l], nb.dw_part[l], H, in_l, c->S))) return fail(rc);
     }
   }
@@ -931,6 +943,7 @@ int minppo_ctx_read(minppo_ctx* c, int32_t what, void* dst, size_t bytes, void* 
     case 5: src = c->counts; have = EM * 4; break;
     case 6: src = c->stats; have = 2 * EM * 4; break;
     case 7: src = c->trace; have = static_cast<size_t>(2 * c->m_tiles) * 32 * 8; break;
+    case 8: src = c->trace2; have = static_cast<size_t>(c->sm_count) * 8 * 8; break;
     default: set_error("minppo_ctx_read: unknown buffer %d", what); return MINPPO_ERR_ARG;
   }
   if (bytes > have) { set_error("minppo_ctx_read: %zu bytes requested, buffer has %zu", bytes, have); return MINPPO_ERR_ARG; }
