@@ -52,11 +52,10 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) opt_kernel(const OptArgs a) {
   const float bs = block_sum<OPT_THREADS>(ss, scratch);
   if (threadIdx.x == 0) a.block_ss[blockIdx.x] = bs;
   grid_barrier(a.barrier, a.err_flag);
-  if (threadIdx.x < 32) {
-    float s = 0.f;
-    for (int b = threadIdx.x; b < G; b += 32) s += __ldcg(a.block_ss + b);
-    s = warp_sum(s);
-    if (threadIdx.x == 0) s_bcast[0] = sqrtf(s);
+  {
+    const float v = static_cast<int>(threadIdx.x) < G ? __ldcg(a.block_ss + threadIdx.x) : 0.f;   // G <= OPT_THREADS
+    const float tot = block_sum<OPT_THREADS>(v, scratch);
+    if (threadIdx.x == 0) s_bcast[0] = sqrtf(tot);
   }
   if (threadIdx.x == 32) step_scalars(a, count, s_bcast[1], s_bcast[2], s_bcast[3]);
   __syncthreads();

@@ -23,6 +23,10 @@
 
 namespace minppo {
 
+// 16 warps per CTA: warps 0..5 run the GEMM roles in phase 1, all of them the element-wise phases (one CTA
+// per SM: with 6 warps the dependent divide / sqrt chains of the Adam phase had nothing to hide behind)
+constexpr int DWOPT_THREADS = 512;
+
 struct alignas(64) DwOptParams {
   GemmParams gemm;
   OptArgs opt;
@@ -42,9 +46,9 @@ struct alignas(64) DwOptParams {
 // column sums of rows [r0, r1) of a bf16 [rows][n] matrix (n <= 256): one warp per row, 16-byte loads,
 // fixed summation order (rows within a warp, then warps)
 MINPPO_DEVINL void colsum_rows(const __nv_bfloat16* __restrict__ src, int n, int r0, int r1, float* __restrict__ out,
-                               float* scratch /* [GEMM_THREADS / 32][256] */) {
+                               float* scratch /* [DWOPT_THREADS / 32][256] */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NW = GEMM_THREADS / 32;
+  constexpr int NW = DWOPT_THREADS / 32;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -74,7 +78,7 @@ MINPPO_DEVINL void colsum_rows(const __nv_bfloat16* __restrict__ src, int n, int
 #pragma unroll
   for (int j = 0; j < 8; ++j) scratch[warp * 256 + lane * 8 + j] = acc[j];
   __syncthreads();
-  for (int c = threadIdx.x; c < n; c += GEMM_THREADS) {
+  for (int c = threadIdx.x; c < n; c += DWOPT_THREADS) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < NW; ++w) s += scratch[w * 256 + c];
@@ -82,14 +86,14 @@ MINPPO_DEVINL void colsum_rows(const __nv_bfloat16* __restrict__ src, int n, int
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_constant__ DwOptParams p) {
+__global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_constant__ DwOptParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float scratch[32];
   __shared__ float s_bcast[4];
   __shared__ LeafTab T;
   const OptArgs& a = p.opt;
   const int P = a.P;
-  const int G = static_cast<int>(gridDim.x), NT = GEMM_THREADS;
+  const int G = static_cast<int>(gridDim.x), NT = DWOPT_THREADS;
   const int b = static_cast<int>(blockIdx.x), t = static_cast<int>(threadIdx.x);
   const bool has_extra = p.gemm_ctas < G;
 #define DW_STAMP(slot) do { if (p.trace && t == 0) p.trace[static_cast<size_t>(b) * 8 + (slot)] = clock64(); } while (0)
@@ -134,18 +138,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
   if (!has_extra) ss += reduce_leaves<false>(a, T, b * NT + t, G * NT);
   ss += reduce_leaves<true>(a, T, b * NT + t, G * NT);
   if (!a.do_apply) return;
-  const float bs = block_sum<GEMM_THREADS>(ss, scratch);
+  const float bs = block_sum<DWOPT_THREADS>(ss, scratch);
   if (t == 0) a.block_ss[b] = bs;
   DW_STAMP(3);
   grid_barrier(a.barrier, a.err_flag);
   DW_STAMP(4);
 
   // ---- phase 3 ----------------------------------------------------------------------------------
-  if (t < 32) {
-    float s = 0.f;
-    for (int x = t; x < G; x += 32) s += __ldcg(a.block_ss + x);
-    s = warp_sum(s);
-    if (t == 0) s_bcast[0] = sqrtf(s);
+  {
+    // one load per thread (G <= DWOPT_THREADS): a serial loop over the per-block sums cost five dependent
+    // L2 round trips on lines every SM is hammering at the same time
+    const float v = t < G ? __ldcg(a.block_ss + t) : 0.f;
+    const float tot = block_sum<DWOPT_THREADS>(v, scratch);
+    if (t == 0) s_bcast[0] = sqrtf(tot);
   }
   if (t == 32) step_scalars(a, count, s_bcast[1], s_bcast[2], s_bcast[3]);
   __syncthreads();
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dwopt_kernel(const __grid_con
 }
 
 inline cudaError_t dwopt_launch(const DwOptParams& p, int grid, cudaStream_t stream, bool pdl) {
-  return launch_kernel(dwopt_kernel, grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
+  return launch_kernel(dwopt_kernel, grid, DWOPT_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
 }
 
 }  // namespace minppo

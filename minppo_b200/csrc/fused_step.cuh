@@ -62,6 +62,8 @@ struct alignas(64) FusedNet {
 
 struct alignas(64) FusedParams {
   FusedNet net[2];
+  CUtensorMap tm_xg;             // gathered observation rows [M_pad][Dp], box {64, 128}: TMA store by the actor CTAs,
+                                 // the A operand of both nets' first-layer weight-gradient GEMM
   const int32_t* rowidx;         // [cap] (this minibatch)
   const __nv_bfloat16* obs_img;  // [Bl][Dp]
   const int32_t* count;
@@ -395,13 +397,20 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     cp_async_wait<0>();
     fence_proxy_async_smem();
     mbar_arrive(xfull);
-    worker_bar();                                                // biases / hb / W2T visible to all workers
+    worker_bar();                                                // biases / hb / W2T visible to all workers; X complete
     if (wt == 0) FS_STAMP(1);
+    if (net == 0 && ww == 0 && lane == 0) {
+      for (int kb = 0; kb < nk0; ++kb) tma_store_2d(R1 + kb * 16384, &p.tm_xg, kb * 64, tile * 128);
+      tma_store_commit();
+    }
 
     // ---- epilogue 1: H1 = act(acc0 + b0) -> R0, then TMA store to HBM ------------------------------
     mbar_wait(accf0, 0);
     tc_fence_after();
     if (wt == 0) FS_STAMP(2);
+    // the X store has read R1 before this warp's h1r arrivals let the L2 GEMM (and then epilogue 2, which
+    // overwrites R1) proceed
+    if (net == 0 && ww == 0 && lane == 0) tma_store_wait_read0();
     for (int b = 0; b < nkH; ++b) {
       epilogue_act(acc0, R0, bias_s, act, erow, q, b * 64 + hf * 32, 32);
       fence_proxy_async_smem();

@@ -246,6 +246,8 @@ struct minppo_ctx {
   void* perm_ws;
   size_t perm_ws_bytes;
   __nv_bfloat16* obs_img;
+  __nv_bfloat16* xg;           // gathered observation rows of the current minibatch [M_pad][Dp] (fused path)
+  CUtensorMap m_xg_k, m_xg_mn;
   unsigned long long* barrier;
   int* err_flag;
   NetBufs net[2];
@@ -422,6 +424,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
       g.po_loss = c->po_loss + (net == 0 ? 1 : 0);          // [0] = sum max(vl, vlc), [1] = sum min(l1, l2)
     }
     p.rowidx = ridx; p.obs_img = c->obs_img; p.count = c->counts + s;
+    p.tm_xg = c->m_xg_k;
     p.adv_sum = c->stats + s; p.adv_sq = c->stats + c->E * c->M + s;
     p.action = u.action; p.v_old = u.value; p.logp_old = u.log_prob; p.adv = c->adv; p.tgt = c->tgt;
     p.log_std = u.params + c->leaves.back().offset;
@@ -522,7 +525,8 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
         g.cta_begin = cta;
         const int in_l = l == 0 ? c->D : H;
         const int in_pad = l == 0 ? c->Dp : H;
-        if (l == 0) { g.amode = A_GATHER_MN; g.rowidx = ridx; g.gimage = c->obs_img; g.ldg = c->Dp; }
+        if (l == 0 && c->fused && !(c->skip_mask & 1)) { g.amode = A_TMA_MN; g.tmA = c->m_xg_mn; }   // rows gathered by the fused kernel
+        else if (l == 0) { g.amode = A_GATHER_MN; g.rowidx = ridx; g.gimage = c->obs_img; g.ldg = c->Dp; }
         else { g.amode = A_TMA_MN; g.tmA = nb.m_act_mn[l]; }
         g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
         g.kb_total = c->M_pad / 64;
@@ -760,7 +764,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     // spare CTAs of the one-CTA-per-SM dwopt grid: >= one per GEMM group -> they form the bias gradients
     const int spare = c->sm_count - per_split * S;
     const bool merged_ok = !(getenv("MINPPO_SPLIT_OPT") && atoi(getenv("MINPPO_SPLIT_OPT")) != 0) && !getenv("MINPPO_SKIP");
-    c->cs_chunks = (merged_ok && spare >= 2 * c->L && !getenv("MINPPO_TC_COLSUM")) ? spare / (2 * c->L) : 0;
+    c->cs_chunks = (merged_ok && spare >= 2 * c->L && getenv("MINPPO_CTA_COLSUM")) ? spare / (2 * c->L) : 0;
   }
   c->opt_blocks = c->sm_count;
   if (c->P > opt_max_params(c->opt_blocks)) { set_error("parameter count %lld exceeds the single-sweep optimizer kernel (%d)", c->P, opt_max_params(c->opt_blocks)); return fail(MINPPO_ERR_UNSUPPORTED); }
@@ -800,6 +804,9 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   c->perm_ws_bytes = perm_workspace_bytes(c->E, c->B);
   { uint8_t* p; ALLOC(p, c->perm_ws_bytes); c->perm_ws = p; }
   ALLOC(c->obs_img, static_cast<size_t>(c->Bl) * c->Dp + 256);   // slack: MN gather may read one chunk past Dp
+  ALLOC(c->xg, static_cast<size_t>(c->M_pad) * c->Dp);
+  if ((rc = make_tmap(&c->m_xg_k, c->xg, c->Dp, c->M_pad, c->Dp, 64, 128))) return fail(rc);
+  if ((rc = make_tmap(&c->m_xg_mn, c->xg, c->Dp, c->M_pad, c->Dp, 64, 64))) return fail(rc);
   ALLOC(c->barrier, 1);
   ALLOC(c->err_flag, 1);
   for (int net = 0; net < 2; ++net) {

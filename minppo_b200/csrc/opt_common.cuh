@@ -24,19 +24,23 @@ MINPPO_DEVINL float block_sum(float v, float* scratch /*[32]*/) {
 }
 
 // Sense-free grid barrier on a monotonically increasing 64-bit counter.  All blocks of the
-// grid are co-resident (grid <= #SMs, one block per SM).  A bounded spin turns a scheduling
-// surprise into an error flag instead of a hung GPU.
+// grid are co-resident (grid <= #SMs, one block per SM).  Arrive = atom.add.release.gpu, wait =
+// ld.acquire.gpu polling by one thread, bracketed by CTA barriers (cumulativity carries the other
+// threads' writes).  A bounded spin turns a scheduling surprise into an error flag instead of a
+// hung GPU.
 MINPPO_DEVINL void grid_barrier(unsigned long long* counter, int* err_flag) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long old = atomicAdd(counter, 1ULL);
+    unsigned long long old;
+    asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(old) : "l"(counter) : "memory");
     const unsigned long long target = (old / gridDim.x + 1ULL) * gridDim.x;
     const long long t0 = clock64();
-    while (*reinterpret_cast<volatile unsigned long long*>(counter) < target) {
+    for (;;) {
+      unsigned long long cur;
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(counter) : "memory");
+      if (cur >= target) break;
       if (clock64() - t0 > 4000000000LL) { atomicExch(err_flag, MINPPO_ERR_BARRIER); break; }
     }
-    __threadfence();
   }
   __syncthreads();
 }

@@ -92,6 +92,8 @@ MINPPO_DEVINL float warp_colsum32(float (&v)[32]) {
 }
 
 // The whole CTA (GEMM_THREADS threads) calls this; it returns after the TMEM columns are released.
+// Warps 0..5 carry the roles; a caller may run with more warps per CTA (dwopt.cuh): they only take part
+// in the two CTA-wide barriers.
 template <int EPI>
 MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
   const uint32_t raw = smem_u32(smem_raw);
@@ -128,7 +130,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
   const bool kColsum = EPI == EPI_PARTIAL && G.colsum_out != nullptr && BMODE == B_TMA_MN && cs_nc > 0;
   constexpr uint32_t kTmemCols = EPI == EPI_PARTIAL ? 512 : 256;
   if (kColsum) {
-    for (int i = threadIdx.x; i < GEMM_ONES_BYTES / 16; i += GEMM_THREADS)
+    for (int i = threadIdx.x; i < GEMM_ONES_BYTES / 16; i += blockDim.x)
       sts128(ones + i * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));       // bf16 1.0
     fence_proxy_async_smem();
   }
@@ -211,7 +213,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
       }
       umma_commit(tmem_full_bar);            // accumulator complete
     }
-  } else {
+  } else if (warp < GEMM_THREADS / 32) {
     // ===================== gather producer (optional) + epilogue =====================
     const int et = threadIdx.x - 64;         // 0..127
     if (kGather) {

@@ -1,6 +1,7 @@
 """Print the cycle timeline of the fused step kernel (MINPPO_TRACE=1) for a few CTAs of the last minibatch step."""
 import os, sys
 os.environ["MINPPO_TRACE"] = "1"
+os.environ.setdefault("MINPPO_PDL", "0")     # clean per-kernel timelines
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import numpy as np, torch
@@ -56,4 +57,7 @@ print("--- dwopt kernel, cycles per CTA (globaltimer-free: per-SM clock64 deltas
 for k in range(5):
     print(f"  {lab[k]:30s} gemm CTAs: mean {d[:128, k].mean():8.0f} min {d[:128, k].min():8.0f} max {d[:128, k].max():8.0f}"
           f" | extra CTAs: mean {d[128:, k].mean():8.0f} max {d[128:, k].max():8.0f}")
+for gi in range(4):
+    seg = d[32 * gi:32 * gi + 32, 0]
+    print(f"  phase 1 of GEMM group {gi} (net {gi // 2}, layer {gi % 2}): mean {seg.mean():8.0f} min {seg.min():8.0f} max {seg.max():8.0f}")
 print("  total per CTA: mean", (t2[:, 5] - t2[:, 0]).mean(), "max", (t2[:, 5] - t2[:, 0]).max())
