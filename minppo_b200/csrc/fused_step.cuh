@@ -45,9 +45,9 @@ constexpr int FS_BARS = FS_RED + 8 * 40 * 4;            // mbarriers + tmem slot
 constexpr int FS_SMEM_BYTES = FS_BARS + 256 + 1024;     // + alignment slack
 
 struct alignas(64) FusedNet {
-  CUtensorMap tm_w0t;            // W0^T image [H][Dp]   box {64, H}
-  CUtensorMap tm_w1t;            // W1^T image [H][H]    box {64, H}
-  CUtensorMap tm_w1n;            // W1   image [H][H]    box {64, H}   (n = in, k = out)
+  CUtensorMap tm_w0;             // W0 image [Dp][H] (as stored: [in][out])  box {64 out, 64 in}: MN-major B of L1
+  CUtensorMap tm_w1;             // W1 image [H][H]                          box {64 out, 64 in}: MN-major B of L2
+  CUtensorMap tm_w1k;            // W1 image [H][H]                          box {64 out, H in}:  K-major  B of dH1 (n = in, k = out)
   CUtensorMap tm_h1;             // act[1] [M_pad][H]    box {64, 128}  (TMA store)
   CUtensorMap tm_dz2;            // dz[2]
   CUtensorMap tm_dz1;            // dz[1]
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   if (warp == 0) {
     // ===================== weight producer: W0^T, W1^T, W1 k-blocks through the ring ==========
     if (elect_one()) {
-      tma_prefetch_desc(&G.tm_w0t); tma_prefetch_desc(&G.tm_w1t); tma_prefetch_desc(&G.tm_w1n);
+      tma_prefetch_desc(&G.tm_w0); tma_prefetch_desc(&G.tm_w1); tma_prefetch_desc(&G.tm_w1k);
       griddep_wait();                 // the weight images are rewritten by the previous optimizer step
       const uint32_t bytes = static_cast<uint32_t>(H) * 128u;
       const int total = nk0 + 2 * nkH;
@@ -250,9 +250,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
         const uint32_t ph = (i >> 1) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], bytes);
-        const CUtensorMap* m = i < nk0 ? &G.tm_w0t : (i < nk0 + nkH ? &G.tm_w1t : &G.tm_w1n);
-        const int kb = i < nk0 ? i : (i < nk0 + nkH ? i - nk0 : i - nk0 - nkH);
-        tma_load_2d(RB + s * FS_BSTAGE, m, &full_bar[s], kb * 64, 0);
+        if (i < nk0 + nkH) {            // forward: k-block of W0 / W1 as stored, one {64 out, 64 in} box per 64 outputs
+          const CUtensorMap* m = i < nk0 ? &G.tm_w0 : &G.tm_w1;
+          const int kb = i < nk0 ? i : i - nk0;
+          for (int c = 0; c < nkH; ++c) tma_load_2d(RB + s * FS_BSTAGE + c * 8192, m, &full_bar[s], c * 64, kb * 64);
+        } else {                        // dH1: k-block (64 outputs) of W1 for all H inputs
+          tma_load_2d(RB + s * FS_BSTAGE, &G.tm_w1k, &full_bar[s], (i - nk0 - nkH) * 64, 0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -262,7 +266,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       int i = 0;
       // a_ready: per-k-block barriers of the A operand (the epilogue that produces A publishes it in
       // 64-column blocks, so this GEMM starts while the previous epilogue is still running)
-      auto gemm = [&](uint32_t a_base, int nk, uint32_t acc, uint64_t* a_ready) {
+      const uint32_t idesc_bmn = umma_idesc_bf16(128, static_cast<uint32_t>(H), 0u, 1u);     // B as stored: MN-major
+      auto gemm = [&](uint32_t a_base, int nk, uint32_t acc, uint64_t* a_ready, bool b_mn) {
         for (int kb = 0; kb < nk; ++kb, ++i) {
           const int s = i & 1;
           const uint32_t ph = (i >> 1) & 1;
@@ -272,8 +277,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
           const uint32_t sa = a_base + kb * 16384, sb = RB + s * FS_BSTAGE;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            umma_bf16(acc, umma_smem_desc(sa + j * 32, 16, 1024), umma_smem_desc(sb + j * 32, 16, 1024), idesc,
-                      (kb > 0 || j > 0) ? 1u : 0u);
+            umma_bf16(acc, umma_smem_desc(sa + j * 32, 16, 1024),
+                      b_mn ? umma_smem_desc(sb + j * 2048, 8192, 1024) : umma_smem_desc(sb + j * 32, 16, 1024),
+                      b_mn ? idesc_bmn : idesc, (kb > 0 || j > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
         }
       };
@@ -281,11 +287,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       mbar_wait(xfull, 0);
       tc_fence_after();
       FS_STAMP(18);
-      gemm(R1, nk0, acc0, nullptr);   // L1: X W0^T
+      gemm(R1, nk0, acc0, nullptr, true);    // L1: X W0
       umma_commit(accf0);
       FS_STAMP(19);
       FS_STAMP(20);
-      gemm(R0, nkH, acc1, h1r);       // L2: H1 W1^T
+      gemm(R0, nkH, acc1, h1r, true);        // L2: H1 W1
       umma_commit(accf1);
       FS_STAMP(21);
       // ---- head forward: out[128 x 16] = H2 (W2_hi + W2_lo); A = H2 K-major, B = W2^T K-major, N = 16
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       FS_STAMP(22);
       // accumulates into acc1: every worker warp has read the head / dW2 columns of acc1 before its first
       // arrival on dz2r[0], while acc0 (dA2) is still being drained by the dZ2 epilogue
-      gemm(R1, nkH, acc1, dz2r);      // dH1: dZ2 W1
+      gemm(R1, nkH, acc1, dz2r, false);      // dH1: dZ2 W1^T
       umma_commit(dh1f);
       FS_STAMP(23);
     }
@@ -343,18 +349,27 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     const int q = warp & 3, hf = ww >> 2;
     const int erow = q * 32 + lane;                              // epilogue row == TMEM lane
     const int act = G.act, aout = G.aout;
-    const int srow = wt >> 1, shalf = wt & 1;                    // gather mapping: (row, k-block parity)
+    const int gchunk = wt & 7, grow0 = wt >> 3;                  // gather mapping: 8 lanes per 128-byte line, rows grow0 + 32 g
     if (wt == 0) FS_STAMP(0);
 
     // ---- gather the observation rows of this tile into R1 ---------------------------------------
-    const int src_g = p.rowidx[tile * 128 + srow];
+    int src_g[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) src_g[g] = p.rowidx[tile * 128 + grow0 + 32 * g];
     const int lrow = tile * 128 + erow;                          // loss row of this thread (hf == 0 warps)
     const int count = min(*p.count, p.cap);
     const bool live = (hf == 0) && (lrow < count);
     const int src_l = live ? p.rowidx[lrow] : 0;
-    for (int kb = shalf; kb < nk0; kb += 2)
-      gather_line(R1 + kb * 16384, srow, p.obs_img + static_cast<size_t>(src_g) * p.Dp + kb * 64);
+    // one warp instruction copies 4 rows x 128 contiguous bytes (4 L1 wavefronts; a lane-per-row mapping needed 32)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int row = grow0 + 32 * g;
+      const __nv_bfloat16* src = p.obs_img + static_cast<size_t>(src_g[g]) * p.Dp + gchunk * 8;
+      const uint32_t dst = R1 + row * 128 + ((gchunk ^ (row & 7)) << 4);
+      for (int kb = 0; kb < nk0; ++kb) cp_async_16(dst + kb * 16384, src + kb * 64);
+    }
     cp_async_commit();
+    if (wt == 0) FS_STAMP(26);
     // per-row loss inputs, prefetched (used after the head GEMM); static within one update
     float in0 = 0.f, in1 = 0.f, actn[FS_AP];
 #pragma unroll
@@ -362,16 +377,25 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     if (live) {
       if (net == 0) {
         in0 = p.logp_old[src_l]; in1 = p.adv[src_l];
+        const float* ap = p.action + static_cast<size_t>(src_l) * aout;
+        if ((aout & 1) == 0) {                                     // rows are 8-byte aligned: half the load wavefronts
 #pragma unroll
-        for (int j = 0; j < FS_AP; ++j) if (j < aout) actn[j] = p.action[static_cast<size_t>(src_l) * aout + j];
+          for (int j = 0; j < FS_AP; j += 2)
+            if (j < aout) { const float2 v = *reinterpret_cast<const float2*>(ap + j); actn[j] = v.x; actn[j + 1] = v.y; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < FS_AP; ++j) if (j < aout) actn[j] = ap[j];
+        }
       } else {
         in0 = p.v_old[src_l]; in1 = p.tgt[src_l];
       }
     }
     const float adv_sum = *p.adv_sum, adv_sq = *p.adv_sq;
+    if (wt == 0) FS_STAMP(27);
     // ---- everything below reads what the previous optimizer step wrote (PDL: see common.cuh) -------
     griddep_wait();
     if (wt == 0) griddep_launch();
+    if (wt == 0) FS_STAMP(28);
     // ---- small operands: biases, head bias / log_std, head kernel^T image (bf16 hi / lo, swizzled) --
     // (all global loads first: the st.shared wrappers are ordering barriers for the compiler)
     const float b0v = wt < H ? __ldcg(G.b0 + wt) : 0.f;             // H <= 256 == FS_WORKERS
@@ -390,11 +414,14 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     }
     for (int i = wt; i < 1024; i += FS_WORKERS) cp_async_16(W2T + i * 16, G.w2img + i);
     cp_async_commit();
+    if (wt == 0) FS_STAMP(29);
     if (wt < H) { bias_s[wt] = b0v; bias_s[256 + wt] = b1v; }
     if (wt < 32) hb[wt] = hbv;
     if (wt >= 16 && wt < 32) hb[16 + wt] = 1.f / expf(hbv);          // 1 / scale (unused columns: 1)
     if (wt == 32) hb[48] = logdet;
+    if (wt == 0) FS_STAMP(30);
     cp_async_wait<0>();
+    if (wt == 0) FS_STAMP(31);
     fence_proxy_async_smem();
     mbar_arrive(xfull);
     worker_bar();                                                // biases / hb / W2T visible to all workers; X complete

@@ -202,13 +202,13 @@ using namespace minppo;
 struct NetBufs {
   std::vector<__nv_bfloat16*> act;     // act[l], l = 1..L   [M_pad][H]
   std::vector<__nv_bfloat16*> dz;      // dz[l],  l = 1..L   [M_pad][H]
-  std::vector<__nv_bfloat16*> wt;      // wt[l],  l = 0..L-1 [H][Kp_l]   (kernel^T)
-  std::vector<__nv_bfloat16*> wn;      // wn[l],  l = 1..L-1 [H][H]      (kernel as stored)
+  std::vector<__nv_bfloat16*> wn;      // wn[l],  l = 0..L-1 [in_pad_l][H]: bf16 image of the kernel as stored ([in][out]; rows >= in are 0)
   std::vector<float*> dw_part;         // dw_part[l], l = 0..L-1 [S][in_l][H]
   uint8_t* w2img;                      // head kernel^T bf16 hi / lo image (16 KB, fused path)
   std::vector<float*> dbias;           // dbias[l], l = 0..L-1 [S][H]: bias-gradient partials from the dW GEMM (ones x dz[l+1])
   std::vector<float*> colsum;          // colsum[l],  l = 1..L-1 [m_tiles][H]  -> bias grad of layer l-1
-  std::vector<CUtensorMap> m_act_k, m_act_mn, m_dz_k, m_dz_mn, m_wt, m_wn, m_dw;
+  std::vector<CUtensorMap> m_act_k, m_act_mn, m_dz_k, m_dz_mn, m_wn_mn, m_wn, m_dw;
+  // m_wn_mn[l]: box {64 out, 64 in} -- MN-major B of the forward GEMMs;  m_wn[l] (l >= 1): box {64 out, H in} -- K-major B of dX
 };
 
 struct UpdatePtrs {
@@ -360,8 +360,7 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
     } else if (lf.is_kernel) {                 // hidden kernels: split-K partials of the dW GEMM
       const int in_l = lf.layer == 0 ? c->D : H;
       ol.grad_src = c->net[lf.net].dw_part[lf.layer]; ol.src_offset = 0; ol.nparts = c->S; ol.part_stride = in_l * H; ol.late = 1;
-      ol.img_t = c->net[lf.net].wt[lf.layer]; ol.ld_t = lf.layer == 0 ? c->Dp : H;
-      if (lf.layer >= 1) { ol.img_n = c->net[lf.net].wn[lf.layer]; ol.ld_n = H; }
+      ol.img_n = c->net[lf.net].wn[lf.layer]; ol.ld_n = H;
     } else {                                   // hidden biases: column sums of dz[l+1], computed by the dW GEMM (ones x dz)
       ol.grad_src = c->net[lf.net].dbias[lf.layer]; ol.src_offset = 0; ol.nparts = c->cs_chunks > 0 ? c->cs_chunks : c->S;
       ol.part_stride = H; ol.late = 1;
@@ -411,7 +410,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     for (int net = 0; net < 2; ++net) {
       FusedNet& g = p.net[net];
       NetBufs& nb = c->net[net];
-      g.tm_w0t = nb.m_wt[0]; g.tm_w1t = nb.m_wt[1]; g.tm_w1n = nb.m_wn[1];
+      g.tm_w0 = nb.m_wn_mn[0]; g.tm_w1 = nb.m_wn_mn[1]; g.tm_w1k = nb.m_wn[1];
       g.tm_h1 = nb.m_act_k[1]; g.tm_dz2 = nb.m_dz_k[2]; g.tm_dz1 = nb.m_dz_k[1];
       g.b0 = u.params + find_leaf(c, net, 0, 0).offset;
       g.b1 = u.params + find_leaf(c, net, 1, 0).offset;
@@ -447,8 +446,8 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
       GemmGroup& g = p.g[net];
       NetBufs& nb = c->net[net];
       g.cta_begin = net * c->m_tiles;
-      g.bmode = B_TMA_K;
-      g.tmB = nb.m_wt[l];
+      g.bmode = B_TMA_MN;                 // kernel image as stored [in = k][out = n]
+      g.tmB = nb.m_wn_mn[l];
       if (l == 0) {
         g.amode = A_GATHER_K; g.rowidx = ridx; g.gimage = c->obs_img; g.ldg = c->Dp; g.kb_total = c->Dp / 64;
       } else {
@@ -811,11 +810,11 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   ALLOC(c->err_flag, 1);
   for (int net = 0; net < 2; ++net) {
     NetBufs& nb = c->net[net];
-    nb.act.assign(L + 1, nullptr); nb.dz.assign(L + 1, nullptr); nb.wt.assign(L, nullptr); nb.wn.assign(L, nullptr);
+    nb.act.assign(L + 1, nullptr); nb.dz.assign(L + 1, nullptr); nb.wn.assign(L, nullptr);
     nb.dw_part.assign(L, nullptr); nb.colsum.assign(L, nullptr); nb.dbias.assign(L, nullptr);
     ALLOC(nb.w2img, 16384);
     nb.m_act_k.resize(L + 1); nb.m_act_mn.resize(L + 1); nb.m_dz_k.resize(L + 1); nb.m_dz_mn.resize(L + 1);
-    nb.m_wt.resize(L); nb.m_wn.resize(L); nb.m_dw.resize(L);
+    nb.m_wn_mn.resize(L); nb.m_wn.resize(L); nb.m_dw.resize(L);
     for (int l = 1; l <= L; ++l) {
       ALLOC(nb.act[l], static_cast<size_t>(c->M_pad) * H);
       ALLOC(nb.dz[l], static_cast<size_t>(c->M_pad) * H);
@@ -827,10 +826,9 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     for (int l = 0; l < L; ++l) {
       const int kp = l == 0 ? c->Dp : H;
       const int in_l = l == 0 ? c->D : H;
-      ALLOC(nb.wt[l], static_cast<size_t>(H) * kp);
-      if ((rc = make_tmap(&nb.m_wt[l], nb.wt[l], kp, H, kp, 64, H))) return fail(rc);
+      ALLOC(nb.wn[l], static_cast<size_t>(kp) * H);
+      if ((rc = make_tmap(&nb.m_wn_mn[l], nb.wn[l], H, kp, H, 64, 64))) return fail(rc);
       if (l >= 1) {
-        ALLOC(nb.wn[l], static_cast<size_t>(H) * H);
         if ((rc = make_tmap(&nb.m_wn[l], nb.wn[l], H, H, H, 64, H))) return fail(rc);
         ALLOC(nb.colsum[l], static_cast<size_t>(c->m_tiles) * H);
       }

@@ -70,8 +70,9 @@ struct OptLeaf {
   int nparts;                    // partials to sum (fixed order)
   int part_stride;               // floats between consecutive partials
   float grad_bias;               // constant added to every element (-ent_coef for log_std)
-  __nv_bfloat16* img_t;          // bf16 image [out][ld_t] (transposed; forward GEMM B operand) or null
-  __nv_bfloat16* img_n;          // bf16 image [in][ld_n]  (dX GEMM B operand) or null
+  __nv_bfloat16* img_t;          // unused (was: transposed image); kept null
+  __nv_bfloat16* img_n;          // bf16 image [in][ld_n] of a hidden kernel, ld_n == cols (the B operand of the
+                                 // forward GEMMs as MN-major and of the dX GEMMs as K-major), or null
   int ld_t, ld_n;
   uint8_t* img_w2;               // output-head kernels: 16 KB bf16 hi / lo image of kernel^T in the fused kernel's
                                  // shared-memory layout (fused_step.cuh FS_W2T), or null

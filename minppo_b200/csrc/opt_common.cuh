@@ -89,15 +89,9 @@ MINPPO_DEVINL void step_scalars(const OptArgs& a, int count, float& lr, float& c
   c1 = 1.0f - powf(a.b1, cnt1);
   c2 = 1.0f - powf(a.b2, cnt1);
 }
-// bf16 images of a hidden kernel element (what the tcgen05 GEMMs read)
+// bf16 images of a kernel element (what the tcgen05 GEMMs read)
 MINPPO_DEVINL void write_images(const OptLeaf& L, int i, float p) {
-  if (L.img_t || L.img_n) {
-    const int e = i - L.offset;
-    const int r = e / L.cols, c = e % L.cols;              // kernel [in=r][out=c]
-    const __nv_bfloat16 b = __float2bfloat16_rn(p);
-    if (L.img_t) L.img_t[static_cast<size_t>(c) * L.ld_t + r] = b;
-    if (L.img_n) L.img_n[static_cast<size_t>(r) * L.ld_n + c] = b;
-  }
+  if (L.img_n) L.img_n[i - L.offset] = __float2bfloat16_rn(p);      // same [in][out] layout as the arena leaf: coalesced
   if (L.img_w2) {                                          // head kernel [in=r][out=j] -> kernel^T hi / lo, SW128
     const int e = i - L.offset;
     const int r = e / L.cols, j = e % L.cols;

@@ -43,6 +43,12 @@ if has ncu; then
   python scripts/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1
   cat gpurun_out/launches_summary.txt
 fi
+if has ncudw; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dwopt_kernel" -s 20 -c 2 -f -o gpurun_out/prof_dwopt \
+    python bench.py --quick --steps 1 --warmup 3 > gpurun_out/ncu_dwopt.log 2>&1
+  echo "exit $?" >> gpurun_out/ncu_dwopt.log
+  tail -n 2 gpurun_out/ncu_dwopt.log
+fi
 if has ncufull; then
   timeout 1500 ncu --set full --clock-control none --import-source on \
     -k regex:"umma_gemm_kernel|opt_kernel|fused_step_kernel" -s 40 -c 4 -f -o gpurun_out/prof_full \
