@@ -252,9 +252,10 @@ MINPPO_DEVINL void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
   hi = __bfloat16_as_ushort(h);
   lo = __bfloat16_as_ushort(l);
 }
-// byte offset of element (j, c) inside a [16][ncols] bf16 SW128 tile set (2 KB per 64 columns)
-MINPPO_DEVINL uint32_t sw16_off(int j, int c) {
-  return static_cast<uint32_t>((c >> 6) * 2048 + j * 128 + ((((c & 63) >> 3) ^ (j & 7)) << 4) + (c & 7) * 2);
+// byte offset of element (row rr, column c) inside a [32][ncols] bf16 SW128 tile set (4 KB per 64 columns).
+// The 16-wide head operands are stored as a bf16 hi / lo pair stacked along the rows: rr = part * 16 + j.
+MINPPO_DEVINL uint32_t sw32_off(int rr, int c) {
+  return static_cast<uint32_t>((c >> 6) * 4096 + rr * 128 + ((((c & 63) >> 3) ^ (rr & 7)) << 4) + (c & 7) * 2);
 }
 MINPPO_DEVINL float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 MINPPO_DEVINL float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }

@@ -102,6 +102,20 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   leaf_tab_build(T, a, t, NT);
   __syncthreads();
 
+  // Per-step scalars (two powf, A exp/log): computed up front by the last thread, whose warp has no GEMM role,
+  // so they never sit on the critical path between the barriers.
+  const bool scal_thread = t == NT - 1;
+  int count = 0;
+  float ent = a.entropy_const;                           // A * (0.5 + 0.5 log 2pi) + sum log|scale|
+  if (scal_thread && a.do_apply) {
+    count = __ldcg(a.count);                             // Adam step count BEFORE this step
+    step_scalars(a, count, s_bcast[1], s_bcast[2], s_bcast[3]);
+    if (b == 0 && a.losses_out) {
+      // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the second barrier)
+      for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(__ldcg(a.params + a.off_logstd + j))));
+    }
+  }
+
   // ---- phase 1 ----------------------------------------------------------------------------------
   if (b < p.gemm_ctas) {
     umma_gemm_body<EPI_PARTIAL>(p.gemm, smem_raw);       // PDL wait / trigger inside (TMA producer warp)
@@ -123,12 +137,6 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
         asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (j % lines) * 128));
       }
     }
-  }
-  const int count = a.do_apply ? __ldcg(a.count) : 0;   // Adam step count BEFORE this step
-  float ent = a.entropy_const;                           // A * (0.5 + 0.5 log 2pi) + sum log|scale|
-  if (a.do_apply && b == 0 && t == 0 && a.losses_out) {
-    // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the second barrier)
-    for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(__ldcg(a.params + a.off_logstd + j))));
   }
   DW_STAMP(1);
   grid_barrier(a.barrier, a.err_flag);
@@ -152,7 +160,6 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     const float tot = block_sum<DWOPT_THREADS>(v, scratch);
     if (t == 0) s_bcast[0] = sqrtf(tot);
   }
-  if (t == 32) step_scalars(a, count, s_bcast[1], s_bcast[2], s_bcast[3]);
   __syncthreads();
   AdamScalars sc;
   sc.gnorm = s_bcast[0]; sc.lr = s_bcast[1]; sc.c1 = s_bcast[2]; sc.c2 = s_bcast[3];
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   apply_adam(a, T, sc, b * NT + t, G * NT);
   __syncthreads();
   DW_STAMP(5);
-  if (b == 0 && t == 0) {
+  if (b == 0 && scal_thread) {
     *a.count = count + 1;
     if (a.losses_out) {
       // gflat[P] = sum max(vl, vlc), gflat[P+1] = sum min(l1, l2) over the global minibatch

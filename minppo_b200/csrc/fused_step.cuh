@@ -17,9 +17,8 @@
 // hi/lo pair (x = hi + lo to 2^-17), the cross terms hi*hi + hi*lo + lo*hi are accumulated in
 // fp32, so the heads keep fp32-level accuracy while costing a few dozen tiny UMMAs.
 //
-// Warp roles: warp 0 TMA producer (weight k-blocks through a 2-stage ring), warp 1 TMEM
-// allocator + MMA issuer, warps 2..9 workers (gather, epilogues, loss), two per TMEM lane
-// quadrant.  H1, dZ2 and dZ1 are also written to HBM (bf16, TMA stores) for the split-K
+// Warp roles: warps 0..7 workers (gather, epilogues, loss), two per TMEM lane quadrant; warp 8 TMA
+// producer (weight k-blocks through a 2-stage ring); warp 9 TMEM allocator + MMA issuer.  H1, dZ2 and dZ1 are also written to HBM (bf16, TMA stores) for the split-K
 // weight-gradient GEMM (umma_gemm.cuh, EPI_PARTIAL), which runs as its own launch over all tiles.
 #pragma once
 
@@ -30,14 +29,17 @@
 namespace minppo {
 
 constexpr int FS_THREADS = 320;
-constexpr int FS_WORKERS = 256;
+constexpr int FS_WORKERS = 256;                         // warps 0..7
+constexpr int FS_TMA_WARP = 8;                          // weight producer
+constexpr int FS_MMA_WARP = 9;                          // TMEM allocator + MMA issuer: the highest warp id wins the
+                                                        // issue arbiter, so the single issuing thread is never starved
 constexpr int FS_AP = 16;                               // padded head width (A <= 16)
 constexpr int FS_R0 = 0;                                // H1                  64 KB
 constexpr int FS_R1 = 65536;                            // X / H2 / dZ2 / dZ1  64 KB
 constexpr int FS_RB = 131072;                           // weight ring   2 x 32 KB
 constexpr int FS_BSTAGE = 32768;
-constexpr int FS_W2T = 196608;                          // head kernel^T bf16 [16][H] SW128: hi (+0), lo (+8192)
-constexpr int FS_GT = FS_W2T + 16384;                   // g^T bf16 [16][128] SW128: hi (+0), lo (+4096)
+constexpr int FS_W2T = 196608;                          // head kernel^T bf16 [32][H] SW128: rows 0..15 hi, 16..31 lo; 4 KB per 64 columns
+constexpr int FS_GT = FS_W2T + 16384;                   // g^T bf16 [32][128] SW128: rows 0..15 hi, 16..31 lo; 4 KB per 64 rows
 constexpr int FS_BIAS = FS_GT + 8192;                   // [2][256] f32
 constexpr int FS_HB = FS_BIAS + 2048;                   // f32: head bias [16], log_std [16], 1/scale [16], log-det [1]
 constexpr int FS_RED = FS_HB + 256;                     // [8][40] f32
@@ -206,7 +208,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   uint64_t* gr = bars + 11;             // g^T hi/lo written
   uint64_t* h1r = bars + 12;            // [4] H1 columns [64 b, 64 b + 64) in R0 (k-block b of the L2 GEMM)
   uint64_t* dz2r = bars + 16;           // [4] dZ2 columns [64 b, 64 b + 64) in R1 (k-block b of the dH1 GEMM)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* w0x = bars + 20;            // [2] W0 k-blocks 2, 3 parked in R0 (free until epilogue 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int net = static_cast<int>(blockIdx.x) / p.m_tiles;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   const uint32_t R0 = base + FS_R0, R1 = base + FS_R1, RB = base + FS_RB;
   const uint32_t W2T = base + FS_W2T, GT = base + FS_GT;
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == FS_WORKERS) {
     FS_STAMP(16);
     mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
     mbar_init(&empty_bar[0], 1); mbar_init(&empty_bar[1], 1);
@@ -224,9 +227,10 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     mbar_init(xfull, FS_WORKERS);
     mbar_init(h2r, 8); mbar_init(gr, 8);
     for (int b = 0; b < 4; ++b) { mbar_init(&h1r[b], 8); mbar_init(&dz2r[b], 8); }
+    mbar_init(&w0x[0], 1); mbar_init(&w0x[1], 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == FS_MMA_WARP) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -235,31 +239,40 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256;
-  const uint32_t acc_head = acc1;               // [256, 272): head outputs (after acc1 is drained)
-  const uint32_t acc_dw = acc1 + 16;            // [272, 272 + 16 * ceil(H/128)): head-kernel gradient
+  const uint32_t acc_head = acc1;               // [256, 288): head outputs, hi | lo halves (after acc1 is drained)
+  const uint32_t acc_dw = acc1 + 32;            // [288, 288 + 32 * ceil(H/128)): head-kernel gradient, hi | lo halves
 
-  if (warp == 0) {
+  if (warp == FS_TMA_WARP) {
     // ===================== weight producer: W0^T, W1^T, W1 k-blocks through the ring ==========
     if (elect_one()) {
       tma_prefetch_desc(&G.tm_w0); tma_prefetch_desc(&G.tm_w1); tma_prefetch_desc(&G.tm_w1k);
       griddep_wait();                 // the weight images are rewritten by the previous optimizer step
       const uint32_t bytes = static_cast<uint32_t>(H) * 128u;
-      const int total = nk0 + 2 * nkH;
+      // Ring items: W0 k-blocks 0, 1, then W1 (L2), then W1 (dH1).  W0 k-blocks 2.. do not wait for a ring slot:
+      // they are parked in R0, which nothing touches before epilogue 1, so the whole L1 GEMM is fed up front.
+      const int nring0 = nk0 < 2 ? nk0 : 2;
+      const int total = nring0 + 2 * nkH;
       for (int i = 0; i < total; ++i) {
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], bytes);
-        if (i < nk0 + nkH) {            // forward: k-block of W0 / W1 as stored, one {64 out, 64 in} box per 64 outputs
-          const CUtensorMap* m = i < nk0 ? &G.tm_w0 : &G.tm_w1;
-          const int kb = i < nk0 ? i : i - nk0;
+        if (i < nring0 + nkH) {         // forward: k-block of W0 / W1 as stored, one {64 out, 64 in} box per 64 outputs
+          const CUtensorMap* m = i < nring0 ? &G.tm_w0 : &G.tm_w1;
+          const int kb = i < nring0 ? i : i - nring0;
           for (int c = 0; c < nkH; ++c) tma_load_2d(RB + s * FS_BSTAGE + c * 8192, m, &full_bar[s], c * 64, kb * 64);
         } else {                        // dH1: k-block (64 outputs) of W1 for all H inputs
-          tma_load_2d(RB + s * FS_BSTAGE, &G.tm_w1k, &full_bar[s], (i - nk0 - nkH) * 64, 0);
+          tma_load_2d(RB + s * FS_BSTAGE, &G.tm_w1k, &full_bar[s], (i - nring0 - nkH) * 64, 0);
+        }
+        if (i == nring0 - 1) {
+          for (int kb = 2; kb < nk0; ++kb) {
+            mbar_arrive_expect_tx(&w0x[kb - 2], bytes);
+            for (int c = 0; c < nkH; ++c) tma_load_2d(R0 + (kb - 2) * FS_BSTAGE + c * 8192, &G.tm_w0, &w0x[kb - 2], c * 64, kb * 64);
+          }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == FS_MMA_WARP) {
     // ===================== MMA issuer ==========================================================
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(H), 0u, 0u);
@@ -287,27 +300,35 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       mbar_wait(xfull, 0);
       tc_fence_after();
       FS_STAMP(18);
-      gemm(R1, nk0, acc0, nullptr, true);    // L1: X W0
+      gemm(R1, nk0 < 2 ? nk0 : 2, acc0, nullptr, true);    // L1: X W0, k-blocks 0, 1 from the ring
+      for (int kb = 2; kb < nk0; ++kb) {                   // ... k-blocks 2, 3 parked in R0
+        mbar_wait(&w0x[kb - 2], 0);
+        tc_fence_after();
+        const uint32_t sa = R1 + kb * 16384, sb = R0 + (kb - 2) * FS_BSTAGE;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_bf16(acc0, umma_smem_desc(sa + j * 32, 16, 1024), umma_smem_desc(sb + j * 2048, 8192, 1024), idesc_bmn, 1u);
+      }
       umma_commit(accf0);
       FS_STAMP(19);
       FS_STAMP(20);
       gemm(R0, nkH, acc1, h1r, true);        // L2: H1 W1
       umma_commit(accf1);
       FS_STAMP(21);
-      // ---- head forward: out[128 x 16] = H2 (W2_hi + W2_lo); A = H2 K-major, B = W2^T K-major, N = 16
+      // ---- head forward: [out_hi | out_lo][128 x 32] = H2 [W2_hi | W2_lo]; A = H2 K-major, B = W2^T K-major with the
+      //      bf16 hi / lo halves stacked along N (the workers add the two 16-column halves)
       mbar_wait(h2r, 0);
       tc_fence_after();
       {
-        const uint32_t idesc_h = umma_idesc_bf16(128, 16u, 0u, 0u);
+        const uint32_t idesc_h = umma_idesc_bf16(128, 32u, 0u, 0u);
         uint32_t accum = 0;
-        for (int part = 0; part < 2; ++part)
-          for (int kb = 0; kb < nkH; ++kb)
+        for (int kb = 0; kb < nkH; ++kb)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              umma_bf16(acc_head, umma_smem_desc(R1 + kb * 16384 + j * 32, 16, 1024),
-                        umma_smem_desc(W2T + part * 8192 + kb * 2048 + j * 32, 16, 1024), idesc_h, accum);
-              accum = 1;
-            }
+          for (int j = 0; j < 4; ++j) {
+            umma_bf16(acc_head, umma_smem_desc(R1 + kb * 16384 + j * 32, 16, 1024),
+                      umma_smem_desc(W2T + kb * 4096 + j * 32, 16, 1024), idesc_h, accum);
+            accum = 1;
+          }
         umma_commit(headf);
       }
       FS_STAMP(24);
@@ -315,22 +336,19 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       mbar_wait(gr, 0);
       tc_fence_after();
       {
-        // dA2[128 x H] = g W2^T, K = 16: A = g^T (MN-major, 64-row chunks 2 KB apart), B = W2^T (MN-major)
+        // dA2[128 x H] = g W2^T, K = 16: A = g^T (MN-major, 64-row panels 4 KB apart), B = W2^T (MN-major, 64-column
+        // panels 4 KB apart); the lo halves sit 16 rows = 2 KB into each panel
         const uint32_t idesc_a = umma_idesc_bf16(128, static_cast<uint32_t>(H), 1u, 1u);
-        umma_bf16(acc0, umma_smem_desc(GT, 2048, 1024), umma_smem_desc(W2T, 2048, 1024), idesc_a, 0u);            // hi * hi
-        umma_bf16(acc0, umma_smem_desc(GT, 2048, 1024), umma_smem_desc(W2T + 8192, 2048, 1024), idesc_a, 1u);     // hi * lo
-        umma_bf16(acc0, umma_smem_desc(GT + 4096, 2048, 1024), umma_smem_desc(W2T, 2048, 1024), idesc_a, 1u);     // lo * hi
-        // dW2[c][j] = sum_r H2[r][c] g[r][j]: A = H2 (MN-major: M = c, K = rows), B = g^T (K-major, N = 16)
-        const uint32_t idesc_w = umma_idesc_bf16(128, 16u, 1u, 0u);
+        umma_bf16(acc0, umma_smem_desc(GT, 4096, 1024), umma_smem_desc(W2T, 4096, 1024), idesc_a, 0u);            // hi * hi
+        umma_bf16(acc0, umma_smem_desc(GT, 4096, 1024), umma_smem_desc(W2T + 2048, 4096, 1024), idesc_a, 1u);     // hi * lo
+        umma_bf16(acc0, umma_smem_desc(GT + 2048, 4096, 1024), umma_smem_desc(W2T, 4096, 1024), idesc_a, 1u);     // lo * hi
+        // [dW2_hi | dW2_lo][c][j] = sum_r H2[r][c] g[r][j]: A = H2 (MN-major: M = c, K = rows), B = g^T (K-major, N = 32)
+        const uint32_t idesc_w = umma_idesc_bf16(128, 32u, 1u, 0u);
         for (int mh = 0; mh < (H + 127) / 128; ++mh) {
-          uint32_t accum = 0;
-          for (int part = 0; part < 2; ++part)
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              umma_bf16(acc_dw + 16 * mh, umma_smem_desc(R1 + 2 * mh * 16384 + t * 2048, 16384, 1024),
-                        umma_smem_desc(GT + part * 4096 + (t >> 2) * 2048 + (t & 3) * 32, 16, 1024), idesc_w, accum);
-              accum = 1;
-            }
+          for (int t = 0; t < 8; ++t)
+            umma_bf16(acc_dw + 32 * mh, umma_smem_desc(R1 + 2 * mh * 16384 + t * 2048, 16384, 1024),
+                      umma_smem_desc(GT + (t >> 2) * 4096 + (t & 3) * 32, 16, 1024), idesc_w, t > 0 ? 1u : 0u);
         }
         umma_commit(bwdf);
       }
@@ -344,8 +362,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     }
   } else {
     // ===================== workers ==============================================================
-    const int wt = static_cast<int>(threadIdx.x) - 64;          // 0..255
-    const int ww = warp - 2;                                     // 0..7
+    const int wt = static_cast<int>(threadIdx.x);               // 0..255
+    const int ww = warp;                                         // 0..7
     const int q = warp & 3, hf = ww >> 2;
     const int erow = q * 32 + lane;                              // epilogue row == TMEM lane
     const int act = G.act, aout = G.aout;
@@ -370,26 +388,6 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     }
     cp_async_commit();
     if (wt == 0) FS_STAMP(26);
-    // per-row loss inputs, prefetched (used after the head GEMM); static within one update
-    float in0 = 0.f, in1 = 0.f, actn[FS_AP];
-#pragma unroll
-    for (int j = 0; j < FS_AP; ++j) actn[j] = 0.f;
-    if (live) {
-      if (net == 0) {
-        in0 = p.logp_old[src_l]; in1 = p.adv[src_l];
-        const float* ap = p.action + static_cast<size_t>(src_l) * aout;
-        if ((aout & 1) == 0) {                                     // rows are 8-byte aligned: half the load wavefronts
-#pragma unroll
-          for (int j = 0; j < FS_AP; j += 2)
-            if (j < aout) { const float2 v = *reinterpret_cast<const float2*>(ap + j); actn[j] = v.x; actn[j + 1] = v.y; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < FS_AP; ++j) if (j < aout) actn[j] = ap[j];
-        }
-      } else {
-        in0 = p.v_old[src_l]; in1 = p.tgt[src_l];
-      }
-    }
     const float adv_sum = *p.adv_sum, adv_sq = *p.adv_sq;
     if (wt == 0) FS_STAMP(27);
     // ---- everything below reads what the previous optimizer step wrote (PDL: see common.cuh) -------
@@ -429,6 +427,26 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     if (net == 0 && ww == 0 && lane == 0) {
       for (int kb = 0; kb < nk0; ++kb) tma_store_2d(R1 + kb * 16384, &p.tm_xg, kb * 64, tile * 128);
       tma_store_commit();
+    }
+    // per-row loss inputs, requested while the L1 GEMM runs (used after the head GEMM)
+    float in0 = 0.f, in1 = 0.f, actn[FS_AP];
+#pragma unroll
+    for (int j = 0; j < FS_AP; ++j) actn[j] = 0.f;
+    if (live) {
+      if (net == 0) {
+        in0 = p.logp_old[src_l]; in1 = p.adv[src_l];
+        const float* ap = p.action + static_cast<size_t>(src_l) * aout;
+        if ((aout & 1) == 0) {                                     // rows are 8-byte aligned: half the load wavefronts
+#pragma unroll
+          for (int j = 0; j < FS_AP; j += 2)
+            if (j < aout) { const float2 v = *reinterpret_cast<const float2*>(ap + j); actn[j] = v.x; actn[j + 1] = v.y; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < FS_AP; ++j) if (j < aout) actn[j] = ap[j];
+        }
+      } else {
+        in0 = p.v_old[src_l]; in1 = p.tgt[src_l];
+      }
     }
 
     // ---- epilogue 1: H1 = act(acc0 + b0) -> R0, then TMA store to HBM ------------------------------
@@ -475,8 +493,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     for (int j = 0; j < FS_AP; ++j) { dls[j] = 0.f; g[j] = 0.f; }
     if (hf == 0) {
       float out[FS_AP];
-      tmem_ld_32x16(acc_head + (static_cast<uint32_t>(q * 32) << 16), out);
-      tmem_ld_wait();
+      {
+        float o2[32];
+        tmem_ld_32x32(acc_head + (static_cast<uint32_t>(q * 32) << 16), o2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < FS_AP; ++j) out[j] = o2[j] + o2[FS_AP + j];      // W2_hi and W2_lo contributions
+      }
       if (live) {
         const float inv_n = p.inv_mb;
         if (net == 0) {
@@ -528,9 +551,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       for (int j = 0; j < FS_AP; ++j) {
         uint32_t hi, lo;
         split_bf16(g[j], hi, lo);
-        const uint32_t off = sw16_off(j, erow);
-        sts_u16(GT + off, hi);
-        sts_u16(GT + 4096 + off, lo);
+        sts_u16(GT + sw32_off(j, erow), hi);
+        sts_u16(GT + sw32_off(16 + j, erow), lo);
       }
     }
     fence_proxy_async_smem();
@@ -563,8 +585,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     if (wt == 0) FS_STAMP(8);
     if (hf * 128 < H) {                                          // warp (q, hf) reads the c-tile mh = hf
       float dw[FS_AP];
-      tmem_ld_32x16(acc_dw + 16 * hf + (static_cast<uint32_t>(q * 32) << 16), dw);
-      tmem_ld_wait();
+      {
+        float d2[32];
+        tmem_ld_32x32(acc_dw + 32 * hf + (static_cast<uint32_t>(q * 32) << 16), d2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < FS_AP; ++j) dw[j] = d2[j] + d2[FS_AP + j];       // g_hi and g_lo contributions
+      }
       const int c = hf * 128 + erow;
       if (c < H) {
 #pragma unroll
@@ -609,7 +636,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == FS_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace minppo

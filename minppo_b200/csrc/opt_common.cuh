@@ -97,9 +97,8 @@ MINPPO_DEVINL void write_images(const OptLeaf& L, int i, float p) {
     const int r = e / L.cols, j = e % L.cols;
     uint32_t hi, lo;
     split_bf16(p, hi, lo);
-    const uint32_t off = sw16_off(j, r);
-    *reinterpret_cast<uint16_t*>(L.img_w2 + off) = static_cast<uint16_t>(hi);
-    *reinterpret_cast<uint16_t*>(L.img_w2 + 8192 + off) = static_cast<uint16_t>(lo);
+    *reinterpret_cast<uint16_t*>(L.img_w2 + sw32_off(j, r)) = static_cast<uint16_t>(hi);
+    *reinterpret_cast<uint16_t*>(L.img_w2 + sw32_off(16 + j, r)) = static_cast<uint16_t>(lo);
   }
 }
 
@@ -199,20 +198,20 @@ MINPPO_DEVINL float reduce_leaves(const OptArgs& a, const LeafTab& T, int first,
   return ss;
 }
 
-// clip + Adam over the arena, three elements in flight per thread; gradient from gflat
+// clip + Adam over the arena, four elements in flight per thread; gradient from gflat
 MINPPO_DEVINL void apply_adam(const OptArgs& a, const LeafTab& T, const AdamScalars& sc, int first, int stride) {
   const int P = a.P;
   int l = 0;
 #pragma unroll 1
-  for (int i0 = first; i0 < P; i0 += 3 * stride) {
-    float g[3], pv[3], mv[3], nv[3];
+  for (int i0 = first; i0 < P; i0 += 4 * stride) {
+    float g[4], pv[4], mv[4], nv[4];
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * stride;
       if (i < P) { g[u] = __ldcg(a.gflat + i); pv[u] = __ldcg(a.params + i); mv[u] = __ldcg(a.mu + i); nv[u] = __ldcg(a.nu + i); }
     }
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * stride;
       if (i < P) {
         adam_element(a, sc, g[u], pv[u], mv[u], nv[u]);
