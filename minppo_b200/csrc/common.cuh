@@ -86,6 +86,25 @@ MINPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Busy-polling wait (mbarrier.test_wait never suspends the thread): for the single MMA-issuing thread, whose
+// wake-up latency after a suspended try_wait showed up as ~2k idle cycles in front of a GEMM.
+MINPPO_DEVINL void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
 // generic-proxy writes (st.shared / cp.async) -> visible to the async proxy (UMMA / TMA)
 MINPPO_DEVINL void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -284,8 +284,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
         for (int kb = 0; kb < nk; ++kb, ++i) {
           const int s = i & 1;
           const uint32_t ph = (i >> 1) & 1;
-          if (a_ready) mbar_wait(&a_ready[kb], 0);
-          mbar_wait(&full_bar[s], ph);
+          if (a_ready) mbar_wait_spin(&a_ready[kb], 0);
+          mbar_wait_spin(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = a_base + kb * 16384, sb = RB + s * FS_BSTAGE;
 #pragma unroll
@@ -297,12 +297,12 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
         }
       };
       FS_STAMP(17);
-      mbar_wait(xfull, 0);
+      mbar_wait_spin(xfull, 0);
       tc_fence_after();
       FS_STAMP(18);
       gemm(R1, nk0 < 2 ? nk0 : 2, acc0, nullptr, true);    // L1: X W0, k-blocks 0, 1 from the ring
       for (int kb = 2; kb < nk0; ++kb) {                   // ... k-blocks 2, 3 parked in R0
-        mbar_wait(&w0x[kb - 2], 0);
+        mbar_wait_spin(&w0x[kb - 2], 0);
         tc_fence_after();
         const uint32_t sa = R1 + kb * 16384, sb = R0 + (kb - 2) * FS_BSTAGE;
 #pragma unroll
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       FS_STAMP(21);
       // ---- head forward: [out_hi | out_lo][128 x 32] = H2 [W2_hi | W2_lo]; A = H2 K-major, B = W2^T K-major with the
       //      bf16 hi / lo halves stacked along N (the workers add the two 16-column halves)
-      mbar_wait(h2r, 0);
+      mbar_wait_spin(h2r, 0);
       tc_fence_after();
       {
         const uint32_t idesc_h = umma_idesc_bf16(128, 32u, 0u, 0u);
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       }
       FS_STAMP(24);
       // ---- backward through the head --------------------------------------------------------------
-      mbar_wait(gr, 0);
+      mbar_wait_spin(gr, 0);
       tc_fence_after();
       {
         // dA2[128 x H] = g W2^T, K = 16: A = g^T (MN-major, 64-row panels 4 KB apart), B = W2^T (MN-major, 64-column

@@ -194,7 +194,9 @@ def test_fused_step_kernel_equals_layerwise_kernels(name, cuda_device):
     assert rel_err(a["losses"], b["losses"]) < 2e-4
     # the gradient read back is the LAST step's; on config 1 (5-row minibatches, 128 steps) the two
     # runs have drifted apart by then, so the tight check is for the few-step case only
-    assert rel_err(a["grad"][:-4], b["grad"][:-4]) < (2e-3 if name == "medium" else 1e-1)
+    # (both paths are separately held to the oracle at 5e-3; between them the fused path's tensor-core
+    # heads (bf16 hi/lo split) vs the fp32 SIMT heads drift apart by ~2e-3 of the largest gradient entry)
+    assert rel_err(a["grad"][:-4], b["grad"][:-4]) < (4e-3 if name == "medium" else 1e-1)
     lr = hp.opt_lr if not hp.anneal_lr else hp.training_lr
     nsteps = hp.update_epochs * hp.num_minibatches
     assert np.abs(a["params"] - b["params"]).max() < lr * (2.0 + 0.15 * nsteps)
