@@ -118,8 +118,10 @@ MINPPO_DEVINL float dclip_f(float x, float lo, float hi) {
   return (x > lo && x < hi) ? 1.f : ((x == lo || x == hi) ? 0.5f : 0.f);
 }
 // accumulator (32 columns per chunk) -> +bias, activation, bf16 -> swizzled smem tile
+// (not inlined: epilogue 1 and 2 share one copy of the code -- the kernel's straight-line worker path is larger than
+//  the instruction cache, and "no instruction" was a quarter of its stall samples)
 template <int ACT>
-MINPPO_DEVINL void epilogue_act_t(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int row, int q, int col0,
+__device__ __noinline__ void epilogue_act_t(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int row, int q, int col0,
                                   int ncols) {
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
   for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
@@ -157,7 +159,7 @@ MINPPO_DEVINL void epilogue_act(uint32_t tmem_acc, uint32_t dst_base, const floa
 // every thread touches only its own 16-byte chunks).  The bias gradients (column sums of dZ) are
 // not formed here: the weight-gradient GEMM gets them from the tensor core as ones x dZ.
 template <int ACT>
-MINPPO_DEVINL void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, int row, int q, int col0,
+__device__ __noinline__ void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, int row, int q, int col0,
                                    int ncols) {
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
   for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
@@ -401,27 +403,28 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     float hbv = 0.f;
     if (wt < 16) hbv = wt < aout ? __ldcg(G.b2 + wt) : 0.f;
     else if (wt < 32) hbv = (net == 0 && wt - 16 < aout) ? __ldcg(p.log_std + wt - 16) : 0.f;
-    float logdet = 0.f;
-    if (wt == 32 && net == 0) {
+    for (int i = wt; i < 1024; i += FS_WORKERS) cp_async_16(W2T + i * 16, G.w2img + i);
+    cp_async_commit();
+    if (wt == 0) FS_STAMP(29);
+    // the L1 GEMM needs only the gathered rows: publish them before the (slower) staging of the small operands
+    cp_async_wait<1>();
+    fence_proxy_async_smem();
+    mbar_arrive(xfull);
+    if (wt == 0) FS_STAMP(31);
+    if (wt < H) { bias_s[wt] = b0v; bias_s[256 + wt] = b1v; }
+    if (wt < 32) hb[wt] = hbv;
+    if (wt >= 16 && wt < 32) hb[16 + wt] = 1.f / expf(hbv);          // 1 / scale (unused columns: 1)
+    if (net == 0 && wt == 32) {
       // distrax: log|det| = sum log|scale|, scale = exp(log_std); summed in index order (train.py:223)
-      float ls[FS_AP];
+      float ls[FS_AP], logdet = 0.f;
 #pragma unroll
       for (int j = 0; j < FS_AP; ++j) ls[j] = j < aout ? __ldcg(p.log_std + j) : 0.f;
 #pragma unroll
       for (int j = 0; j < FS_AP; ++j) if (j < aout) logdet += logf(fabsf(expf(ls[j])));
+      hb[48] = logdet;
     }
-    for (int i = wt; i < 1024; i += FS_WORKERS) cp_async_16(W2T + i * 16, G.w2img + i);
-    cp_async_commit();
-    if (wt == 0) FS_STAMP(29);
-    if (wt < H) { bias_s[wt] = b0v; bias_s[256 + wt] = b1v; }
-    if (wt < 32) hb[wt] = hbv;
-    if (wt >= 16 && wt < 32) hb[16 + wt] = 1.f / expf(hbv);          // 1 / scale (unused columns: 1)
-    if (wt == 32) hb[48] = logdet;
     if (wt == 0) FS_STAMP(30);
     cp_async_wait<0>();
-    if (wt == 0) FS_STAMP(31);
-    fence_proxy_async_smem();
-    mbar_arrive(xfull);
     worker_bar();                                                // biases / hb / W2T visible to all workers; X complete
     if (wt == 0) FS_STAMP(1);
     if (net == 0 && ww == 0 && lane == 0) {

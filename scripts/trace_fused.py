@@ -28,11 +28,11 @@ out = torch.empty((n, 32), dtype=torch.int64, device=dev)
 _lib.check(learner.lib.minppo_ctx_read(learner._h, 7, out.data_ptr(), out.numel() * 8, torch.cuda.current_stream(dev).cuda_stream))
 torch.cuda.synchronize()
 tr = out.cpu().numpy()
-names = {26: "w: gather issued", 27: "w: loss inputs requested", 28: "w: griddep wait passed", 29: "w: staging loads issued", 30: "w: staging stored", 31: "w: cp.async complete", 16: "kernel start (t0)", 0: "workers start", 1: "gather+stage done, xfull", 17: "mma: start", 18: "mma: xfull seen", 19: "mma: L1 issued",
+names = {26: "w: gather issued", 27: "w: loss inputs requested", 28: "w: griddep wait passed", 29: "w: staging loads issued", 30: "w: staging stored", 31: "w: gather landed, xfull arrive", 16: "kernel start (t0)", 0: "workers start", 1: "gather+stage done, xfull", 17: "mma: start", 18: "mma: xfull seen", 19: "mma: L1 issued",
          2: "w: acc0 ready", 3: "w: epi1 done (h1r)", 20: "mma: h1r seen", 21: "mma: L2 issued", 4: "w: acc1 ready", 5: "w: epi2 done (h2r)",
          24: "mma: head fwd issued", 6: "w: head out ready", 7: "w: loss done + tile sums", 25: "mma: dA2/dW2 issued", 8: "w: bwd accs ready",
          9: "w: dz2 epilogue done (dz2r)", 22: "mma: dz2r seen", 23: "mma: dH1 issued", 10: "w: dh1 acc ready", 11: "w: epi3 done", 12: "w: stores done"}
-order = [16, 0, 17, 26, 27, 28, 29, 30, 31, 1, 18, 19, 2, 3, 20, 21, 4, 5, 24, 6, 7, 25, 8, 9, 22, 23, 10, 11, 12]
+order = [16, 0, 17, 26, 27, 28, 29, 31, 30, 1, 18, 19, 2, 3, 20, 21, 4, 5, 24, 6, 7, 25, 8, 9, 22, 23, 10, 11, 12]
 for cta in (0, 1, n // 2, n - 1):
     t0 = tr[cta, 16]
     print(f"--- CTA {cta} ({'actor' if cta < n // 2 else 'critic'})")
