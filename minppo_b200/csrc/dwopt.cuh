@@ -143,8 +143,40 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   DW_STAMP(2);
 
   // ---- phase 2 ----------------------------------------------------------------------------------
-  if (!has_extra) ss += reduce_leaves<false>(a, T, b * NT + t, G * NT);
-  ss += reduce_leaves<true>(a, T, b * NT + t, G * NT);
+  // Fast path (every shape the fused step supports): at most one 4-element unit of a hidden kernel / bias per
+  // thread, so the reduced gradient and the optimizer state of those elements stay in registers across the second
+  // barrier and only the few small leaves go through gflat.
+  int n_units = 0;
+  for (int l = 0; l < T.nleaves; ++l)
+    if (T.leaf[l].late) n_units += T.size[l] >> 2;
+  const bool fast = n_units <= G * NT;
+  const int gtid = b * NT + t;
+  float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float pv[4], mv[4], nv[4];
+  int ul = -1, ui = 0;                                   // leaf and first arena index of this thread's unit
+  if (!has_extra) ss += reduce_leaves<false>(a, T, gtid, G * NT);
+  if (fast) {
+    if (gtid < n_units) {
+      int x = gtid, l = 0;
+      for (; l < T.nleaves; ++l) {
+        if (!T.leaf[l].late) continue;
+        const int n = T.size[l] >> 2;
+        if (x < n) break;
+        x -= n;
+      }
+      const OptLeaf& L = T.leaf[l];
+      ul = l; ui = L.offset + 4 * x;
+      if (a.do_apply) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { pv[u] = __ldcg(a.params + ui + u); mv[u] = __ldcg(a.mu + ui + u); nv[u] = __ldcg(a.nu + ui + u); }
+      }
+      g4 = sum_partials16_v4(L.grad_src + L.src_offset + 4 * x, L.nparts, L.part_stride);
+      if (!a.do_apply || a.keep_gflat) { float* dst = a.gflat + ui; dst[0] = g4.x; dst[1] = g4.y; dst[2] = g4.z; dst[3] = g4.w; }
+      ss = fmaf(g4.x, g4.x, ss); ss = fmaf(g4.y, g4.y, ss); ss = fmaf(g4.z, g4.z, ss); ss = fmaf(g4.w, g4.w, ss);
+    }
+  } else {
+    ss += reduce_leaves<true>(a, T, gtid, G * NT);
+  }
   if (!a.do_apply) return;
   const float bs = block_sum<DWOPT_THREADS>(ss, scratch);
   if (t == 0) a.block_ss[b] = bs;
@@ -164,7 +196,24 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   AdamScalars sc;
   sc.gnorm = s_bcast[0]; sc.lr = s_bcast[1]; sc.c1 = s_bcast[2]; sc.c2 = s_bcast[3];
   sc.trigger = sc.gnorm < a.max_norm;                    // optax.clip_by_global_norm
-  apply_adam(a, T, sc, b * NT + t, G * NT);
+  if (fast) {
+    if (ul >= 0) {
+      const OptLeaf& L = T.leaf[ul];
+      const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        adam_element(a, sc, gv[u], pv[u], mv[u], nv[u]);
+        a.params[ui + u] = pv[u];
+        a.mu[ui + u] = mv[u];
+        a.nu[ui + u] = nv[u];
+      }
+      if (L.img_n)             // 4 consecutive bf16 of the kernel image (unit index is a multiple of 4: 8-byte aligned)
+        *reinterpret_cast<uint2*>(L.img_n + (ui - L.offset)) = make_uint2(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]));
+    }
+    apply_adam_class<false>(a, T, sc, gtid, G * NT);
+  } else {
+    apply_adam(a, T, sc, gtid, G * NT);
+  }
   __syncthreads();
   DW_STAMP(5);
   if (b == 0 && scal_thread) {

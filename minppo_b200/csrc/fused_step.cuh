@@ -431,27 +431,6 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       for (int kb = 0; kb < nk0; ++kb) tma_store_2d(R1 + kb * 16384, &p.tm_xg, kb * 64, tile * 128);
       tma_store_commit();
     }
-    // per-row loss inputs, requested while the L1 GEMM runs (used after the head GEMM)
-    float in0 = 0.f, in1 = 0.f, actn[FS_AP];
-#pragma unroll
-    for (int j = 0; j < FS_AP; ++j) actn[j] = 0.f;
-    if (live) {
-      if (net == 0) {
-        in0 = p.logp_old[src_l]; in1 = p.adv[src_l];
-        const float* ap = p.action + static_cast<size_t>(src_l) * aout;
-        if ((aout & 1) == 0) {                                     // rows are 8-byte aligned: half the load wavefronts
-#pragma unroll
-          for (int j = 0; j < FS_AP; j += 2)
-            if (j < aout) { const float2 v = *reinterpret_cast<const float2*>(ap + j); actn[j] = v.x; actn[j + 1] = v.y; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < FS_AP; ++j) if (j < aout) actn[j] = ap[j];
-        }
-      } else {
-        in0 = p.v_old[src_l]; in1 = p.tgt[src_l];
-      }
-    }
-
     // ---- epilogue 1: H1 = act(acc0 + b0) -> R0, then TMA store to HBM ------------------------------
     mbar_wait(accf0, 0);
     tc_fence_after();
@@ -474,6 +453,29 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       }
       tma_store_commit();
     }
+
+    // per-row loss inputs, requested here, in the shadow of the L2 GEMM's tail (32 distinct lines per load
+    // instruction: ~2.5k cycles of load/store-unit time that must not sit in front of a GEMM or an epilogue)
+    float in0 = 0.f, in1 = 0.f, actn[FS_AP];
+#pragma unroll
+    for (int j = 0; j < FS_AP; ++j) actn[j] = 0.f;
+    if (live) {
+      if (net == 0) {
+        in0 = p.logp_old[src_l]; in1 = p.adv[src_l];
+        const float* ap = p.action + static_cast<size_t>(src_l) * aout;
+        if ((aout & 1) == 0) {                                     // rows are 8-byte aligned: half the load wavefronts
+#pragma unroll
+          for (int j = 0; j < FS_AP; j += 2)
+            if (j < aout) { const float2 v = *reinterpret_cast<const float2*>(ap + j); actn[j] = v.x; actn[j + 1] = v.y; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < FS_AP; ++j) if (j < aout) actn[j] = ap[j];
+        }
+      } else {
+        in0 = p.v_old[src_l]; in1 = p.tgt[src_l];
+      }
+    }
+
 
     // ---- epilogue 2: H2 = act(acc1 + b1) -> R1 -------------------------------------------------------
     mbar_wait(accf1, 0);

@@ -225,4 +225,30 @@ MINPPO_DEVINL void apply_adam(const OptArgs& a, const LeafTab& T, const AdamScal
   }
 }
 
+// clip + Adam restricted to the leaves of one class (same job numbering as reduce_leaves<LATE>, one element per
+// job): used by the merged kernel for the small leaves when the hidden-kernel elements stay in registers.
+template <bool LATE>
+MINPPO_DEVINL void apply_adam_class(const OptArgs& a, const LeafTab& T, const AdamScalars& sc, int first, int stride) {
+  const int nl = T.nleaves;
+  int l = -1, base = 0, n = 0;
+#pragma unroll 1
+  for (int j = first;; j += stride) {
+    while (l < nl && j >= base + n) {
+      base += n;
+      n = 0;
+      do { ++l; } while (l < nl && (T.leaf[l].late != 0) != LATE);
+      if (l < nl) n = T.size[l];
+    }
+    if (l >= nl) break;
+    const OptLeaf& L = T.leaf[l];
+    const int i = L.offset + (j - base);
+    float g = __ldcg(a.gflat + i), pv = __ldcg(a.params + i), mv = __ldcg(a.mu + i), nv = __ldcg(a.nu + i);
+    adam_element(a, sc, g, pv, mv, nv);
+    a.params[i] = pv;
+    a.mu[i] = mv;
+    a.nu[i] = nv;
+    write_images(L, i, pv);
+  }
+}
+
 }  // namespace minppo

@@ -152,6 +152,16 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // EPI_PARTIAL: warps beyond the six role warps (a caller running more warps per CTA, dwopt.cuh) help draining the
+  // accumulator: the 32-column chunks of a TMEM lane quadrant are dealt round-robin to the warps sharing it.
+  const int nwarps = static_cast<int>(blockDim.x) >> 5;
+  const int pq = warp & 3;
+  const int first_helper = 6 + ((pq - 2) & 3);
+  const int helpers_q = (EPI == EPI_PARTIAL && first_helper < nwarps) ? (nwarps - 1 - first_helper) / 4 + 1 : 0;
+  const int drain_members = 1 + helpers_q;
+  const int drain_idx = warp < 6 ? 0 : 1 + (warp - first_helper) / 4;
+  const int drain_threads = EPI == EPI_PARTIAL ? GEMM_EPI_THREADS + 32 * max(0, nwarps - 6) : GEMM_EPI_THREADS;
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -267,7 +277,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
       tc_fence_after();
     }
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c0 = 0; c0 < N; c0 += 32) {
+    for (int c0 = 32 * drain_idx; c0 < N; c0 += 32 * drain_members) {
       float v[32];
       if (nkb > 0) {
         tmem_ld_32x32(taddr + c0, v);
@@ -351,7 +361,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
     if (EPI == EPI_PARTIAL) {
       // tmC: fp32 [splits][m_store][N], box {32, 128, 1}: rows >= m_store are clipped by the TMA unit
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(drain_threads) : "memory");
       if (et == 0) {
         for (int c0 = 0; c0 < N; c0 += 32) tma_store_3d(base + (c0 >> 5) * 16384, &G.tmC, c0, m_tile * GEMM_BM, split);
         tma_store_commit();
@@ -366,6 +376,34 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
         G.colsum[static_cast<size_t>(m_tile) * N + c] = s;
       }
     }
+  }
+
+  else if (EPI == EPI_PARTIAL) {
+    // ===================== helper warps: drain their share of the accumulator =====================
+    const int r = pq * 32 + static_cast<int>(lane_id());
+    if (nkb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(pq * 32) << 16);
+    for (int c0 = 32 * drain_idx; c0 < N; c0 += 32 * drain_members) {
+      float v[32];
+      if (nkb > 0) {
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      const uint32_t dst = base + (c0 >> 5) * 16384 + r * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128(dst + ((j ^ (r & 7)) << 4),
+               make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                          __float_as_uint(v[4 * j + 3])));
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;" ::"r"(drain_threads) : "memory");
   }
 
   tc_fence_before();
