@@ -31,7 +31,7 @@ struct alignas(64) DwOptParams {
   GemmParams gemm;
   OptArgs opt;
   int gemm_ctas;                 // CTAs [0, gemm_ctas) run the GEMM; the others pre-reduce the small leaves
-  long long* trace;              // debug: [grid][8] clock64 stamps (null = off)
+  long long* trace;              // debug: [grid][16] clock64 stamps (null = off)
   // bias gradients on the otherwise idle extra CTAs: column sums of dz (bf16 [cs_rows][cs_n]) of GEMM group i
   // -> cs_out[i] as [cs_chunks][cs_n] partials (row chunk c of extra CTA e = c * ngroups + i)
   const __nv_bfloat16* cs_src[GEMM_MAX_GROUPS];
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   const int G = static_cast<int>(gridDim.x), NT = DWOPT_THREADS;
   const int b = static_cast<int>(blockIdx.x), t = static_cast<int>(threadIdx.x);
   const bool has_extra = p.gemm_ctas < G;
-#define DW_STAMP(slot) do { if (p.trace && t == 0) p.trace[static_cast<size_t>(b) * 8 + (slot)] = clock64(); } while (0)
+#define DW_STAMP(slot) do { if (p.trace && t == 0) p.trace[static_cast<size_t>(b) * 16 + (slot)] = clock64(); } while (0)
   float ss = 0.f;
   DW_STAMP(0);
   leaf_tab_build(T, a, t, NT);
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
 
   // ---- phase 1 ----------------------------------------------------------------------------------
   if (b < p.gemm_ctas) {
-    umma_gemm_body<EPI_PARTIAL>(p.gemm, smem_raw);       // PDL wait / trigger inside (TMA producer warp)
+    umma_gemm_body<EPI_PARTIAL>(p.gemm, smem_raw, p.trace ? p.trace + static_cast<size_t>(b) * 16 : nullptr);   // PDL wait / trigger inside
   } else {
     griddep_wait();                                      // the small-leaf partials come from the fused step kernel
     if (t == 0) griddep_launch();
@@ -156,8 +156,10 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   int ul = -1, ui = 0;                                   // leaf and first arena index of this thread's unit
   if (!has_extra) ss += reduce_leaves<false>(a, T, gtid, G * NT);
   if (fast) {
-    if (gtid < n_units) {
-      int x = gtid, l = 0;
+    // units dealt to warps round-robin over the CTAs (balanced, 512 contiguous bytes per warp and partial)
+    const int unit = (((t >> 5) * G + b) << 5) + (t & 31);
+    if (unit < n_units) {
+      int x = unit, l = 0;
       for (; l < T.nleaves; ++l) {
         if (!T.leaf[l].late) continue;
         const int n = T.size[l] >> 2;

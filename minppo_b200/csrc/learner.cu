@@ -792,7 +792,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   ALLOC(c->gnorms, static_cast<size_t>(EM));
   ALLOC(c->losses_scratch, 4);
   ALLOC(c->trace, static_cast<size_t>(2 * c->m_tiles) * 32);
-  ALLOC(c->trace2, static_cast<size_t>(c->sm_count) * 8);
+  ALLOC(c->trace2, static_cast<size_t>(c->sm_count) * 16);
   c->trace_on = getenv("MINPPO_TRACE") != nullptr;
   c->pdl = !(getenv("MINPPO_PDL") && atoi(getenv("MINPPO_PDL")) == 0);
   c->merged_opt = !(getenv("MINPPO_SPLIT_OPT") && atoi(getenv("MINPPO_SPLIT_OPT")) != 0);
@@ -948,7 +948,7 @@ int minppo_ctx_read(minppo_ctx* c, int32_t what, void* dst, size_t bytes, void* 
     case 5: src = c->counts; have = EM * 4; break;
     case 6: src = c->stats; have = 2 * EM * 4; break;
     case 7: src = c->trace; have = static_cast<size_t>(2 * c->m_tiles) * 32 * 8; break;
-    case 8: src = c->trace2; have = static_cast<size_t>(c->sm_count) * 8 * 8; break;
+    case 8: src = c->trace2; have = static_cast<size_t>(c->sm_count) * 16 * 8; break;
     default: set_error("minppo_ctx_read: unknown buffer %d", what); return MINPPO_ERR_ARG;
   }
   if (bytes > have) { set_error("minppo_ctx_read: %zu bytes requested, buffer has %zu", bytes, have); return MINPPO_ERR_ARG; }

@@ -110,6 +110,7 @@ struct LeafTab {
   OptLeaf leaf[MINPPO_MAX_LEAVES];
   int size[MINPPO_MAX_LEAVES];
   int nleaves;
+  int n_early;                   // elements of the leaves with late == 0
 };
 MINPPO_DEVINL void leaf_tab_build(LeafTab& T, const OptArgs& a, int tid, int nthreads) {
   constexpr int WORDS = sizeof(OptLeaf) / 4;
@@ -118,7 +119,13 @@ MINPPO_DEVINL void leaf_tab_build(LeafTab& T, const OptArgs& a, int tid, int nth
   for (int w = tid; w < a.nleaves * WORDS; w += nthreads) dst[w] = src[w];
   for (int l = tid; l < a.nleaves; l += nthreads)
     T.size[l] = (l + 1 < a.nleaves ? a.leaf[l + 1].offset : a.P) - a.leaf[l].offset;
-  if (tid == 0) T.nleaves = a.nleaves;
+  if (tid == 0) {
+    T.nleaves = a.nleaves;
+    int n = 0;
+    for (int l = 0; l < a.nleaves; ++l)
+      if (!a.leaf[l].late) n += (l + 1 < a.nleaves ? a.leaf[l + 1].offset : a.P) - a.leaf[l].offset;
+    T.n_early = n;
+  }
 }
 
 // fixed-order sum of `nparts` partials, 16 loads in flight
@@ -229,6 +236,7 @@ MINPPO_DEVINL void apply_adam(const OptArgs& a, const LeafTab& T, const AdamScal
 // job): used by the merged kernel for the small leaves when the hidden-kernel elements stay in registers.
 template <bool LATE>
 MINPPO_DEVINL void apply_adam_class(const OptArgs& a, const LeafTab& T, const AdamScalars& sc, int first, int stride) {
+  if (!LATE && first >= T.n_early) return;
   const int nl = T.nleaves;
   int l = -1, base = 0, n = 0;
 #pragma unroll 1

@@ -95,7 +95,8 @@ MINPPO_DEVINL float warp_colsum32(float (&v)[32]) {
 // Warps 0..5 carry the roles; a caller may run with more warps per CTA (dwopt.cuh): they only take part
 // in the two CTA-wide barriers.
 template <int EPI>
-MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
+MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long long* trace = nullptr) {
+#define GEMM_STAMP(slot) do { if (trace) trace[(slot)] = clock64(); } while (0)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B: 1024-B aligned tiles
   uint8_t* aligned = smem_raw + (base - raw);
@@ -151,6 +152,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 64) GEMM_STAMP(6);                 // prologue done
 
   // EPI_PARTIAL: warps beyond the six role warps (a caller running more warps per CTA, dwopt.cuh) help draining the
   // accumulator: the 32-column chunks of a TMEM lane quadrant are dealt round-robin to the warps sharing it.
@@ -169,6 +171,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
       tma_prefetch_desc(&G.tmB);
       griddep_wait();                  // PDL (common.cuh): operands are written by the preceding kernel
       griddep_launch();
+      GEMM_STAMP(7);                   // dependency wait passed
       const uint32_t a_bytes = kTmaA ? GEMM_A_BYTES : 0;
       const uint32_t b_bytes = static_cast<uint32_t>(N) * GEMM_BK * 2;
       for (int i = 0; i < nkb; ++i) {
@@ -204,6 +207,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
         const uint32_t ph = (i / GEMM_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (i == 0) GEMM_STAMP(8);     // first operands landed
         const uint32_t sa = base + s * GEMM_STAGE_BYTES;
         const uint32_t sb = sa + GEMM_A_BYTES;
 #pragma unroll
@@ -222,6 +226,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
         umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
       }
       umma_commit(tmem_full_bar);            // accumulator complete
+      GEMM_STAMP(9);                         // all MMAs issued
     }
   } else if (warp < GEMM_THREADS / 32) {
     // ===================== gather producer (optional) + epilogue =====================
@@ -276,6 +281,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
+    if (et == 0) GEMM_STAMP(10);                // accumulator complete
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     for (int c0 = 32 * drain_idx; c0 < N; c0 += 32 * drain_members) {
       float v[32];
@@ -363,10 +369,12 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw) {
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, %0;" ::"r"(drain_threads) : "memory");
       if (et == 0) {
+        GEMM_STAMP(11);                            // tile staged in shared memory
         for (int c0 = 0; c0 < N; c0 += 32) tma_store_3d(base + (c0 >> 5) * 16384, &G.tmC, c0, m_tile * GEMM_BM, split);
         tma_store_commit();
         tma_store_wait_all0();
         fence_proxy_async_global();
+        GEMM_STAMP(12);                            // partial tile written
       }
     }
     if (EPI == EPI_DACT) {

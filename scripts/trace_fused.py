@@ -47,7 +47,7 @@ print("total cycles per CTA: actor mean", tot[:n // 2].mean(), "critic mean", to
 # ---- dwopt kernel phases (last minibatch step): stamps 0 start, 1 phase-1 done, 2 barrier-1 passed, 3 phase-2 done,
 # 4 barrier-2 passed, 5 end
 nsm = torch.cuda.get_device_properties(dev).multi_processor_count
-o2 = torch.empty((nsm, 8), dtype=torch.int64, device=dev)
+o2 = torch.empty((nsm, 16), dtype=torch.int64, device=dev)
 _lib.check(learner.lib.minppo_ctx_read(learner._h, 8, o2.data_ptr(), o2.numel() * 8, torch.cuda.current_stream(dev).cuda_stream))
 torch.cuda.synchronize()
 t2 = o2.cpu().numpy()
@@ -60,4 +60,8 @@ for k in range(5):
 for gi in range(4):
     seg = d[32 * gi:32 * gi + 32, 0]
     print(f"  phase 1 of GEMM group {gi} (net {gi // 2}, layer {gi % 2}): mean {seg.mean():8.0f} min {seg.min():8.0f} max {seg.max():8.0f}")
+gl = ["prologue done", "dependency wait passed", "first operands landed", "all MMAs issued", "accumulator complete (epilogue)", "tile staged in smem", "partial tile written"]
+print("  GEMM body, cycles since kernel start (mean over GEMM CTAs 32..127):")
+for k in range(7):
+    print(f"    {gl[k]:34s} {(t2[32:128, 6 + k] - t2[32:128, 0]).mean():8.0f}")
 print("  total per CTA: mean", (t2[:, 5] - t2[:, 0]).mean(), "max", (t2[:, 5] - t2[:, 0]).max())
