@@ -102,24 +102,28 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   leaf_tab_build(T, a, t, NT);
   __syncthreads();
 
-  // Per-step scalars (two powf, A exp/log): computed up front by the last thread, whose warp has no GEMM role,
-  // so they never sit on the critical path between the barriers.
+  // Per-step scalars (two powf, A exp/log): computed by the last thread, whose warp has no GEMM role, while the
+  // GEMM is in flight (GEMM CTAs) or up front (spare CTAs) -- never between the barriers, never in front of the
+  // CTA-wide barrier of the GEMM prologue.
   const bool scal_thread = t == NT - 1;
   int count = 0;
   float ent = a.entropy_const;                           // A * (0.5 + 0.5 log 2pi) + sum log|scale|
-  if (scal_thread && a.do_apply) {
-    count = __ldcg(a.count);                             // Adam step count BEFORE this step
-    step_scalars(a, count, s_bcast[1], s_bcast[2], s_bcast[3]);
-    if (b == 0 && a.losses_out) {
-      // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the second barrier)
-      for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(__ldcg(a.params + a.off_logstd + j))));
+  auto scalars = [&]() {
+    if (scal_thread && a.do_apply) {
+      count = __ldcg(a.count);                           // Adam step count BEFORE this step
+      step_scalars(a, count, s_bcast[1], s_bcast[2], s_bcast[3]);
+      if (b == 0 && a.losses_out) {
+        // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the second barrier)
+        for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(__ldcg(a.params + a.off_logstd + j))));
+      }
     }
-  }
+  };
 
   // ---- phase 1 ----------------------------------------------------------------------------------
   if (b < p.gemm_ctas) {
-    umma_gemm_body<EPI_PARTIAL>(p.gemm, smem_raw, p.trace ? p.trace + static_cast<size_t>(b) * 16 : nullptr);   // PDL wait / trigger inside
+    umma_gemm_body<EPI_PARTIAL>(p.gemm, smem_raw, p.trace ? p.trace + static_cast<size_t>(b) * 16 : nullptr, scalars);   // PDL wait / trigger inside
   } else {
+    scalars();
     griddep_wait();                                      // the small-leaf partials come from the fused step kernel
     if (t == 0) griddep_launch();
     const int e = b - p.gemm_ctas, ne = G - p.gemm_ctas;

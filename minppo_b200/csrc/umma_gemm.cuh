@@ -94,8 +94,10 @@ MINPPO_DEVINL float warp_colsum32(float (&v)[32]) {
 // The whole CTA (GEMM_THREADS threads) calls this; it returns after the TMEM columns are released.
 // Warps 0..5 carry the roles; a caller may run with more warps per CTA (dwopt.cuh): they only take part
 // in the two CTA-wide barriers.
-template <int EPI>
-MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long long* trace = nullptr) {
+struct GemmNoIdle { MINPPO_DEVINL void operator()() const {} };
+// `idle` runs on the helper warps (warps >= 6, if the caller has any) while the GEMM is in flight.
+template <int EPI, typename IdleFn = GemmNoIdle>
+MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long long* trace = nullptr, IdleFn idle = IdleFn()) {
 #define GEMM_STAMP(slot) do { if (trace) trace[(slot)] = clock64(); } while (0)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B: 1024-B aligned tiles
@@ -107,6 +109,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
   uint64_t* empty_bar = bars + GEMM_STAGES;        // [STAGES]
   uint64_t* tmem_full_bar = bars + 2 * GEMM_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 1);
+  uint64_t* chunk_bar = bars + 2 * GEMM_STAGES + 2;   // [8] EPI_PARTIAL: 32-column chunk c of the tile staged by its four warps
 
   const int warp = threadIdx.x >> 5;
   int grp = 0;
@@ -142,6 +145,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    for (int c = 0; c < GEMM_MAXN / 32; ++c) mbar_init(&chunk_bar[c], 4);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -162,7 +166,6 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
   const int helpers_q = (EPI == EPI_PARTIAL && first_helper < nwarps) ? (nwarps - 1 - first_helper) / 4 + 1 : 0;
   const int drain_members = 1 + helpers_q;
   const int drain_idx = warp < 6 ? 0 : 1 + (warp - first_helper) / 4;
-  const int drain_threads = EPI == EPI_PARTIAL ? GEMM_EPI_THREADS + 32 * max(0, nwarps - 6) : GEMM_EPI_THREADS;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -227,6 +230,20 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
       }
       umma_commit(tmem_full_bar);            // accumulator complete
       GEMM_STAMP(9);                         // all MMAs issued
+      if (EPI == EPI_PARTIAL) {
+        // This thread is idle from here on: it TMA-stores each 32-column chunk of the fp32 tile as soon as the four
+        // warps draining it have staged it (tmC: fp32 [splits][m_store][N], box {32, 128, 1}; rows >= m_store are
+        // clipped by the TMA unit), so the store overlaps the rest of the drain.
+        for (int c = 0; c < N / 32; ++c) {
+          mbar_wait(&chunk_bar[c], 0);
+          if (c == 0) GEMM_STAMP(11);          // first chunk staged
+          tma_store_3d(base + c * 16384, &G.tmC, c * 32, m_tile * GEMM_BM, split);
+        }
+        tma_store_commit();
+        tma_store_wait_all0();
+        fence_proxy_async_global();
+        GEMM_STAMP(12);                        // partial tile written
+      }
     }
   } else if (warp < GEMM_THREADS / 32) {
     // ===================== gather producer (optional) + epilogue =====================
@@ -345,6 +362,9 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
           sts128(dst + ((j ^ (r & 7)) << 4),
                  make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
                             __float_as_uint(v[4 * j + 3])));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&chunk_bar[c0 >> 5]);
       }
     }
     if (kColsum) {
@@ -364,19 +384,6 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
         G.colsum_out[static_cast<size_t>(split) * N + cs_c0 + ch * 32 + lane_id()] = out;
       }
     }
-    if (EPI == EPI_PARTIAL) {
-      // tmC: fp32 [splits][m_store][N], box {32, 128, 1}: rows >= m_store are clipped by the TMA unit
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, %0;" ::"r"(drain_threads) : "memory");
-      if (et == 0) {
-        GEMM_STAMP(11);                            // tile staged in shared memory
-        for (int c0 = 0; c0 < N; c0 += 32) tma_store_3d(base + (c0 >> 5) * 16384, &G.tmC, c0, m_tile * GEMM_BM, split);
-        tma_store_commit();
-        tma_store_wait_all0();
-        fence_proxy_async_global();
-        GEMM_STAMP(12);                            // partial tile written
-      }
-    }
     if (EPI == EPI_DACT) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = et; c < N; c += GEMM_EPI_THREADS) {
@@ -389,6 +396,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
   else if (EPI == EPI_PARTIAL) {
     // ===================== helper warps: drain their share of the accumulator =====================
     const int r = pq * 32 + static_cast<int>(lane_id());
+    idle();
     if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -409,9 +417,10 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
         sts128(dst + ((j ^ (r & 7)) << 4),
                make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
                           __float_as_uint(v[4 * j + 3])));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&chunk_bar[c0 >> 5]);
     }
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 1, %0;" ::"r"(drain_threads) : "memory");
   }
 
   tc_fence_before();
