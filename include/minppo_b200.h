@@ -41,6 +41,7 @@ extern "C" {
 #define MINPPO_PRNG_PARTITIONABLE 1 /* jax_threefry_partitionable = True  (JAX >= 0.5 default) */
 
 #define MINPPO_MAX_LEAVES 32
+#define MINPPO_MAX_RANKS 8
 
 typedef struct minppo_ctx minppo_ctx;
 
@@ -115,6 +116,15 @@ int64_t minppo_param_layout(const minppo_config* cfg, int32_t* nleaves, int64_t*
 int minppo_nccl_unique_id(void* id128_host);
 int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host, minppo_ctx** out);
 int minppo_ctx_destroy(minppo_ctx* ctx);
+
+/* ---- gradient exchange over NVLink peer memory (world_size > 1, optional) ----------------------
+ * Default for sharded ranks is ncclAllReduce + a separate optimizer launch per minibatch.  With peer buffers set, the
+ * all-reduce is fused INTO the weight-gradient/optimizer kernel: reduce-scatter + all-gather by direct loads / stores
+ * on the peers' exchange buffers with flag synchronisation (no NCCL call, no extra launch on the per-minibatch path).
+ * Every rank exports one CUDA-IPC handle (64 bytes); the host framework all-gathers them (rank order) and hands the
+ * table back.  All ranks must then issue the same sequence of minppo_update calls. */
+int minppo_ctx_ipc_handle(minppo_ctx* ctx, void* handle64_host);
+int minppo_ctx_set_peers(minppo_ctx* ctx, const void* handles_host /* [world_size][64] */);
 
 /* ---- (4) one learner update: replaces train.py:185-281 ---------------------------------
  * In place: params, mu, nu (f32 [P]), count (i32 [1], Adam step count == TrainState.step).

@@ -221,6 +221,17 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   const uint32_t R0 = base + FS_R0, R1 = base + FS_R1, RB = base + FS_RB;
   const uint32_t W2T = base + FS_W2T, GT = base + FS_GT;
 
+  // Env-sharded ranks size the row lists for the worst case (learner.cu: 1.5 x the mean + 256 rows); the tiles
+  // beyond this minibatch's actual row count have nothing to do except zeroing their partial sums.
+  if (tile * 128 >= min(*p.count, p.cap)) {
+    griddep_wait();                                     // the previous optimizer step may still be reading the partials
+    float* part = p.part + static_cast<size_t>(tile) * p.part_stride;
+    for (int i = threadIdx.x; i < H * G.aout; i += FS_THREADS) part[G.po_w2 + i] = 0.f;
+    if (static_cast<int>(threadIdx.x) < G.aout) part[G.po_b2 + threadIdx.x] = 0.f;
+    if (net == 0 && static_cast<int>(threadIdx.x) < G.aout) part[p.po_logstd + threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) part[G.po_loss] = 0.f;
+    return;
+  }
   if (threadIdx.x == FS_WORKERS) {
     FS_STAMP(16);
     mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);

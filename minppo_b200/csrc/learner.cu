@@ -263,6 +263,12 @@ struct minppo_ctx {
   // nccl
   ncclComm_t comm;
   bool have_comm;
+  // gradient exchange over peer memory (dwopt.cuh PeerXchg)
+  float* xchg;                // [xbuf | rbuf | ss | flags] (world_size > 1), exported by CUDA IPC
+  unsigned int* xseq;
+  PeerXchg px;
+  bool peers_set;
+  void* peer_ptr[MINPPO_MAX_RANKS];
   // per-kernel-class event profiling (eager mode only)
   bool profiling;
   std::vector<cudaEvent_t> prof_events;      // pairs (begin, end)
@@ -529,6 +535,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
         else { g.amode = A_TMA_MN; g.tmA = nb.m_act_mn[l]; }
         g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
         g.kb_total = c->M_pad / 64;
+        g.k_count = c->cfg.world_size > 1 ? c->counts + s : nullptr;
         g.tmC = nb.m_dw[l];
         g.colsum_out = c->cs_chunks > 0 ? nullptr : nb.dbias[l];
         dp.cs_src[ng - 1] = nb.dz[l + 1]; dp.cs_out[ng - 1] = nb.dbias[l];
@@ -549,14 +556,16 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     dp.cs_rows = c->M_pad; dp.cs_n = H; dp.cs_chunks = c->cs_chunks;
     if (s + 1 < c->E * c->M) { dp.next_ridx = ridx + c->cap; dp.obs_img = c->obs_img; dp.next_rows = c->cap; dp.obs_ld = c->Dp; }
     dp.trace = c->trace_on ? c->trace2 : nullptr;
-    o.do_reduce = 1; o.do_apply = sharded ? 0 : 1;
+    const bool px_on = sharded && c->peers_set;          // all-reduce fused into this launch (peer memory)
+    if (px_on) dp.px = c->px;
+    o.do_reduce = 1; o.do_apply = (sharded && !px_on) ? 0 : 1;
     {
       PROF(PC_DW_GEMM);
       const cudaError_t e = dwopt_launch(dp, c->sm_count, stream, pdl);
       if (e != cudaSuccess) { set_error("dwopt launch failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
       c->launches++;
     }
-    if (sharded) {
+    if (sharded && !px_on) {
       { PROF(PC_ALLREDUCE); RET(nccl_allreduce(c, c->gflat, static_cast<size_t>(c->P) + 2, stream)); }
       o.do_reduce = 0; o.do_apply = 1;
       { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream, pdl)); }
@@ -705,6 +714,7 @@ int minppo_ctx_destroy(minppo_ctx* c) {
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->have_comm) nccl_api()->CommDestroy(c->comm);
+  for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]);
   for (void* p : c->allocs) cudaFree(p);
   delete c;
   return 0;
@@ -786,7 +796,20 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   ALLOC(c->adv, static_cast<size_t>(c->Bl));
   ALLOC(c->tgt, static_cast<size_t>(c->Bl));
   ALLOC(c->stats, static_cast<size_t>(2 * EM));
-  ALLOC(c->gflat, static_cast<size_t>(c->P) + 4);
+  c->xchg = nullptr; c->peers_set = false; memset(&c->px, 0, sizeof(c->px)); memset(c->peer_ptr, 0, sizeof(c->peer_ptr));
+  if (cfg->world_size > 1) {
+    // the local gradient buffer lives inside the exchange allocation so that peers can read it (own cudaMalloc:
+    // CUDA IPC exports whole allocations)
+    const int np = static_cast<int>((c->P + 2 + 3) / 4 * 4);
+    const int q = ((np + cfg->world_size - 1) / cfg->world_size + 3) / 4 * 4;
+    const size_t floats = 2 * static_cast<size_t>(np) + 16 + 32;
+    ALLOC(c->xchg, floats);
+    ALLOC(c->xseq, 1);
+    c->gflat = c->xchg;
+    c->px.np = np; c->px.q = q; c->px.world = 0; c->px.rank = cfg->rank; c->px.seq = c->xseq;
+  } else {
+    ALLOC(c->gflat, static_cast<size_t>(c->P) + 4);
+  }
   ALLOC(c->block_ss, static_cast<size_t>(c->opt_blocks));
   ALLOC(c->head_part, static_cast<size_t>(c->tiles64) * c->head_stride);
   ALLOC(c->gnorms, static_cast<size_t>(EM));
@@ -890,6 +913,36 @@ int minppo_update(minppo_ctx* c, float* params, float* mu, float* nu, int32_t* c
     c->have_graph = true;
   }
   CK(cudaGraphLaunch(c->graph_exec, stream));
+  return 0;
+}
+
+int minppo_ctx_ipc_handle(minppo_ctx* c, void* handle64_host) {
+  if (!c || !handle64_host) { set_error("null argument"); return MINPPO_ERR_ARG; }
+  if (!c->xchg) { set_error("minppo_ctx_ipc_handle: context has world_size == 1"); return MINPPO_ERR_ARG; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->xchg));
+  memcpy(handle64_host, &h, 64);
+  return 0;
+}
+
+int minppo_ctx_set_peers(minppo_ctx* c, const void* handles_host) {
+  if (!c || !handles_host) { set_error("null argument"); return MINPPO_ERR_ARG; }
+  if (!c->xchg) { set_error("minppo_ctx_set_peers: context has world_size == 1"); return MINPPO_ERR_ARG; }
+  const int W = c->cfg.world_size;
+  if (W > MINPPO_MAX_RANKS) { set_error("peer exchange supports up to %d ranks", MINPPO_MAX_RANKS); return MINPPO_ERR_UNSUPPORTED; }
+  for (int r = 0; r < W; ++r) {
+    if (r == c->cfg.rank) { c->px.base[r] = reinterpret_cast<char*>(c->xchg); continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles_host) + 64 * r, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_ptr[r] = ptr;
+    c->px.base[r] = static_cast<char*>(ptr);
+  }
+  c->px.world = W;
+  c->peers_set = true;
+  if (c->have_graph) { cudaGraphExecDestroy(c->graph_exec); cudaGraphDestroy(c->graph); c->have_graph = false; }
   return 0;
 }
 

@@ -206,8 +206,10 @@ MINPPO_DEVINL float reduce_leaves(const OptArgs& a, const LeafTab& T, int first,
 }
 
 // clip + Adam over the arena, four elements in flight per thread; gradient from gflat
-MINPPO_DEVINL void apply_adam(const OptArgs& a, const LeafTab& T, const AdamScalars& sc, int first, int stride) {
+MINPPO_DEVINL void apply_adam(const OptArgs& a, const LeafTab& T, const AdamScalars& sc, int first, int stride,
+                              const float* gsrc = nullptr) {
   const int P = a.P;
+  const float* gbuf = gsrc ? gsrc : a.gflat;
   int l = 0;
 #pragma unroll 1
   for (int i0 = first; i0 < P; i0 += 4 * stride) {
@@ -215,7 +217,7 @@ MINPPO_DEVINL void apply_adam(const OptArgs& a, const LeafTab& T, const AdamScal
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * stride;
-      if (i < P) { g[u] = __ldcg(a.gflat + i); pv[u] = __ldcg(a.params + i); mv[u] = __ldcg(a.mu + i); nv[u] = __ldcg(a.nu + i); }
+      if (i < P) { g[u] = __ldcg(gbuf + i); pv[u] = __ldcg(a.params + i); mv[u] = __ldcg(a.mu + i); nv[u] = __ldcg(a.nu + i); }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {

@@ -59,6 +59,7 @@ struct alignas(64) GemmGroup {
   int splits;                      // split-K factor (EPI_PARTIAL)
   int kb_total;                    // number of 64-wide k-blocks over the whole K
   int m_store;                     // EPI_PARTIAL: rows m < m_store are stored
+  const int32_t* k_count;          // optional: number of valid K rows (device side); k-blocks beyond it are skipped
 };
 
 struct alignas(64) GemmParams {
@@ -119,9 +120,12 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
   const int AMODE = G.amode, BMODE = G.bmode;
   const int m_tile = rem / G.splits;
   const int split = rem % G.splits;
-  const int kb_per = (G.kb_total + G.splits - 1) / G.splits;
+  // K extent: all of it, or only the k-blocks holding valid rows (env-sharded minibatches are padded to a worst-case
+  // capacity; the count is device data and identical for every CTA of the launch)
+  const int kb_total = G.k_count ? min(G.kb_total, (max(*G.k_count, 0) + GEMM_BK - 1) / GEMM_BK) : G.kb_total;
+  const int kb_per = (kb_total + G.splits - 1) / G.splits;
   const int kb0 = split * kb_per;
-  const int kb1 = min(G.kb_total, kb0 + kb_per);
+  const int kb1 = min(kb_total, kb0 + kb_per);
   const int nkb = max(0, kb1 - kb0);
   const int N = G.N;
   const bool kGather = (AMODE == A_GATHER_K || AMODE == A_GATHER_MN);

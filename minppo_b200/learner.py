@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
+import os
 from typing import Any, NamedTuple, Optional
 
 import numpy as np
@@ -162,6 +163,27 @@ class Learner:
             _lib.check(self.lib.minppo_ctx_create(C.byref(self.cconf), idbuf, C.byref(handle)))
         self._h = handle
         self.use_graph = bool(config.learner.use_graph)
+        self.peer_exchange = False
+        if world_size > 1 and os.environ.get("MINPPO_NCCL_ALLREDUCE", "0") != "1":
+            self._connect_peers()
+
+    def _connect_peers(self) -> None:
+        """Exchange the CUDA-IPC handles of the gradient exchange buffers through torch.distributed (plumbing
+        only) and switch the per-minibatch all-reduce to the fused peer-memory path (include/minppo_b200.h).
+        Without an initialised process group the context stays on ncclAllReduce."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() != self.world_size:
+            return
+        buf = C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.minppo_ctx_ipc_handle(self._h, buf))
+            handles = [None] * self.world_size
+            dist.all_gather_object(handles, buf.raw)
+            table = C.create_string_buffer(b"".join(handles), 64 * self.world_size)
+            _lib.check(self.lib.minppo_ctx_set_peers(self._h, table))
+        dist.barrier()                       # every rank has mapped every buffer before the first update
+        self.peer_exchange = True
 
     def close(self) -> None:
         if getattr(self, "_h", None):

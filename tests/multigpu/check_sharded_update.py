@@ -48,14 +48,14 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     dist.init_process_group("nccl", device_id=dev)
-    ids = [nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
     ok = True
     for name, kw in (("small", dict(num_envs=64 * world, num_steps=32, num_minibatches=4, update_epochs=2)),
                      ("wide", dict(num_envs=512 * world, num_steps=64, num_minibatches=8, update_epochs=2))):
         hp = P.Hyper(anneal_lr=False, **kw)
         pr = synth.make_problem(hp, seed=3)
         Nl = hp.num_envs // world
+        ids = [nccl_unique_id() if rank == 0 else None]      # one NCCL unique id per communicator
+        dist.broadcast_object_list(ids, src=0)
         got = run(hp, pr, dev, world, rank, ids[0], rank * Nl, Nl)
         # parameters bit-identical on every rank
         mine = torch.from_numpy(got["params"]).to(dev)
