@@ -27,24 +27,27 @@ namespace minppo {
 // per SM: with 6 warps the dependent divide / sqrt chains of the Adam phase had nothing to hide behind)
 constexpr int DWOPT_THREADS = 512;
 
-// Layout of the exchange allocation of one rank (floats unless noted):
-//   xbuf  [np]      local gradient SUM of the current minibatch (+ the two loss sums at P, P+1)   == OptArgs.gflat
-//   rbuf  [np]      all-reduced gradient: slice q is written by rank q into every rank's rbuf
-//   ss    [16]      ss[q] = sum of squares of slice q of the reduced gradient (written by rank q)
-//   flags [2][16]   u32: ready[q] = n once rank q's xbuf of exchange n is complete; done[q] = n once rank q's slice
-//                   and ss[q] of exchange n have been written HERE
+// Gradient exchange over NVLink peer memory, ONE-SHOT: every rank pushes its local gradient sums into a staging slot
+// on every rank (itself included) while it reduces them, one flag round says "all of rank q's pushes for exchange n
+// are done", then every rank sums the W staging slots in rank order -- same values, same order, so all ranks apply
+// bit-identical gradients with no broadcast -- and continues with the norm and Adam exactly like a single GPU.
+// Exchange allocation of one rank (exported by CUDA IPC):
+//   stage [2][W][np] f32   slot (n & 1, q): rank q's local gradient of exchange n.  Double-buffered: a rank can be at
+//                          most one exchange ahead of the slowest reader (it needs that reader's flag to finish).
+//                          Inside a slot: the 4-element units of the late leaves (16-byte aligned), then the early
+//                          elements and the two loss sums (dwopt job numbering).
+//   flags [16] u32         flags[q] = n once rank q's pushes of exchange n are visible here
 struct PeerXchg {
-  char* base[MINPPO_MAX_RANKS];
-  unsigned int* seq;             // local exchange counter (device memory; exchanges completed so far)
+  char* base[MINPPO_MAX_RANKS];  // rank r's allocation as mapped on THIS device
+  unsigned int* seq;             // local exchange counter (device memory): exchanges completed so far
   int world, rank;
-  int np;                        // floats per buffer (multiple of 4, >= P + 2)
-  int q;                         // floats per slice (multiple of 4); slice r = [r * q, (r + 1) * q)
+  int np;                        // floats per staging slot (multiple of 4)
 };
-MINPPO_DEVINL float* px_xbuf(const PeerXchg& x, int r) { return reinterpret_cast<float*>(x.base[r]); }
-MINPPO_DEVINL float* px_rbuf(const PeerXchg& x, int r) { return reinterpret_cast<float*>(x.base[r]) + x.np; }
-MINPPO_DEVINL float* px_ss(const PeerXchg& x, int r) { return reinterpret_cast<float*>(x.base[r]) + 2 * static_cast<size_t>(x.np); }
+MINPPO_DEVINL float* px_stage(const PeerXchg& x, int r, unsigned int par, int q) {
+  return reinterpret_cast<float*>(x.base[r]) + (static_cast<size_t>(par) * x.world + q) * x.np;
+}
 MINPPO_DEVINL unsigned int* px_flags(const PeerXchg& x, int r) {
-  return reinterpret_cast<unsigned int*>(reinterpret_cast<float*>(x.base[r]) + 2 * static_cast<size_t>(x.np) + 16);
+  return reinterpret_cast<unsigned int*>(reinterpret_cast<float*>(x.base[r]) + 2 * static_cast<size_t>(x.world) * x.np);
 }
 // system-scope accesses for memory another GPU reads or writes
 MINPPO_DEVINL float4 ld_sys_v4(const float* p) {
@@ -52,6 +55,7 @@ MINPPO_DEVINL float4 ld_sys_v4(const float* p) {
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
+MINPPO_DEVINL void st_sys_f32(float* p, float v) { asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 MINPPO_DEVINL void st_sys_v4(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -149,6 +153,9 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
 #define DW_STAMP(slot) do { if (p.trace && t == 0) p.trace[static_cast<size_t>(b) * 16 + (slot)] = clock64(); } while (0)
   float ss = 0.f;
   DW_STAMP(0);
+  __shared__ unsigned int s_seq;
+  const bool px_on = p.px.world > 1;                     // gradient exchange over peer memory fused into this launch
+  if (px_on && t == 0) s_seq = __ldcg(p.px.seq) + 1u;    // number of this exchange
   leaf_tab_build(T, a, t, NT);
   __syncthreads();
 
@@ -209,9 +216,9 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   float pv[4], mv[4], nv[4];
   int ul = -1, ui = 0;                                   // leaf and first arena index of this thread's unit
   if (!has_extra) ss += reduce_leaves<false>(a, T, gtid, G * NT);
+  // units dealt to warps round-robin over the CTAs (balanced, 512 contiguous bytes per warp and partial)
+  const int unit = (((t >> 5) * G + b) << 5) + (t & 31);
   if (fast) {
-    // units dealt to warps round-robin over the CTAs (balanced, 512 contiguous bytes per warp and partial)
-    const int unit = (((t >> 5) * G + b) << 5) + (t & 31);
     if (unit < n_units) {
       int x = unit, l = 0;
       for (; l < T.nleaves; ++l) {
@@ -227,88 +234,70 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
         for (int u = 0; u < 4; ++u) { pv[u] = __ldcg(a.params + ui + u); mv[u] = __ldcg(a.mu + ui + u); nv[u] = __ldcg(a.nu + ui + u); }
       }
       g4 = sum_partials16_v4(L.grad_src + L.src_offset + 4 * x, L.nparts, L.part_stride);
-      if (!a.do_apply || a.keep_gflat || p.px.world > 1) { float* dst = a.gflat + ui; dst[0] = g4.x; dst[1] = g4.y; dst[2] = g4.z; dst[3] = g4.w; }
-      ss = fmaf(g4.x, g4.x, ss); ss = fmaf(g4.y, g4.y, ss); ss = fmaf(g4.z, g4.z, ss); ss = fmaf(g4.w, g4.w, ss);
+      if (!px_on) {
+        if (!a.do_apply || a.keep_gflat) { float* dst = a.gflat + ui; dst[0] = g4.x; dst[1] = g4.y; dst[2] = g4.z; dst[3] = g4.w; }
+        ss = fmaf(g4.x, g4.x, ss); ss = fmaf(g4.y, g4.y, ss); ss = fmaf(g4.z, g4.z, ss); ss = fmaf(g4.w, g4.w, ss);
+      }
     }
   } else {
     ss += reduce_leaves<true>(a, T, gtid, G * NT);
   }
   if (!a.do_apply) return;
-  if (p.px.world > 1) {
-    // ---- gradient all-reduce over NVLink peer memory, fused between the reduction and the optimizer ----------
-    // reduce-scatter: this rank sums slice `rank` of every rank's xbuf in rank order (deterministic; every element
-    // is reduced by exactly one rank, so all ranks apply bit-identical gradients) and writes the result into every
-    // rank's rbuf (all-gather), together with the slice's sum of squares.  Two flag rounds, no host involvement.
+
+  if (px_on) {
+    // ---- one-shot all-reduce over NVLink peer memory (PeerXchg above; requires the fast path) -----------------
     const PeerXchg& X = p.px;
     const int W = X.world, R = X.rank;
-    __shared__ unsigned int s_seq;
-    grid_barrier(a.barrier, a.err_flag);                 // xbuf (== gflat) of this rank complete
-    if (t == 0) s_seq = __ldcg(X.seq) + 1u;
-    __syncthreads();
-    const unsigned int n = s_seq;
+    const unsigned int n = s_seq, par = n & 1u;
+    const int n_late4 = 4 * n_units;
+    // early element (or loss sum) of this thread: same job numbering as apply_adam_class<false>
+    int eidx = -1;
+    if (gtid < T.n_early + 2) {
+      if (gtid >= T.n_early) eidx = P + (gtid - T.n_early);
+      else {
+        int x = gtid, l = 0;
+        for (; l < T.nleaves; ++l) {
+          if (T.leaf[l].late) continue;
+          if (x < T.size[l]) break;
+          x -= T.size[l];
+        }
+        eidx = T.leaf[l].offset + x;
+      }
+    }
+    // push the local sums into slot (par, R) of every rank
+    if (ul >= 0) {
+#pragma unroll
+      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W) st_sys_v4(px_stage(X, r, par, R) + 4 * unit, g4);
+    }
+    if (eidx >= 0) {
+      const float gl = __ldcg(a.gflat + eidx);
+#pragma unroll
+      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W) st_sys_f32(px_stage(X, r, par, R) + n_late4 + gtid, gl);
+    }
+    grid_barrier(a.barrier, a.err_flag);                 // every push of this rank has been issued
     if (b == 0 && t < W) { __threadfence_system(); st_release_sys_u32(px_flags(X, t) + R, n); }
-    px_wait_flags(px_flags(X, R), W, n, a.err_flag);     // every rank's xbuf of exchange n is complete
-    float ss2 = 0.f;
-    const int lo = R * X.q, hi = min(lo + X.q, X.np);
-    for (int i = lo + 4 * gtid; i < hi; i += 4 * G * NT) {
+    px_wait_flags(px_flags(X, R), W, n, a.err_flag);     // every rank's pushes of exchange n have landed here
+    // sum the W slots in rank order
+    ss = 0.f;
+    if (ul >= 0) {
       float4 v[MINPPO_MAX_RANKS];
 #pragma unroll
-      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W) v[r] = ld_sys_v4(px_xbuf(X, r) + i);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < MINPPO_MAX_RANKS; ++q) if (q < W) v[q] = __ldcg(reinterpret_cast<const float4*>(px_stage(X, R, par, q) + 4 * unit));
+      g4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
-#pragma unroll
-      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W) st_sys_v4(px_rbuf(X, r) + i, acc);
-      if (i + 0 < P) ss2 = fmaf(acc.x, acc.x, ss2);      // the loss sums at P, P + 1 are not part of the gradient
-      if (i + 1 < P) ss2 = fmaf(acc.y, acc.y, ss2);
-      if (i + 2 < P) ss2 = fmaf(acc.z, acc.z, ss2);
-      if (i + 3 < P) ss2 = fmaf(acc.w, acc.w, ss2);
+      for (int q = 0; q < MINPPO_MAX_RANKS; ++q) if (q < W) { g4.x += v[q].x; g4.y += v[q].y; g4.z += v[q].z; g4.w += v[q].w; }
+      if (a.keep_gflat) { float* dst = a.gflat + ui; dst[0] = g4.x; dst[1] = g4.y; dst[2] = g4.z; dst[3] = g4.w; }
+      ss = fmaf(g4.x, g4.x, ss); ss = fmaf(g4.y, g4.y, ss); ss = fmaf(g4.z, g4.z, ss); ss = fmaf(g4.w, g4.w, ss);
     }
-    const float bs2 = block_sum<DWOPT_THREADS>(ss2, scratch);
-    if (t == 0) a.block_ss[b] = bs2;
-    grid_barrier(a.barrier, a.err_flag);                 // this rank's slice is written everywhere
-    if (b == 0) {
-      const float v = t < G ? __ldcg(a.block_ss + t) : 0.f;
-      const float tot = block_sum<DWOPT_THREADS>(v, scratch);
-      if (t == 0) s_bcast[0] = tot;
-      __syncthreads();
-      if (t < W) {
-        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(px_ss(X, t) + R), "f"(s_bcast[0]) : "memory");
-        __threadfence_system();
-        st_release_sys_u32(px_flags(X, t) + 16 + R, n);
-      }
+    if (eidx >= 0) {
+      float ge = 0.f;
+      for (int q = 0; q < W; ++q) ge += __ldcg(px_stage(X, R, par, q) + n_late4 + gtid);
+      a.gflat[eidx] = ge;                                // read back by this same thread (small leaves) / after the barrier (losses)
+      if (eidx < P) ss = fmaf(ge, ge, ss);
     }
-    px_wait_flags(px_flags(X, R) + 16, W, n, a.err_flag);   // every slice of rbuf (and its ss) has arrived
-    if (t == 0) {
-      float tot = 0.f;
-      for (int r = 0; r < W; ++r) {
-        float v;
-        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(px_ss(X, R) + r) : "memory");
-        tot += v;
-      }
-      s_bcast[0] = sqrtf(tot);
-    }
-    __syncthreads();
-    AdamScalars sc;
-    sc.gnorm = s_bcast[0]; sc.lr = s_bcast[1]; sc.c1 = s_bcast[2]; sc.c2 = s_bcast[3];
-    sc.trigger = sc.gnorm < a.max_norm;
-    const float* gred = px_rbuf(X, R);                   // the optimizer reads the all-reduced gradient
-    apply_adam(a, T, sc, gtid, G * NT, gred);
-    if (b == 0 && scal_thread) {
-      *X.seq = n;
-      *a.count = count + 1;
-      if (a.losses_out) {
-        const float value_loss = 0.5f * __ldcg(gred + P) * a.inv_mb;
-        const float actor_loss = -__ldcg(gred + P + 1) * a.inv_mb;
-        a.losses_out[0] = actor_loss + a.vf_coef * value_loss - a.ent_coef * ent;
-        a.losses_out[1] = value_loss;
-        a.losses_out[2] = actor_loss;
-        a.losses_out[3] = ent;
-        if (a.gnorm_out) *a.gnorm_out = sc.gnorm;
-      }
-    }
-    return;
+    if (b == 0 && scal_thread) *X.seq = n;
   }
+  if (!a.do_apply) return;
   const float bs = block_sum<DWOPT_THREADS>(ss, scratch);
   if (t == 0) a.block_ss[b] = bs;
   DW_STAMP(3);

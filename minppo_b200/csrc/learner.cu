@@ -556,7 +556,8 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     dp.cs_rows = c->M_pad; dp.cs_n = H; dp.cs_chunks = c->cs_chunks;
     if (s + 1 < c->E * c->M) { dp.next_ridx = ridx + c->cap; dp.obs_img = c->obs_img; dp.next_rows = c->cap; dp.obs_ld = c->Dp; }
     dp.trace = c->trace_on ? c->trace2 : nullptr;
-    const bool px_on = sharded && c->peers_set;          // all-reduce fused into this launch (peer memory)
+    // all-reduce fused into this launch (peer memory); needs the one-unit-per-thread fast path of the kernel
+    const bool px_on = sharded && c->peers_set && c->P / 4 <= static_cast<long long>(c->sm_count) * DWOPT_THREADS;
     if (px_on) dp.px = c->px;
     o.do_reduce = 1; o.do_apply = (sharded && !px_on) ? 0 : 1;
     {
@@ -801,15 +802,12 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     // the local gradient buffer lives inside the exchange allocation so that peers can read it (own cudaMalloc:
     // CUDA IPC exports whole allocations)
     const int np = static_cast<int>((c->P + 2 + 3) / 4 * 4);
-    const int q = ((np + cfg->world_size - 1) / cfg->world_size + 3) / 4 * 4;
-    const size_t floats = 2 * static_cast<size_t>(np) + 16 + 32;
+    const size_t floats = 2 * static_cast<size_t>(cfg->world_size) * np + 32;
     ALLOC(c->xchg, floats);
     ALLOC(c->xseq, 1);
-    c->gflat = c->xchg;
-    c->px.np = np; c->px.q = q; c->px.world = 0; c->px.rank = cfg->rank; c->px.seq = c->xseq;
-  } else {
-    ALLOC(c->gflat, static_cast<size_t>(c->P) + 4);
+    c->px.np = np; c->px.world = 0; c->px.rank = cfg->rank; c->px.seq = c->xseq;
   }
+  ALLOC(c->gflat, static_cast<size_t>(c->P) + 4);
   ALLOC(c->block_ss, static_cast<size_t>(c->opt_blocks));
   ALLOC(c->head_part, static_cast<size_t>(c->tiles64) * c->head_stride);
   ALLOC(c->gnorms, static_cast<size_t>(EM));
