@@ -295,6 +295,25 @@ def run_ours(args):
     value = B / (ms_per_step * 1e-3)
     final_losses = losses.cpu().numpy()
     if args.quick:
+        if os.environ.get("MINPPO_TRACE"):
+            # development: phase stamps of the dwopt kernel of the last minibatch step (one eager update on every rank)
+            learner.use_graph = False
+            one_update()
+            nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+            o2 = torch.empty((nsm, 16), dtype=torch.int64, device=dev)
+            _lib.check(learner.lib.minppo_ctx_read(learner._h, 8, o2.data_ptr(), o2.numel() * 8,
+                                                   torch.cuda.current_stream(dev).cuda_stream))
+            torch.cuda.synchronize(dev)
+            t2 = o2.cpu().numpy()
+            if rank == 0:
+                seq = [0, 1, 2, 13, 14, 15, 3, 4, 5] if world > 1 else [0, 1, 2, 3, 4, 5]
+                lab = {1: "phase 1 done", 2: "barrier 1 passed", 13: "local reduce + pushes issued", 14: "barrier A passed",
+                       15: "peer flags seen", 3: "reduce done, block sums written", 4: "barrier 2 passed", 5: "end"}
+                prev = 0
+                for k in seq[1:]:
+                    dt = (t2[:128, k] - t2[:128, 0]).mean()
+                    print(f"dwopt trace: {lab[k]:34s} {dt:9.0f} (+{dt - prev:.0f})")
+                    prev = dt
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms_per_step, "value": value, "n_gpus": world,
                               "skip": os.environ.get("MINPPO_SKIP", "0"), "clocks": clocks}), flush=True)

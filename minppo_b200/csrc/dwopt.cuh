@@ -274,9 +274,12 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
 #pragma unroll
       for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W) st_sys_f32(px_stage(X, r, par, R) + n_late4 + gtid, gl);
     }
+    DW_STAMP(13);
     grid_barrier(a.barrier, a.err_flag);                 // every push of this rank has been issued
+    DW_STAMP(14);
     if (b == 0 && t < W) { __threadfence_system(); st_release_sys_u32(px_flags(X, t) + R, n); }
     px_wait_flags(px_flags(X, R), W, n, a.err_flag);     // every rank's pushes of exchange n have landed here
+    DW_STAMP(15);
     // sum the W slots in rank order
     ss = 0.f;
     if (ul >= 0) {

@@ -13,6 +13,9 @@ for mode in 0 1; do
   echo "## parity, MINPPO_NCCL_ALLREDUCE=$mode"
   grep -E "^\[(small|wide)|MULTIGPU|^exit|MinppoError" gpurun_out/multigpu_parity_nccl$mode.log | tail -n 6
 done
+MINPPO_TRACE=1 MINPPO_PDL=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+  --master-port 29530 bench.py --gpus $N --quick --steps 3 --warmup 3 > gpurun_out/bench_trace_g$N.log 2>&1
+grep "dwopt trace" gpurun_out/bench_trace_g$N.log
 timeout 600 python bench.py --quick --steps 10 --warmup 3 > gpurun_out/bench_g1.log 2>&1
 tail -n 1 gpurun_out/bench_g1.log | cut -c1-200
 for g in 2 4 8; do
