@@ -36,7 +36,9 @@ constexpr int DWOPT_THREADS = 512;
 //                          most one exchange ahead of the slowest reader (it needs that reader's flag to finish).
 //                          Inside a slot: the 4-element units of the late leaves (16-byte aligned), then the early
 //                          elements and the two loss sums (dwopt job numbering).
-//   flags [16] u32         flags[q] = n once rank q's pushes of exchange n are visible here
+//   flags [W][256] u32     flags[q][b] = n once the pushes of CTA b of rank q for exchange n are visible here.  The
+//                          element -> (CTA, thread) mapping is the same on every rank, so CTA b only ever waits for
+//                          the CTAs b of the other ranks: no grid-wide barrier on the exchange path.
 struct PeerXchg {
   char* base[MINPPO_MAX_RANKS];  // rank r's allocation as mapped on THIS device
   unsigned int* seq;             // local exchange counter (device memory): exchanges completed so far
@@ -67,13 +69,20 @@ MINPPO_DEVINL unsigned int ld_acquire_sys_u32(const unsigned int* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// threads [0, world) wait until flags[t] >= n (bounded), then the CTA proceeds
-MINPPO_DEVINL void px_wait_flags(const unsigned int* flags, int world, unsigned int n, int* err_flag) {
+MINPPO_DEVINL unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// threads [0, world) wait until flags[t * stride] >= n (bounded), then the CTA proceeds
+MINPPO_DEVINL void px_wait_flags(const unsigned int* flags, int stride, int world, unsigned int n, int* err_flag) {
   if (static_cast<int>(threadIdx.x) < world) {
+    const unsigned int* f = flags + static_cast<size_t>(threadIdx.x) * stride;
     const long long t0 = clock64();
-    while (static_cast<int>(ld_acquire_sys_u32(flags + threadIdx.x) - n) < 0) {
+    while (static_cast<int>(ld_relaxed_sys_u32(f) - n) < 0) {
       if (clock64() - t0 > 8000000000LL) { atomicExch(err_flag, MINPPO_ERR_BARRIER); break; }
     }
+    asm volatile("fence.acquire.sys;" ::: "memory");
   }
   __syncthreads();
 }
@@ -92,9 +101,13 @@ struct alignas(64) DwOptParams {
   // one allocation [xbuf | rbuf | ss | flags] (PeerXchg offsets); base[r] is rank r's copy as mapped HERE.
   PeerXchg px;
   // L2 prefetch of the NEXT minibatch's observation rows (the fused step kernel gathers them first thing)
+  const int32_t* row_count;      // optional: rows of this minibatch on this rank (device side); partial sums of the
+                                 // per-tile (early) leaves and the prefetch stop there
+  int part_rows;                 // minibatch rows per early-leaf partial (128: fused step kernel, 64: head_loss kernel)
   const int32_t* next_ridx;      // [next_rows] or null
   const __nv_bfloat16* obs_img;  // [Bl][obs_ld]
   int next_rows, obs_ld;
+  const int32_t* next_count;     // optional: valid entries of next_ridx (device side)
 };
 
 // column sums of rows [r0, r1) of a bf16 [rows][n] matrix (n <= 256): one warp per row, 16-byte loads,
@@ -184,7 +197,8 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     griddep_wait();                                      // the small-leaf partials come from the fused step kernel
     if (t == 0) griddep_launch();
     const int e = b - p.gemm_ctas, ne = G - p.gemm_ctas;
-    ss = reduce_leaves<false>(a, T, e * NT + t, ne * NT);
+    const int live_tiles = p.row_count ? (max(__ldcg(p.row_count), 0) + p.part_rows - 1) / p.part_rows : 0x7fffffff;
+    ss = reduce_leaves<false>(a, T, e * NT + t, ne * NT, live_tiles);
     if (p.cs_chunks > 0 && e < p.cs_chunks * p.gemm.ngroups) {
       const int i = e % p.gemm.ngroups, c = e / p.gemm.ngroups;
       const int per = (p.cs_rows + p.cs_chunks - 1) / p.cs_chunks;
@@ -193,7 +207,8 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     }
     if (p.next_ridx) {                                   // warm L2 for the next step's gather
       const int lines = (p.obs_ld * 2) >> 7;
-      for (int j = e * NT + t; j < p.next_rows * lines; j += ne * NT) {
+      const int nrows = p.next_count ? min(p.next_rows, __ldcg(p.next_count)) : p.next_rows;
+      for (int j = e * NT + t; j < nrows * lines; j += ne * NT) {
         const char* row = reinterpret_cast<const char*>(p.obs_img + static_cast<size_t>(p.next_ridx[j / lines]) * p.obs_ld);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (j % lines) * 128));
       }
@@ -215,7 +230,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float pv[4], mv[4], nv[4];
   int ul = -1, ui = 0;                                   // leaf and first arena index of this thread's unit
-  if (!has_extra) ss += reduce_leaves<false>(a, T, gtid, G * NT);
+  if (!has_extra) ss += reduce_leaves<false>(a, T, gtid, G * NT, p.row_count ? (max(__ldcg(p.row_count), 0) + p.part_rows - 1) / p.part_rows : 0x7fffffff);
   // units dealt to warps round-robin over the CTAs (balanced, 512 contiguous bytes per warp and partial)
   const int unit = (((t >> 5) * G + b) << 5) + (t & 31);
   if (fast) {
@@ -275,10 +290,10 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
       for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W) st_sys_f32(px_stage(X, r, par, R) + n_late4 + gtid, gl);
     }
     DW_STAMP(13);
-    grid_barrier(a.barrier, a.err_flag);                 // every push of this rank has been issued
+    __syncthreads();                                     // every push of this CTA has been issued ...
+    if (t < W) st_release_sys_u32(px_flags(X, t) + R * 256 + b, n);       // ... and is visible before its flag
     DW_STAMP(14);
-    if (b == 0 && t < W) { __threadfence_system(); st_release_sys_u32(px_flags(X, t) + R, n); }
-    px_wait_flags(px_flags(X, R), W, n, a.err_flag);     // every rank's pushes of exchange n have landed here
+    px_wait_flags(px_flags(X, R) + b, 256, W, n, a.err_flag);             // CTA b of every rank has pushed exchange n
     DW_STAMP(15);
     // sum the W slots in rank order
     ss = 0.f;

@@ -555,6 +555,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     dp.gemm_ctas = cta;
     dp.cs_rows = c->M_pad; dp.cs_n = H; dp.cs_chunks = c->cs_chunks;
     if (s + 1 < c->E * c->M) { dp.next_ridx = ridx + c->cap; dp.obs_img = c->obs_img; dp.next_rows = c->cap; dp.obs_ld = c->Dp; }
+    if (sharded) { dp.row_count = c->counts + s; dp.next_count = c->counts + s + 1; dp.part_rows = c->fused ? 128 : 64; }
     dp.trace = c->trace_on ? c->trace2 : nullptr;
     // all-reduce fused into this launch (peer memory); needs the one-unit-per-thread fast path of the kernel
     const bool px_on = sharded && c->peers_set && c->P / 4 <= static_cast<long long>(c->sm_count) * DWOPT_THREADS;
@@ -802,7 +803,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     // the local gradient buffer lives inside the exchange allocation so that peers can read it (own cudaMalloc:
     // CUDA IPC exports whole allocations)
     const int np = static_cast<int>((c->P + 2 + 3) / 4 * 4);
-    const size_t floats = 2 * static_cast<size_t>(cfg->world_size) * np + 32;
+    const size_t floats = 2 * static_cast<size_t>(cfg->world_size) * np + static_cast<size_t>(cfg->world_size) * 256;
     ALLOC(c->xchg, floats);
     ALLOC(c->xseq, 1);
     c->px.np = np; c->px.world = 0; c->px.rank = cfg->rank; c->px.seq = c->xseq;

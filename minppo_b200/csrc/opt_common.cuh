@@ -172,7 +172,7 @@ MINPPO_DEVINL float4 sum_partials16_v4(const float* __restrict__ src, int nparts
 //                  aligned; gflat itself is only 4-byte aligned at a leaf offset).
 // Jobs are dealt round-robin (job = first + k * stride); the leaf walk is monotonic in k.
 template <bool LATE>
-MINPPO_DEVINL float reduce_leaves(const OptArgs& a, const LeafTab& T, int first, int stride) {
+MINPPO_DEVINL float reduce_leaves(const OptArgs& a, const LeafTab& T, int first, int stride, int max_parts = 0x7fffffff) {
   const int nl = T.nleaves;
   int l = -1, base = 0, n = 0;
   float ss = 0.f;
@@ -186,7 +186,7 @@ MINPPO_DEVINL float reduce_leaves(const OptArgs& a, const LeafTab& T, int first,
     }
     if (l >= nl) {
       if (!LATE && j - base < 2)          // the loss sums ride behind the early leaves
-        a.gflat[a.P + (j - base)] = sum_partials16(a.loss_src + a.loss_src_offset + (j - base), a.loss_nparts, a.loss_part_stride);
+        a.gflat[a.P + (j - base)] = sum_partials16(a.loss_src + a.loss_src_offset + (j - base), min(a.loss_nparts, max_parts), a.loss_part_stride);
       break;
     }
     const OptLeaf& L = T.leaf[l];
@@ -197,7 +197,7 @@ MINPPO_DEVINL float reduce_leaves(const OptArgs& a, const LeafTab& T, int first,
       dst[0] = g.x; dst[1] = g.y; dst[2] = g.z; dst[3] = g.w;
       ss = fmaf(g.x, g.x, ss); ss = fmaf(g.y, g.y, ss); ss = fmaf(g.z, g.z, ss); ss = fmaf(g.w, g.w, ss);
     } else {
-      const float g = sum_partials16(L.grad_src + L.src_offset + x, L.nparts, L.part_stride) + L.grad_bias;
+      const float g = sum_partials16(L.grad_src + L.src_offset + x, min(L.nparts, max_parts), L.part_stride) + L.grad_bias;
       a.gflat[L.offset + x] = g;
       ss = fmaf(g, g, ss);
     }
