@@ -139,6 +139,25 @@ int minppo_update(minppo_ctx* ctx, float* params, float* mu, float* nu, int32_t*
                   const uint8_t* done, const float* last_val, const uint32_t* key_in, uint32_t* key_out,
                   float* losses_out, int32_t use_graph, void* stream);
 
+/* ---- (5) policy / value inference for the rollout: replaces train.py:157-160 and 182-183 ------------
+ * One env step's network evaluation on this rank's Nl = N / world_size envs, forward only, on the same bf16 weight
+ * images and with the same rounding points as the learner's forward pass:
+ *   pi, value = network.apply(params, last_obs); rng, action_rng = split(rng);
+ *   action = pi.sample(seed=action_rng); log_prob = pi.log_prob(action)
+ * obs f32 [Nl, D] (read only).  Outputs (each may be NULL): action f32 [Nl, A], log_prob f32 [Nl], value f32 [Nl],
+ * mean f32 [Nl, A] (the distribution's mode, for evaluation).  key_in u32[2] -> key_out u32[2] = rng after the
+ * split (key_out may be NULL, must not alias key_in); key_in == NULL: no sampling, action = mean, log_prob of it.
+ * action == log_prob == mean == NULL: critic only -- the bootstrap value `_, last_val = network.apply(params,
+ * last_obs)` (train.py:182-183).
+ * The normal draw is the GLOBAL jax.random.normal(action_rng, (N, A)): an env-sharded rank produces its rows of it.
+ * flags: MINPPO_POLICY_WEIGHTS_CURRENT = the context's weight images already match `params` (true right after
+ * minppo_update or a previous policy step with the same, unmodified arena) -> skips the image refresh launch.
+ * Enqueues on `stream`, never synchronises; valid inside a caller's graph capture. */
+#define MINPPO_POLICY_WEIGHTS_CURRENT 1
+int minppo_policy_step(minppo_ctx* ctx, const float* params, const float* obs, const uint32_t* key_in,
+                       uint32_t* key_out, float* action, float* log_prob, float* value, float* mean,
+                       int32_t flags, void* stream);
+
 /* Device-side error flag of the last update (0 = ok); synchronises `stream`. */
 int minppo_ctx_check(minppo_ctx* ctx, void* stream);
 

@@ -24,7 +24,9 @@ SYMBOLS = (
     "minppo_nccl_unique_id", "minppo_ctx_create", "minppo_ctx_destroy", "minppo_update",
     "minppo_ctx_check", "minppo_update_launch_count", "minppo_ctx_read", "minppo_debug_gemm",
     "minppo_ctx_profile", "minppo_ctx_profile_read", "minppo_ctx_ipc_handle", "minppo_ctx_set_peers",
+    "minppo_policy_step",
 )
+POLICY_WEIGHTS_CURRENT = 1
 PROFILE_CLASSES = ("gae", "perm_sort", "rows_and_adv_stats", "obs_image", "weight_images", "fwd_gemm", "head_loss",
                    "bwd_gemm", "dw_gemm", "optimizer", "allreduce")
 
@@ -101,6 +103,8 @@ def load() -> C.CDLL:
     lib.minppo_ctx_ipc_handle.argtypes = [vp, vp]
     lib.minppo_ctx_set_peers.restype = C.c_int
     lib.minppo_ctx_set_peers.argtypes = [vp, vp]
+    lib.minppo_policy_step.restype = C.c_int
+    lib.minppo_policy_step.argtypes = [vp] * 9 + [i32, vp]
     lib.minppo_debug_gemm.restype = C.c_int
     lib.minppo_debug_gemm.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     _lib = lib

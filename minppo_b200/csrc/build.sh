@@ -6,9 +6,9 @@ OUT="$HERE/../lib"
 mkdir -p "$OUT"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function"
-for f in gae prng_sort minibatch head_loss adam learner; do
+for f in gae prng_sort minibatch head_loss policy adam learner; do
   $NVCC $FLAGS "$@" -c "$HERE/$f.cu" -o "$OUT/$f.o" &
 done
 wait
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libminppo_b200.so" "$OUT"/{gae,prng_sort,minibatch,head_loss,adam,learner}.o -lcudart -ldl
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libminppo_b200.so" "$OUT"/{gae,prng_sort,minibatch,head_loss,policy,adam,learner}.o -lcudart -ldl
 echo "built $OUT/libminppo_b200.so"

@@ -269,6 +269,11 @@ struct minppo_ctx {
   PeerXchg px;
   bool peers_set;
   void* peer_ptr[MINPPO_MAX_RANKS];
+  // policy / value inference for the rollout (minppo_policy_step): bf16 image of last_obs and the hidden activations
+  int pol_tiles;               // 128-row tiles over the Nl envs of this rank
+  __nv_bfloat16* pol_img;      // [pol_tiles * 128][Dp]
+  __nv_bfloat16* pol_act[2][MINPPO_MAX_LEAVES];   // [net][l], l = 1..L: [pol_tiles * 128][H]
+  CUtensorMap m_pol_img_k, m_pol_act_k[2][MINPPO_MAX_LEAVES];
   // per-kernel-class event profiling (eager mode only)
   bool profiling;
   std::vector<cudaEvent_t> prof_events;      // pairs (begin, end)
@@ -859,6 +864,17 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
       if ((rc = make_tmap_f32_3d(&nb.m_dw[l], nb.dw_part[l], H, in_l, c->S))) return fail(rc);
     }
   }
+  c->pol_tiles = (c->Nl + 127) / 128;
+  {
+    const size_t prow = static_cast<size_t>(c->pol_tiles) * 128;
+    ALLOC(c->pol_img, prow * c->Dp);
+    if ((rc = make_tmap(&c->m_pol_img_k, c->pol_img, c->Dp, prow, c->Dp, 64, 128))) return fail(rc);
+    for (int net = 0; net < 2; ++net)
+      for (int l = 1; l <= L; ++l) {
+        ALLOC(c->pol_act[net][l], prow * H);
+        if ((rc = make_tmap(&c->m_pol_act_k[net][l], c->pol_act[net][l], H, prow, H, 64, 128))) return fail(rc);
+      }
+  }
 #undef ALLOC
   if (cfg->world_size > 1) {
     NcclApi* api = nccl_api();
@@ -913,6 +929,60 @@ int minppo_update(minppo_ctx* c, float* params, float* mu, float* nu, int32_t* c
   }
   CK(cudaGraphLaunch(c->graph_exec, stream));
   return 0;
+}
+
+int minppo_policy_step(minppo_ctx* c, const float* params, const float* obs, const uint32_t* key_in, uint32_t* key_out,
+                       float* action, float* log_prob, float* value, float* mean, int32_t flags, void* stream_v) {
+  if (!c || !params || !obs) { set_error("minppo_policy_step: null pointer"); return MINPPO_ERR_ARG; }
+  if (key_in && key_out == key_in) { set_error("minppo_policy_step: key_out must not alias key_in"); return MINPPO_ERR_ARG; }
+  const bool actor = action || log_prob || mean;
+  if (!actor && !value) { set_error("minppo_policy_step: no output requested"); return MINPPO_ERR_ARG; }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int L = c->L, H = c->H;
+  // bf16 image of last_obs, zero padded to Dp columns (rows >= Nl of the image stay zero from allocation)
+  RET(obs_image_launch(obs, c->pol_img, c->Nl, c->D, c->Dp, stream));
+  if (!(flags & MINPPO_POLICY_WEIGHTS_CURRENT)) {
+    UpdatePtrs u;
+    memset(&u, 0, sizeof(u));
+    u.params = const_cast<float*>(params);               // weight_images only reads the arena
+    OptArgs o;
+    fill_opt_args(c, u, &o);
+    RET(weight_images_launch(o, stream));
+  }
+  const int first = actor ? 0 : 1;                        // critic only: the bootstrap value (train.py:182-183)
+  for (int l = 0; l < L; ++l) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    int ng = 0;
+    for (int net = first; net < 2; ++net) {
+      GemmGroup& g = p.g[ng];
+      g.cta_begin = ng * c->pol_tiles;
+      ++ng;
+      g.bmode = B_TMA_MN; g.tmB = c->net[net].m_wn_mn[l];
+      g.amode = A_TMA_K;
+      if (l == 0) { g.tmA = c->m_pol_img_k; g.kb_total = c->Dp / 64; }
+      else { g.tmA = c->m_pol_act_k[net][l]; g.kb_total = H / 64; }
+      g.out = c->pol_act[net][l + 1]; g.ldo = H;
+      g.bias = params + find_leaf(c, net, l, 0).offset;
+      g.act = act_kind(c, net);
+      g.N = H; g.m_tiles = c->pol_tiles; g.splits = 1; g.m_store = c->pol_tiles * 128;
+    }
+    p.ngroups = ng;
+    RET(launch_gemm<EPI_ACT>(p, ng * c->pol_tiles, stream));
+  }
+  PolicyHeadArgs a;
+  memset(&a, 0, sizeof(a));
+  a.h_a = actor ? c->pol_act[0][L] : nullptr;
+  a.h_c = c->pol_act[1][L];
+  a.params = params;
+  a.off_w3a = static_cast<int>(find_leaf(c, 0, L, 1).offset); a.off_b3a = static_cast<int>(find_leaf(c, 0, L, 0).offset);
+  a.off_w3c = static_cast<int>(find_leaf(c, 1, L, 1).offset); a.off_b3c = static_cast<int>(find_leaf(c, 1, L, 0).offset);
+  a.off_logstd = static_cast<int>(c->leaves.back().offset);
+  a.H = H; a.A = c->A; a.ldh = H; a.rows = c->Nl;
+  a.n0 = c->n0; a.n_total = static_cast<long long>(c->N) * c->A;
+  a.key_in = actor ? key_in : nullptr; a.key_out = actor ? key_out : nullptr; a.mode = c->cfg.prng_mode;
+  a.action = action; a.log_prob = log_prob; a.value = value; a.mean_out = mean;
+  return policy_head_launch(a, stream);
 }
 
 int minppo_ctx_ipc_handle(minppo_ctx* c, void* handle64_host) {

@@ -61,6 +61,26 @@ struct HeadLossArgs {
 int head_loss_init();
 int head_loss_launch(const HeadLossArgs& a, int tiles, cudaStream_t stream);
 
+// ---- policy.cu ---------------------------------------------------------------------------
+struct PolicyHeadArgs {
+  const __nv_bfloat16* h_a;      // last hidden activation, actor  [rows_pad][ldh]; null = critic only (bootstrap value)
+  const __nv_bfloat16* h_c;      // last hidden activation, critic [rows_pad][ldh]
+  const float* params;           // fp32 arena
+  int off_w3a, off_b3a, off_w3c, off_b3c, off_logstd;
+  int H, A, ldh;
+  int rows;                      // env rows of this rank
+  long long n0;                  // first GLOBAL env index of this rank
+  long long n_total;             // elements of the global normal draw, N * A
+  const uint32_t* key_in;        // RunnerState.rng [2]; null = no sampling (action = mean)
+  uint32_t* key_out;             // rng after `rng, action_rng = split(rng)`; may be null; must not alias key_in
+  int mode;                      // MINPPO_PRNG_*
+  float* action;                 // [rows][A] or null
+  float* log_prob;               // [rows] or null
+  float* value;                  // [rows] or null
+  float* mean_out;               // [rows][A] or null
+};
+int policy_head_launch(const PolicyHeadArgs& a, cudaStream_t stream);
+
 // ---- adam.cu -----------------------------------------------------------------------------
 struct OptLeaf {
   int offset;                    // first element in the arena

@@ -237,6 +237,41 @@ class Learner:
                 _ptr(rng), _ptr(rng_out), _ptr(losses), int(self.use_graph), _stream_ptr(dev)))
         return train_state, rng_out, losses
 
+    # -- policy / value inference for the rollout -------------------------------------------
+    def policy_step(self, params: torch.Tensor, last_obs: torch.Tensor, rng: Optional[torch.Tensor],
+                    weights_current: bool = False, want_mean: bool = False):
+        """train.py:157-160: ``pi, value = network.apply(params, last_obs); rng, action_rng = split(rng);
+        action = pi.sample(seed=action_rng); log_prob = pi.log_prob(action)`` on this rank's ``Nl`` envs.
+        Returns (action [Nl, A], log_prob [Nl], value [Nl], rng', mean or None).  ``rng=None``: no sampling
+        (action = the mode of pi, rng' = None).  Nothing synchronises."""
+        dev = self.device
+        obs = _check(last_obs, "last_obs", torch.float32, (self.Nl, self.obs_dim), dev)
+        _check(params, "params", torch.float32, (self.P,), dev)
+        if rng is not None and (rng.numel() != 2 or rng.element_size() != 4 or rng.device != dev):
+            raise ValueError("rng must hold two 32-bit words on the learner's device")
+        action = torch.empty((self.Nl, self.act_dim), dtype=torch.float32, device=dev)
+        log_prob = torch.empty((self.Nl,), dtype=torch.float32, device=dev)
+        value = torch.empty((self.Nl,), dtype=torch.float32, device=dev)
+        mean = torch.empty_like(action) if want_mean else None
+        rng_out = torch.empty_like(rng) if rng is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.minppo_policy_step(
+                self._h, _ptr(params), _ptr(obs), _ptr(rng), _ptr(rng_out), _ptr(action), _ptr(log_prob), _ptr(value),
+                _ptr(mean), _lib.POLICY_WEIGHTS_CURRENT if weights_current else 0, _stream_ptr(dev)))
+        return action, log_prob, value, rng_out, mean
+
+    def bootstrap_value(self, params: torch.Tensor, last_obs: torch.Tensor, weights_current: bool = False) -> torch.Tensor:
+        """train.py:182-183: ``_, last_val = network.apply(params, last_obs)`` (critic only)."""
+        dev = self.device
+        obs = _check(last_obs, "last_obs", torch.float32, (self.Nl, self.obs_dim), dev)
+        _check(params, "params", torch.float32, (self.P,), dev)
+        value = torch.empty((self.Nl,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.minppo_policy_step(
+                self._h, _ptr(params), _ptr(obs), None, None, None, None, _ptr(value), None,
+                _lib.POLICY_WEIGHTS_CURRENT if weights_current else 0, _stream_ptr(dev)))
+        return value
+
     def check(self) -> None:
         """Synchronise and raise if the device-side error flag is set, a row list overflowed
         or a gradient norm is not finite (the reference has no such guard)."""

@@ -246,6 +246,30 @@ def gaussian_entropy(log_std, act_dim: int):
     return dt(act_dim * (0.5 + 0.5 * LOG_2PI)) + np.log(np.abs(scale)).sum()
 
 
+def policy_step(params: Dict, obs, rng, hp: Hyper, mode: int = 0, gemm="exact", sample: bool = True):
+    """One env step's network evaluation, train.py:157-160:
+
+        pi, value = network.apply(params, last_obs); rng, action_rng = jax.random.split(rng)
+        action = pi.sample(seed=action_rng); log_prob = pi.log_prob(action)
+
+    distrax.MultivariateNormalDiag.sample = loc + scale * jax.random.normal(action_rng, (N, A)) (Normal(0,1)._sample_n
+    pushed through the Shift / ScalarAffine bijectors).  Returns (action, log_prob, value, rng', mean).
+    ``sample=False``: action = mean, rng unchanged.  ``obs`` is the GLOBAL [N, D] batch."""
+    from . import threefry as tf
+
+    mean, log_std, value, _ = actor_critic_forward(params, obs, hp, gemm)
+    dt = mean.dtype.type
+    if sample:
+        rng2, action_rng = tf.split(np.asarray(rng, np.uint32), 2, mode)
+        n, a = mean.shape
+        eps = tf.normal_f32(action_rng, n * a, mode, erfinv="xla").reshape(n, a).astype(mean.dtype)
+        action = mean + np.exp(log_std).astype(mean.dtype) * eps
+    else:
+        rng2, action = np.asarray(rng, np.uint32), mean.copy()
+    logp, _, _ = gaussian_log_prob(mean, log_std, action)
+    return action.astype(mean.dtype), logp.astype(mean.dtype), value, rng2, mean
+
+
 # ----------------------------------------------------------------------------------------
 # loss and gradient  (train.py:218-247)
 # ----------------------------------------------------------------------------------------

@@ -147,12 +147,45 @@ def _erfinv_f32(x: np.ndarray) -> np.ndarray:
     return erfinv(x.astype(np.float64)).astype(np.float32)
 
 
-def normal_f32(key: np.ndarray, n: int, mode: int = LEGACY) -> np.ndarray:
-    """``jax.random.normal(key, (n,))`` in float32: bits -> uniform(-1+eps, 1) -> erfinv.
-    Only used to check the anchors quoted from JAX's documentation."""
-    bits = random_bits(key, n, mode)
+_GILES_LT = (2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503,
+             -0.00417768164, 0.246640727, 1.50140941)
+_GILES_GE = (-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613,
+             0.00943887047, 1.00167406, 2.83297682)
+
+
+def erfinv_xla_f32(x: np.ndarray) -> np.ndarray:
+    """XLA's single-precision ``erf_inv`` as ``jax.random.normal`` reaches it (``lax.erf_inv``): M. Giles'
+    polynomial -- ``w = -log1p(-x*x)``; ``w < 5``: degree-8 polynomial in ``w - 2.5``; else in ``sqrt(w) - 3``;
+    result ``p * x``.  float32 throughout (third-party arithmetic restated from the published algorithm;
+    anchored by the JAX-documentation normal() values in tests/test_oracle_threefry.py)."""
+    x = np.asarray(x, np.float32)
+    f = np.float32
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = -np.log1p(-(x * x)).astype(np.float32)
+        lt = w < f(5.0)
+        wl = (w - f(2.5)).astype(np.float32)
+        wg = (np.sqrt(np.where(lt, f(9.0), w)).astype(np.float32) - f(3.0)).astype(np.float32)
+        ww = np.where(lt, wl, wg).astype(np.float32)
+        p = np.where(lt, f(_GILES_LT[0]), f(_GILES_GE[0])).astype(np.float32)
+        for cl, cg in zip(_GILES_LT[1:], _GILES_GE[1:]):
+            p = (np.where(lt, f(cl), f(cg)) + p * ww).astype(np.float32)
+        out = (p * x).astype(np.float32)
+    return np.where(np.abs(x) == f(1.0), np.copysign(f(np.inf), x), out).astype(np.float32)
+
+
+def normal_from_bits_f32(bits: np.ndarray, erfinv: str = "xla") -> np.ndarray:
+    """``jax.random.normal`` element-wise from its 32 random bits (jax/_src/random.py ``_uniform`` + ``_normal_real``):
+    mantissa trick -> [0,1) -> uniform(nextafter(-1,0), 1) -> sqrt(2) * erf_inv(u)."""
+    bits = np.asarray(bits, np.uint32)
     f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
     lo = np.nextafter(np.float32(-1.0), np.float32(0.0))
     hi = np.float32(1.0)
     u = np.maximum(lo, f * (hi - lo) + lo).astype(np.float32)
-    return (np.float32(math.sqrt(2.0)) * _erfinv_f32(u)).astype(np.float32)
+    e = erfinv_xla_f32(u) if erfinv == "xla" else _erfinv_f32(u)
+    return (np.float32(math.sqrt(2.0)) * e).astype(np.float32)
+
+
+def normal_f32(key: np.ndarray, n: int, mode: int = LEGACY, erfinv: str = "scipy") -> np.ndarray:
+    """``jax.random.normal(key, (n,))`` in float32.  ``erfinv="scipy"``: correctly rounded erf_inv (checks the anchors
+    quoted from JAX's documentation); ``"xla"``: the polynomial XLA evaluates (what the policy sampler mirrors)."""
+    return normal_from_bits_f32(random_bits(key, n, mode), erfinv)

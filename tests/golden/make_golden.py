@@ -60,6 +60,20 @@ def main():
     np.savez_compressed(os.path.join(HERE, "lr_schedule_golden.npz"),
                         one_update=np.array([P.learning_rate(c, hq, np.float32) for c in range(128)], np.float32),
                         default=np.array([P.learning_rate(c, hd, np.float32) for c in range(128)], np.float32))
+
+    # ---- policy step (train.py:157-160): normal draws (XLA erf_inv) and one sampled step at N=16 -----------------
+    pol = {}
+    for mode, tag in ((threefry.LEGACY, "legacy"), (threefry.PARTITIONABLE, "partitionable")):
+        key = threefry.prng_key(1337)
+        pol[f"normal_{tag}_160"] = threefry.normal_f32(key, 160, mode, erfinv="xla")
+        pol[f"normal_{tag}_7"] = threefry.normal_f32(key, 7, mode, erfinv="xla")
+        hq = P.Hyper(num_envs=16, num_steps=10, num_minibatches=32, update_epochs=4, anneal_lr=False, prng_mode=mode)
+        pq = synth.make_problem(hq, seed=1)
+        obs0 = pq["traj"]["obs"][0]
+        a, lp, v, rng2, mean = P.policy_step(pq["params"], obs0, pq["rng"], hq, mode)
+        pol[f"step_{tag}_action"], pol[f"step_{tag}_log_prob"], pol[f"step_{tag}_value"] = a, lp, v
+        pol[f"step_{tag}_rng"], pol[f"step_{tag}_mean"] = rng2, mean
+    np.savez_compressed(os.path.join(HERE, "policy_golden.npz"), **pol)
     print("wrote", sorted(os.listdir(HERE)))
 
 

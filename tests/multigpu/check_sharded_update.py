@@ -32,12 +32,15 @@ def run(hp, pr, dev, world, rank, nccl_id, n0, Nl):
     mem = Memory(done=t(tr["done"]), action=t(tr["action"]), value=t(tr["value"]), reward=t(tr["reward"]),
                  log_prob=t(tr["log_prob"]), obs=t(tr["obs"]))
     rng = torch.as_tensor(pr["rng"].view(np.int32)).to(dev)
+    # one env step of the rollout policy on this rank's envs (train.py:157-160): the normal draw is the GLOBAL [N, A] one
+    pa, plp, pv, prng, _ = learner.policy_step(ts.params, mem.obs[0].contiguous(), rng)
+    pol = torch.cat([pa, plp[:, None], pv[:, None]], dim=1).clone()
     for _ in range(2):                                   # two updates: the second replays the captured graph
         ts, rng_out, losses = learner.update(ts, mem, t(pr["last_val"][n0:n0 + Nl]), rng)
     learner.check()
     out = {"params": ts.params.cpu().numpy(), "losses": losses.cpu().numpy(), "rng": rng_out.cpu().numpy(),
            "perms": learner.read("perms").cpu().numpy(), "step": int(ts.step.item()),
-           "counts": learner.read("counts").cpu().numpy()}
+           "counts": learner.read("counts").cpu().numpy(), "pol": pol, "pol_rng": prng.cpu().numpy()}
     learner.close()
     return out
 
@@ -62,6 +65,8 @@ def main():
         allp = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allp, mine)
         same = all(torch.equal(allp[0], x) for x in allp)
+        allpol = [torch.empty_like(got["pol"]) for _ in range(world)]
+        dist.all_gather(allpol, got["pol"])
         if rank == 0:
             ref = run(hp, pr, dev, 1, 0, None, 0, hp.num_envs)
             lr = hp.opt_lr
@@ -69,6 +74,8 @@ def main():
             checks = {
                 "params identical on all ranks": same,
                 "perms bit-exact": bool(np.array_equal(got["perms"], ref["perms"])),
+                "policy step (action, log_prob, value) of the shards == single GPU, bit-exact":
+                    bool(torch.equal(torch.cat(allpol, dim=0), ref["pol"]) and np.array_equal(got["pol_rng"], ref["pol_rng"])),
                 "rng bit-exact": bool(np.array_equal(got["rng"], ref["rng"])),
                 "step": got["step"] == ref["step"] == nsteps,
                 "losses": rel_err(got["losses"], ref["losses"]) < 2e-3,
