@@ -239,6 +239,13 @@ def run_ours(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    if os.environ.get("MINPPO_BENCH_ENABLE_P2P") and torch.cuda.device_count() > 1:
+        # development probe: a cross-device copy makes torch enable peer access on this context (does a context with
+        # peer mappings pay more per kernel boundary?)
+        other = (local_rank + 1) % torch.cuda.device_count()
+        torch.zeros(1024, device=dev).to(f"cuda:{other}")
+        torch.zeros(1024, device=f"cuda:{other}").to(dev)
+        torch.cuda.synchronize()
     nccl_id = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)

@@ -27,23 +27,24 @@ namespace minppo {
 // per SM: with 6 warps the dependent divide / sqrt chains of the Adam phase had nothing to hide behind)
 constexpr int DWOPT_THREADS = 512;
 
-// Gradient exchange over NVLink peer memory, ONE-SHOT: every rank pushes its local gradient sums into a staging slot
-// on every rank (itself included) while it reduces them, one flag round says "all of rank q's pushes for exchange n
-// are done", then every rank sums the W staging slots in rank order -- same values, same order, so all ranks apply
-// bit-identical gradients with no broadcast -- and continues with the norm and Adam exactly like a single GPU.
+// Gradient exchange over NVLink peer memory, ONE-SHOT, Lamport style: every rank pushes its local gradient sums into
+// a staging slot on every OTHER rank; the staging words themselves are the arrival flags (sentinel -0.0f until written),
+// so an exchange costs one NVLink one-way latency -- no release/acknowledge round and no flag round.  Every rank then
+// sums the W contributions in rank order (same values, same order: bit-identical gradients on all ranks with no
+// broadcast), resets the words it consumed to the sentinel and continues with the norm and Adam like a single GPU.
 // Exchange allocation of one rank (exported by CUDA IPC):
-//   stage [2][W][np] f32   slot (n & 1, q): rank q's local gradient of exchange n.  Double-buffered: a rank can be at
-//                          most one exchange ahead of the slowest reader (it needs that reader's flag to finish).
+//   stage [2][W][np] f32   slot (n & 1, q): rank q's local gradient of exchange n (all words start as the sentinel).
 //                          Inside a slot: the 4-element units of the late leaves (16-byte aligned), then the early
-//                          elements and the two loss sums (dwopt job numbering).
-//   flags [W][256] u32     flags[q][b] = n once the pushes of CTA b of rank q for exchange n are visible here.  The
-//                          element -> (CTA, thread) mapping is the same on every rank, so CTA b only ever waits for
-//                          the CTAs b of the other ranks: no grid-wide barrier on the exchange path.
+//                          elements and the two loss sums (dwopt job numbering).  The element -> (CTA, thread)
+//                          mapping is the same on every rank: a thread only ever waits for its own unit.
+//   flags [W][256] u32     unused by this protocol (kept for layout compatibility).
 struct PeerXchg {
   char* base[MINPPO_MAX_RANKS];  // rank r's allocation as mapped on THIS device
   unsigned int* seq;             // local exchange counter (device memory): exchanges completed so far
   int world, rank;
   int np;                        // floats per staging slot (multiple of 4)
+  int ablate;                    // debug (MINPPO_PX_ABLATE, TIMING ONLY, wrong results): 1 = push but never wait for the
+                                 // peers, 2 = neither push nor wait
 };
 MINPPO_DEVINL float* px_stage(const PeerXchg& x, int r, unsigned int par, int q) {
   return reinterpret_cast<float*>(x.base[r]) + (static_cast<size_t>(par) * x.world + q) * x.np;
@@ -191,7 +192,24 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
 
   // ---- phase 1 ----------------------------------------------------------------------------------
   if (b < p.gemm_ctas) {
-    umma_gemm_body<EPI_PARTIAL>(p.gemm, smem_raw, p.trace ? p.trace + static_cast<size_t>(b) * 16 : nullptr, scalars);   // PDL wait / trigger inside
+    // Helper warps (idle until the accumulator is complete): the per-step scalars, and this CTA's share of the L2
+    // prefetch of the NEXT minibatch's observation rows (row lists and the observation image are static during an
+    // update: no dependency on the preceding kernel).  Spread over all GEMM CTAs so that it never rides on the few
+    // spare CTAs, whose number depends on the split-K factor.
+    auto idle_work = [&]() {
+      scalars();
+      if (p.next_ridx) {
+        constexpr int HELPERS = DWOPT_THREADS - GEMM_THREADS;
+        const int h = t - GEMM_THREADS;
+        const int lines = (p.obs_ld * 2) >> 7;
+        const int nrows = p.next_count ? min(p.next_rows, __ldcg(p.next_count)) : p.next_rows;
+        for (int j = b * HELPERS + h; j < nrows * lines; j += p.gemm_ctas * HELPERS) {
+          const char* row = reinterpret_cast<const char*>(p.obs_img + static_cast<size_t>(p.next_ridx[j / lines]) * p.obs_ld);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (j % lines) * 128));
+        }
+      }
+    };
+    umma_gemm_body<EPI_PARTIAL>(p.gemm, smem_raw, p.trace ? p.trace + static_cast<size_t>(b) * 16 : nullptr, idle_work);   // PDL wait / trigger inside
   } else {
     scalars();
     griddep_wait();                                      // the small-leaf partials come from the fused step kernel
@@ -204,14 +222,6 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
       const int per = (p.cs_rows + p.cs_chunks - 1) / p.cs_chunks;
       colsum_rows(p.cs_src[i], p.cs_n, min(p.cs_rows, c * per), min(p.cs_rows, (c + 1) * per),
                   p.cs_out[i] + static_cast<size_t>(c) * p.cs_n, reinterpret_cast<float*>(smem_raw));
-    }
-    if (p.next_ridx) {                                   // warm L2 for the next step's gather
-      const int lines = (p.obs_ld * 2) >> 7;
-      const int nrows = p.next_count ? min(p.next_rows, __ldcg(p.next_count)) : p.next_rows;
-      for (int j = e * NT + t; j < nrows * lines; j += ne * NT) {
-        const char* row = reinterpret_cast<const char*>(p.obs_img + static_cast<size_t>(p.next_ridx[j / lines]) * p.obs_ld);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (j % lines) * 128));
-      }
     }
   }
   DW_STAMP(1);
@@ -262,7 +272,8 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   if (px_on) {
     // ---- one-shot all-reduce over NVLink peer memory (PeerXchg above; requires the fast path) -----------------
     const PeerXchg& X = p.px;
-    const int W = X.world, R = X.rank;
+    const int R = X.rank;
+    const int W = X.ablate == 2 ? 1 : X.world;             // ablation: behave like a lone rank (slot R is never read)
     const unsigned int n = s_seq, par = n & 1u;
     const int n_late4 = 4 * n_units;
     // early element (or loss sum) of this thread: same job numbering as apply_adam_class<false>
@@ -279,40 +290,78 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
         eidx = T.leaf[l].offset + x;
       }
     }
-    // push the local sums into slot (par, R) of every rank
+    // Lamport-style exchange: the data is its own flag.  Every staging word holds the sentinel -0.0f until a peer's
+    // push lands (a gradient that is exactly -0.0 is sent as +0.0: same sums); the reader polls its own unit of each
+    // peer's slot until all four words are real, sums the W contributions in rank order (its own from registers) and
+    // puts the sentinel back.  One NVLink one-way latency per exchange: no release/acknowledge round, no flag round.
+    // Slot reuse (parity of n) is safe without a fence: a peer can only push exchange n + 2 after it has completed
+    // n + 1, which needed this rank's pushes of n + 1, which were issued by a later launch than this one's clears.
+    constexpr unsigned int SENT = 0x80000000u;
+    g4.x = g4.x == 0.f ? 0.f : g4.x; g4.y = g4.y == 0.f ? 0.f : g4.y;
+    g4.z = g4.z == 0.f ? 0.f : g4.z; g4.w = g4.w == 0.f ? 0.f : g4.w;
     if (ul >= 0) {
 #pragma unroll
-      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W) st_sys_v4(px_stage(X, r, par, R) + 4 * unit, g4);
+      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_v4(px_stage(X, r, par, R) + 4 * unit, g4);
     }
+    float gl = 0.f;
     if (eidx >= 0) {
-      const float gl = __ldcg(a.gflat + eidx);
+      gl = __ldcg(a.gflat + eidx);
+      gl = gl == 0.f ? 0.f : gl;
 #pragma unroll
-      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W) st_sys_f32(px_stage(X, r, par, R) + n_late4 + gtid, gl);
+      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_f32(px_stage(X, r, par, R) + n_late4 + gtid, gl);
     }
     DW_STAMP(13);
-    __syncthreads();                                     // every push of this CTA has been issued ...
-    if (t < W) st_release_sys_u32(px_flags(X, t) + R * 256 + b, n);       // ... and is visible before its flag
-    DW_STAMP(14);
-    px_wait_flags(px_flags(X, R) + b, 256, W, n, a.err_flag);             // CTA b of every rank has pushed exchange n
-    DW_STAMP(15);
-    // sum the W slots in rank order
     ss = 0.f;
+    const long long t0 = clock64();
     if (ul >= 0) {
       float4 v[MINPPO_MAX_RANKS];
+      unsigned int pending = X.ablate ? 0u : ((1u << W) - 1u) & ~(1u << R);
 #pragma unroll
-      for (int q = 0; q < MINPPO_MAX_RANKS; ++q) if (q < W) v[q] = __ldcg(reinterpret_cast<const float4*>(px_stage(X, R, par, q) + 4 * unit));
+      for (int q = 0; q < MINPPO_MAX_RANKS; ++q) v[q] = g4;
+      while (pending) {
+#pragma unroll
+        for (int q = 0; q < MINPPO_MAX_RANKS; ++q) {
+          if ((pending >> q) & 1u) {
+            v[q] = ld_sys_v4(px_stage(X, R, par, q) + 4 * unit);
+            if (__float_as_uint(v[q].x) != SENT && __float_as_uint(v[q].y) != SENT && __float_as_uint(v[q].z) != SENT &&
+                __float_as_uint(v[q].w) != SENT)
+              pending &= ~(1u << q);
+          }
+        }
+        if (pending && clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
+      }
+      const float4 own = g4;
       g4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int q = 0; q < MINPPO_MAX_RANKS; ++q) if (q < W) { g4.x += v[q].x; g4.y += v[q].y; g4.z += v[q].z; g4.w += v[q].w; }
+      for (int q = 0; q < MINPPO_MAX_RANKS; ++q) {
+        if (q < W) {
+          const float4 c = q == R ? own : v[q];
+          g4.x += c.x; g4.y += c.y; g4.z += c.z; g4.w += c.w;
+          if (q != R) st_sys_v4(px_stage(X, R, par, q) + 4 * unit, make_float4(-0.f, -0.f, -0.f, -0.f));
+        }
+      }
       if (a.keep_gflat) { float* dst = a.gflat + ui; dst[0] = g4.x; dst[1] = g4.y; dst[2] = g4.z; dst[3] = g4.w; }
       ss = fmaf(g4.x, g4.x, ss); ss = fmaf(g4.y, g4.y, ss); ss = fmaf(g4.z, g4.z, ss); ss = fmaf(g4.w, g4.w, ss);
     }
     if (eidx >= 0) {
       float ge = 0.f;
-      for (int q = 0; q < W; ++q) ge += __ldcg(px_stage(X, R, par, q) + n_late4 + gtid);
+      for (int q = 0; q < W; ++q) {
+        float c = gl;
+        if (q != R) {
+          float* src = px_stage(X, R, par, q) + n_late4 + gtid;
+          unsigned int w;
+          while ((w = ld_relaxed_sys_u32(reinterpret_cast<const unsigned int*>(src))) == SENT && !X.ablate) {
+            if (clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
+          }
+          c = __uint_as_float(w);
+          st_sys_f32(src, -0.f);
+        }
+        ge += c;
+      }
       a.gflat[eidx] = ge;                                // read back by this same thread (small leaves) / after the barrier (losses)
       if (eidx < P) ss = fmaf(ge, ge, ss);
     }
+    DW_STAMP(15);
     if (b == 0 && scal_thread) *X.seq = n;
   }
   if (!a.do_apply) return;

@@ -84,7 +84,7 @@ struct alignas(64) FusedParams {
   long long* trace;              // debug: [ctas][32] clock64 stamps (null = off)
 };
 
-#define FS_STAMP(slot) do { if (p.trace) p.trace[static_cast<size_t>(blockIdx.x) * 32 + (slot)] = clock64(); } while (0)
+#define FS_STAMP(slot) do { if (p.trace) p.trace[static_cast<size_t>(cta_id) * 32 + (slot)] = clock64(); } while (0)
 
 MINPPO_DEVINL void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -214,8 +214,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int net = static_cast<int>(blockIdx.x) / p.m_tiles;
-  const int tile = static_cast<int>(blockIdx.x) % p.m_tiles;
+  // CTA order: (tile, net) with net fastest, so that the LIVE tiles of both nets are the lowest block indices and fit the
+  // first wave even when the grid is sized for an env-sharded rank's worst-case row count (dead tiles come last)
+  const int net = static_cast<int>(blockIdx.x) & 1;
+  const int tile = static_cast<int>(blockIdx.x) >> 1;
+  const int cta_id = net * p.m_tiles + tile;             // trace row (net-major, scripts/trace_fused.py)
   const FusedNet& G = p.net[net];
   const int H = p.H, nkH = H >> 6, nk0 = p.Dp >> 6;
   const uint32_t R0 = base + FS_R0, R1 = base + FS_R1, RB = base + FS_RB;

@@ -14,6 +14,7 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <math.h>
+#include <algorithm>
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -109,6 +110,9 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
   ncclResult_t (*CommDestroy)(ncclComm_t);
   const char* (*GetErrorString)(ncclResult_t);
   bool ok;
@@ -124,9 +128,13 @@ static NcclApi* nccl_api() {
       api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
       api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
       api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+      api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(h, "ncclBroadcast"));
+      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
+      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
       api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
       api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.Broadcast && api.GroupStart && api.GroupEnd &&
+               api.CommDestroy && api.GetErrorString;
     }
   }
   return api.ok ? &api : nullptr;
@@ -243,6 +251,10 @@ struct minppo_ctx {
   bool merged_opt;            // dW GEMM + reduction + Adam in one launch (MINPPO_SPLIT_OPT=1 disables)
   int skip_mask;              // debug (MINPPO_SKIP): 1 = no fused step, 2 = no dW GEMM, 4 = no optimizer (timing ablation only)
   int32_t *perms, *rowidx, *counts;
+  int32_t* perm_tmp;          // world_size > 1: the epochs THIS rank sorts ([ceil(E / W)][B]); broadcast into perms
+  bool padded;                // row lists sized for a worst-case row count (world_size > 1, or MINPPO_EMULATE_SHARD_PAD=W: timing probe
+                              // of the sharded shapes on one GPU): device-side row counts bound the per-minibatch work
+  bool share_perm;            // epoch e is sorted by rank e % W only and broadcast (MINPPO_SHARE_PERM=0: every rank sorts all)
   void* perm_ws;
   size_t perm_ws_bytes;
   __nv_bfloat16* obs_img;
@@ -316,6 +328,10 @@ static int dev_alloc(minppo_ctx* c, T** p, size_t n, bool zero = true) {
   c->allocs.push_back(q);
   *p = reinterpret_cast<T*>(q);
   return 0;
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) p[i] = v;
 }
 
 static const LeafInfo& find_leaf(const minppo_ctx* c, int net, int layer, int is_kernel) {
@@ -540,7 +556,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
         else { g.amode = A_TMA_MN; g.tmA = nb.m_act_mn[l]; }
         g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
         g.kb_total = c->M_pad / 64;
-        g.k_count = c->cfg.world_size > 1 ? c->counts + s : nullptr;
+        g.k_count = c->padded ? c->counts + s : nullptr;
         g.tmC = nb.m_dw[l];
         g.colsum_out = c->cs_chunks > 0 ? nullptr : nb.dbias[l];
         dp.cs_src[ng - 1] = nb.dz[l + 1]; dp.cs_out[ng - 1] = nb.dbias[l];
@@ -560,11 +576,11 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     dp.gemm_ctas = cta;
     dp.cs_rows = c->M_pad; dp.cs_n = H; dp.cs_chunks = c->cs_chunks;
     if (s + 1 < c->E * c->M) { dp.next_ridx = ridx + c->cap; dp.obs_img = c->obs_img; dp.next_rows = c->cap; dp.obs_ld = c->Dp; }
-    if (sharded) { dp.row_count = c->counts + s; dp.next_count = c->counts + s + 1; dp.part_rows = c->fused ? 128 : 64; }
+    if (c->padded) { dp.row_count = c->counts + s; dp.next_count = c->counts + s + 1; dp.part_rows = c->fused ? 128 : 64; }
     dp.trace = c->trace_on ? c->trace2 : nullptr;
     // all-reduce fused into this launch (peer memory); needs the one-unit-per-thread fast path of the kernel
     const bool px_on = sharded && c->peers_set && c->P / 4 <= static_cast<long long>(c->sm_count) * DWOPT_THREADS;
-    if (px_on) dp.px = c->px;
+    if (px_on) { dp.px = c->px; dp.px.ablate = getenv("MINPPO_PX_ABLATE") ? atoi(getenv("MINPPO_PX_ABLATE")) : 0; }
     o.do_reduce = 1; o.do_apply = (sharded && !px_on) ? 0 : 1;
     {
       PROF(PC_DW_GEMM);
@@ -614,7 +630,26 @@ static int enqueue_update(minppo_ctx* c, const UpdatePtrs& u, cudaStream_t strea
     RET(gae_launch(u.reward, u.value, u.done, u.last_val, c->adv, c->tgt, c->T, c->Nl, gamma, gl, c->sm_count, 0, stream));
     c->launches++;
   }
-  {
+  if (c->share_perm) {
+    // The permutations depend only on the key chain, so the ranks split the sorting work by epoch (rank e % W sorts
+    // epoch e) and broadcast: every rank still ends up with the same GLOBAL permutations, bit for bit.
+    PROF(PC_PERM);
+    const int W = cfg.world_size, R = cfg.rank;
+    const int mine = R < c->E ? (c->E - R + W - 1) / W : 0;
+    RET(perm_launch(u.key_in, u.key_out, cfg.prng_mode, mine, c->B, c->perm_tmp, c->perm_ws, c->perm_ws_bytes, stream, R, W, c->E));
+    NcclApi* api = nccl_api();
+    ncclResult_t r = api->GroupStart();
+    for (int e = 0; e < c->E && r == ncclSuccess; ++e) {
+      const int root = e % W;
+      int32_t* dst = c->perms + static_cast<size_t>(e) * c->B;
+      const int32_t* src = root == R ? c->perm_tmp + static_cast<size_t>(e / W) * c->B : dst;
+      r = api->Broadcast(src, dst, static_cast<size_t>(c->B), ncclInt32, root, c->comm, stream);
+    }
+    const ncclResult_t r2 = api->GroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) { set_error("ncclBroadcast (permutations) failed: %s", api->GetErrorString(r)); return MINPPO_ERR_NCCL; }
+    c->launches += (mine > 0 ? perm_launch_count(c->B) : 0) + (u.key_out ? 1 : 0);
+  } else {
     PROF(PC_PERM);
     RET(perm_launch(u.key_in, u.key_out, cfg.prng_mode, c->E, c->B, c->perms, c->perm_ws, c->perm_ws_bytes, stream));
     c->launches += perm_launch_count(c->B) + (u.key_out ? 1 : 0);
@@ -751,10 +786,14 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   c->D = cfg->obs_dim; c->Dp = (c->D + 63) / 64 * 64; c->A = cfg->act_dim;
   c->B = static_cast<long long>(c->T) * c->N; c->Bl = static_cast<long long>(c->T) * c->Nl;
   c->mb = static_cast<int>(c->B / c->M);
-  if (cfg->world_size == 1) c->cap = c->mb;
+  const int pad_emul = (cfg->world_size == 1 && getenv("MINPPO_EMULATE_SHARD_PAD")) ? atoi(getenv("MINPPO_EMULATE_SHARD_PAD")) : 0;
+  c->padded = cfg->world_size > 1 || pad_emul > 1;
+  if (!c->padded) c->cap = c->mb;
   else {
     long long cap = (3LL * c->mb / cfg->world_size + 1) / 2 + 256;    // 1.5 x mean + 256 rows
-    if (cap > c->mb) cap = c->mb;
+    if (pad_emul == 3) cap = c->mb + 128;                             // probe: one spare tile only
+    else if (pad_emul > 1) cap = c->mb + c->mb / 2 + 256;                  // what a rank of a pad_emul-way job with this many rows would get
+    if (cap > c->mb && pad_emul <= 1) cap = c->mb;
     if (cap > c->Bl) cap = c->Bl;
     c->cap = static_cast<int>(cap);
   }
@@ -770,7 +809,17 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     int per_split = 0;
     for (int l = 0; l < c->L; ++l) per_split += 2 * (((l == 0 ? c->Dp : c->H) + 127) / 128);
     int S = cfg->dw_splits > 0 ? cfg->dw_splits : (c->sm_count / (per_split > 0 ? per_split : 1));
-    const int kb_total = c->M_pad / 64;
+    if (getenv("MINPPO_DW_SPLITS")) S = atoi(getenv("MINPPO_DW_SPLITS"));           // development probe
+    // k-blocks (64 minibatch rows each) the splits share.  Padded row lists (env-sharded ranks): size the split for the
+    // rows a minibatch is EXPECTED to have on this rank (mean + 3 sigma of the hypergeometric count), not for the
+    // worst-case capacity -- the kernel splits the live k-blocks at run time, an over-sized S only removes spare CTAs.
+    int kb_total = c->M_pad / 64;
+    if (c->padded) {
+      const double mean = pad_emul > 1 ? c->mb : static_cast<double>(c->mb) / cfg->world_size;
+      const long long rows = static_cast<long long>(mean + 3.0 * sqrt(mean)) + 1;
+      kb_total = static_cast<int>(std::min<long long>(c->M_pad, rows + 63) / 64);
+      if (kb_total < 1) kb_total = 1;
+    }
     if (S > kb_total) S = kb_total;
     if (S > 32) S = 32;
     if (S < 1) S = 1;
@@ -810,6 +859,8 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     const int np = static_cast<int>((c->P + 2 + 3) / 4 * 4);
     const size_t floats = 2 * static_cast<size_t>(cfg->world_size) * np + static_cast<size_t>(cfg->world_size) * 256;
     ALLOC(c->xchg, floats);
+    // staging words start as the "not yet written" sentinel -0.0f of the Lamport-style exchange (dwopt.cuh)
+    fill_u32_kernel<<<296, 256>>>(reinterpret_cast<uint32_t*>(c->xchg), 2 * static_cast<size_t>(cfg->world_size) * np, 0x80000000u);
     ALLOC(c->xseq, 1);
     c->px.np = np; c->px.world = 0; c->px.rank = cfg->rank; c->px.seq = c->xseq;
   }
@@ -825,6 +876,9 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   c->merged_opt = !(getenv("MINPPO_SPLIT_OPT") && atoi(getenv("MINPPO_SPLIT_OPT")) != 0);
   c->skip_mask = getenv("MINPPO_SKIP") ? atoi(getenv("MINPPO_SKIP")) : 0;
   ALLOC(c->perms, static_cast<size_t>(c->E) * c->B);
+  c->perm_tmp = nullptr;
+  c->share_perm = cfg->world_size > 1 && !(getenv("MINPPO_SHARE_PERM") && atoi(getenv("MINPPO_SHARE_PERM")) == 0);
+  if (c->share_perm) ALLOC(c->perm_tmp, static_cast<size_t>((c->E + cfg->world_size - 1) / cfg->world_size) * c->B);
   ALLOC(c->rowidx, static_cast<size_t>(EM) * c->cap);
   ALLOC(c->counts, static_cast<size_t>(EM));
   c->perm_ws_bytes = perm_workspace_bytes(c->E, c->B);

@@ -20,8 +20,11 @@ int gae_launch(const float* reward, const float* value, const uint8_t* done, con
 
 // ---- prng_sort.cu ------------------------------------------------------------------------
 size_t perm_workspace_bytes(int epochs, long long B);
+// Sorts `epochs` permutations: perm_out[j] = permutation of epoch epoch_first + j * epoch_step of the update's key chain;
+// key_out = the key after key_epochs splits (-1: epochs).
 int perm_launch(const uint32_t* key_in_dev, uint32_t* key_out_dev, int mode, int epochs, long long B,
-                int32_t* perm_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+                int32_t* perm_out, void* ws, size_t ws_bytes, cudaStream_t stream, int epoch_first = 0,
+                int epoch_step = 1, int key_epochs = -1);
 int perm_launch_count(long long B);
 
 // ---- minibatch.cu ------------------------------------------------------------------------

@@ -57,6 +57,7 @@ constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 2048
 struct SortArgs {
   const uint32_t* key_in_dev;   // update input key [2]
   int mode, round;
+  int epoch_first, epoch_step;  // blockIdx.y = j sorts epoch epoch_first + j * epoch_step of the update's key chain
   uint32_t n;
   const uint32_t* keys_in;      // [E][n] (pass > 0)
   uint32_t* keys_out;           // [E][n]
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(SortArgs a) {
   uint32_t sub[2] = {0, 0};
   if (!a.keys_in) {
     uint32_t kin[2] = {a.key_in_dev[0], a.key_in_dev[1]};
-    round_subkey(kin, a.mode, epoch, a.round, sub);
+    round_subkey(kin, a.mode, a.epoch_first + epoch * a.epoch_step, a.round, sub);
   }
   uint32_t key[RS_ITEMS], rank[RS_ITEMS];
   bool valid[RS_ITEMS];
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(SortArgs a) {
   uint32_t sub[2] = {0, 0};
   if (!a.keys_in) {
     uint32_t kin[2] = {a.key_in_dev[0], a.key_in_dev[1]};
-    round_subkey(kin, a.mode, epoch, a.round, sub);
+    round_subkey(kin, a.mode, a.epoch_first + epoch * a.epoch_step, a.round, sub);
   }
   uint32_t key[RS_ITEMS], rank[RS_ITEMS];
   int32_t val[RS_ITEMS];
@@ -234,9 +235,16 @@ size_t perm_workspace_bytes(int epochs, long long B) {
 }
 
 // perm_out: int32 [E][B].  ws as sized above.  key_out (device, [2]) receives the key after E splits.
+// Sorted epochs: epoch_first + j * epoch_step, j = 0 .. epochs-1 (perm_out[j]); key_out always advances `key_epochs` splits.
 int perm_launch(const uint32_t* key_in_dev, uint32_t* key_out_dev, int mode, int epochs, long long B,
-                int32_t* perm_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  if (B <= 0 || B > 0x7fffffffLL || epochs <= 0) return MINPPO_ERR_ARG;
+                int32_t* perm_out, void* ws, size_t ws_bytes, cudaStream_t stream, int epoch_first, int epoch_step,
+                int key_epochs) {
+  if (key_epochs < 0) key_epochs = epochs;
+  if (epochs == 0) {
+    if (key_out_dev) key_advance_kernel<<<1, 32, 0, stream>>>(key_in_dev, key_out_dev, mode, key_epochs);
+    return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
+  }
+  if (B <= 0 || B > 0x7fffffffLL || epochs < 0) return MINPPO_ERR_ARG;
   if (ws_bytes < perm_workspace_bytes(epochs, B)) return MINPPO_ERR_WORKSPACE;
   const size_t n = static_cast<size_t>(B), E = static_cast<size_t>(epochs);
   const int tiles = static_cast<int>((n + RS_TILE - 1) / RS_TILE);
@@ -259,6 +267,7 @@ int perm_launch(const uint32_t* key_in_dev, uint32_t* key_out_dev, int mode, int
       a.key_in_dev = key_in_dev;
       a.mode = mode;
       a.round = r;
+      a.epoch_first = epoch_first; a.epoch_step = epoch_step;
       a.n = static_cast<uint32_t>(n);
       a.keys_in = pass == 0 ? nullptr : ((pass & 1) ? k0 : k1);
       a.keys_out = (pass & 1) ? k1 : k0;
@@ -274,7 +283,7 @@ int perm_launch(const uint32_t* key_in_dev, uint32_t* key_out_dev, int mode, int
       rs_scatter_kernel<<<grid, RS_THREADS, 0, stream>>>(a);
     }
   }
-  if (key_out_dev) key_advance_kernel<<<1, 32, 0, stream>>>(key_in_dev, key_out_dev, mode, epochs);
+  if (key_out_dev) key_advance_kernel<<<1, 32, 0, stream>>>(key_in_dev, key_out_dev, mode, key_epochs);
   return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }
 

@@ -5,7 +5,8 @@ reproduce the single-process oracle update on the same global batch and the same
 
 What this pins: the row-ownership rule (flat = t*N + n; rank owns envs [r*N/G, (r+1)*N/G)), local
 flat index t*Nl + (n - n0), two-pass global advantage statistics, sums (not means) being reduced,
--ent_coef added once, and that params stay identical on all ranks with no broadcast."""
+-ent_coef added once, that params stay identical on all ranks with no broadcast, and that sorting each epoch's
+permutation on one rank (e % world) and broadcasting it reproduces the single-process permutations."""
 import os
 import socket
 
@@ -46,11 +47,16 @@ def sharded_update(rank: int, world: int, pr, hp: P.Hyper):
         dist.all_reduce(t)
         return t.numpy()
 
-    # every rank computes the GLOBAL permutations redundantly from the same key
+    # The GLOBAL permutations depend only on the key chain: rank e % world sorts epoch e and broadcasts it
+    # (learner.cu enqueue_update, share_perm), so every rank holds all of them without sorting all of them.
     perms = []
     for e in range(E):
         rng, sub = threefry.split(rng, 2, hp.prng_mode)
-        perms.append(threefry.permutation(sub, hp.batch_size, hp.prng_mode))
+        mine = e % world == rank
+        pt = torch.from_numpy(threefry.permutation(sub, hp.batch_size, hp.prng_mode).astype(np.int64)) if mine \
+            else torch.zeros(hp.batch_size, dtype=torch.int64)
+        dist.broadcast(pt, src=e % world)
+        perms.append(pt.numpy())
     rows = [[shard_rows(perms[e][k * mbs:(k + 1) * mbs], N, n0, Nl) for k in range(M)] for e in range(E)]
     # advantage statistics of all E*M minibatches up front: sum, then centred second moment
     sums = allreduce(np.array([[flat["adv"][rows[e][k]].sum() for k in range(M)] for e in range(E)]))
