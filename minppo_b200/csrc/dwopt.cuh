@@ -38,16 +38,23 @@ constexpr int DWOPT_THREADS = 512;
 //                          elements and the two loss sums (dwopt job numbering).  The element -> (CTA, thread)
 //                          mapping is the same on every rank: a thread only ever waits for its own unit.
 //   flags [W][256] u32     unused by this protocol (kept for layout compatibility).
+//   result [2][np] f32     two-phase variant: the reduced gradient of exchange n, pushed by the owners of its units.
 struct PeerXchg {
   char* base[MINPPO_MAX_RANKS];  // rank r's allocation as mapped on THIS device
   unsigned int* seq;             // local exchange counter (device memory): exchanges completed so far
   int world, rank;
   int np;                        // floats per staging slot (multiple of 4)
+  int two_phase;                 // 0: one-shot push to every rank; 1: reduce at rank (CTA index % W), result pushed back
   int ablate;                    // debug (MINPPO_PX_ABLATE, TIMING ONLY, wrong results): 1 = push but never wait for the
                                  // peers, 2 = neither push nor wait
 };
 MINPPO_DEVINL float* px_stage(const PeerXchg& x, int r, unsigned int par, int q) {
   return reinterpret_cast<float*>(x.base[r]) + (static_cast<size_t>(par) * x.world + q) * x.np;
+}
+// result slots of the two-phase exchange: [2][np] f32 behind the flags
+MINPPO_DEVINL float* px_result(const PeerXchg& x, int r, unsigned int par) {
+  return reinterpret_cast<float*>(x.base[r]) + 2 * static_cast<size_t>(x.world) * x.np + static_cast<size_t>(x.world) * 256 +
+         static_cast<size_t>(par) * x.np;
 }
 MINPPO_DEVINL unsigned int* px_flags(const PeerXchg& x, int r) {
   return reinterpret_cast<unsigned int*>(reinterpret_cast<float*>(x.base[r]) + 2 * static_cast<size_t>(x.world) * x.np);
@@ -297,66 +304,108 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     // Slot reuse (parity of n) is safe without a fence: a peer can only push exchange n + 2 after it has completed
     // n + 1, which needed this rank's pushes of n + 1, which were issued by a later launch than this one's clears.
     constexpr unsigned int SENT = 0x80000000u;
-    g4.x = g4.x == 0.f ? 0.f : g4.x; g4.y = g4.y == 0.f ? 0.f : g4.y;
-    g4.z = g4.z == 0.f ? 0.f : g4.z; g4.w = g4.w == 0.f ? 0.f : g4.w;
-    if (ul >= 0) {
-#pragma unroll
-      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_v4(px_stage(X, r, par, R) + 4 * unit, g4);
-    }
+    auto canon = [](float x) { return x == 0.f ? 0.f : x; };
+    auto is_real4 = [](const float4& v) {
+      return __float_as_uint(v.x) != SENT && __float_as_uint(v.y) != SENT && __float_as_uint(v.z) != SENT && __float_as_uint(v.w) != SENT;
+    };
+    const float4 sent4 = make_float4(-0.f, -0.f, -0.f, -0.f);
+    g4.x = canon(g4.x); g4.y = canon(g4.y); g4.z = canon(g4.z); g4.w = canon(g4.w);
     float gl = 0.f;
-    if (eidx >= 0) {
-      gl = __ldcg(a.gflat + eidx);
-      gl = gl == 0.f ? 0.f : gl;
+    if (eidx >= 0) gl = canon(__ldcg(a.gflat + eidx));
+    // TWO-PHASE (X.two_phase, used for W >= 4): the units of CTA b are reduced by rank b % W only.  A non-owner pushes its
+    // unit to the owner (one store instead of W - 1) and polls the result slot; the owner polls the W - 1 contributions,
+    // sums in rank order and pushes the result to everybody.  Two NVLink latencies instead of one, but (W - 1) / W of a
+    // gradient sent and received per rank instead of W - 1 gradients -- and the same sums, bit for bit, as ONE-SHOT.
+    const bool two = X.two_phase != 0;
+    const int owner = two ? b % W : R;
+    const bool reduce_here = owner == R;
+    if (ul >= 0) {
+      if (reduce_here) {
+        if (!two) {
 #pragma unroll
-      for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_f32(px_stage(X, r, par, R) + n_late4 + gtid, gl);
+          for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_v4(px_stage(X, r, par, R) + 4 * unit, g4);
+        }
+      } else {
+        st_sys_v4(px_stage(X, owner, par, R) + 4 * unit, g4);
+      }
+    }
+    if (eidx >= 0) {
+      if (reduce_here) {
+        if (!two) {
+#pragma unroll
+          for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_f32(px_stage(X, r, par, R) + n_late4 + gtid, gl);
+        }
+      } else {
+        st_sys_f32(px_stage(X, owner, par, R) + n_late4 + gtid, gl);
+      }
     }
     DW_STAMP(13);
     ss = 0.f;
     const long long t0 = clock64();
     if (ul >= 0) {
-      float4 v[MINPPO_MAX_RANKS];
-      unsigned int pending = X.ablate ? 0u : ((1u << W) - 1u) & ~(1u << R);
+      if (reduce_here) {
+        float4 v[MINPPO_MAX_RANKS];
+        unsigned int pending = X.ablate ? 0u : ((1u << W) - 1u) & ~(1u << R);
 #pragma unroll
-      for (int q = 0; q < MINPPO_MAX_RANKS; ++q) v[q] = g4;
-      while (pending) {
+        for (int q = 0; q < MINPPO_MAX_RANKS; ++q) v[q] = g4;
+        while (pending) {
+#pragma unroll
+          for (int q = 0; q < MINPPO_MAX_RANKS; ++q) {
+            if ((pending >> q) & 1u) {
+              v[q] = ld_sys_v4(px_stage(X, R, par, q) + 4 * unit);
+              if (is_real4(v[q])) pending &= ~(1u << q);
+            }
+          }
+          if (pending && clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
+        }
+        const float4 own = g4;
+        g4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < MINPPO_MAX_RANKS; ++q) {
-          if ((pending >> q) & 1u) {
-            v[q] = ld_sys_v4(px_stage(X, R, par, q) + 4 * unit);
-            if (__float_as_uint(v[q].x) != SENT && __float_as_uint(v[q].y) != SENT && __float_as_uint(v[q].z) != SENT &&
-                __float_as_uint(v[q].w) != SENT)
-              pending &= ~(1u << q);
+          if (q < W) {
+            const float4 c = q == R ? own : v[q];
+            g4.x += c.x; g4.y += c.y; g4.z += c.z; g4.w += c.w;
+            if (q != R) st_sys_v4(px_stage(X, R, par, q) + 4 * unit, sent4);
           }
         }
-        if (pending && clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
-      }
-      const float4 own = g4;
-      g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (two) {
+          const float4 res = make_float4(canon(g4.x), canon(g4.y), canon(g4.z), canon(g4.w));
 #pragma unroll
-      for (int q = 0; q < MINPPO_MAX_RANKS; ++q) {
-        if (q < W) {
-          const float4 c = q == R ? own : v[q];
-          g4.x += c.x; g4.y += c.y; g4.z += c.z; g4.w += c.w;
-          if (q != R) st_sys_v4(px_stage(X, R, par, q) + 4 * unit, make_float4(-0.f, -0.f, -0.f, -0.f));
+          for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_v4(px_result(X, r, par) + 4 * unit, res);
         }
+      } else {
+        float* src = px_result(X, R, par) + 4 * unit;
+        float4 v = g4;
+        while (!X.ablate) {
+          v = ld_sys_v4(src);
+          if (is_real4(v)) break;
+          if (clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
+        }
+        g4 = v;
+        st_sys_v4(src, sent4);
       }
       if (a.keep_gflat) { float* dst = a.gflat + ui; dst[0] = g4.x; dst[1] = g4.y; dst[2] = g4.z; dst[3] = g4.w; }
       ss = fmaf(g4.x, g4.x, ss); ss = fmaf(g4.y, g4.y, ss); ss = fmaf(g4.z, g4.z, ss); ss = fmaf(g4.w, g4.w, ss);
     }
     if (eidx >= 0) {
       float ge = 0.f;
-      for (int q = 0; q < W; ++q) {
-        float c = gl;
-        if (q != R) {
-          float* src = px_stage(X, R, par, q) + n_late4 + gtid;
-          unsigned int w;
-          while ((w = ld_relaxed_sys_u32(reinterpret_cast<const unsigned int*>(src))) == SENT && !X.ablate) {
-            if (clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
-          }
-          c = __uint_as_float(w);
-          st_sys_f32(src, -0.f);
+      auto poll1 = [&](float* src, float fallback) {
+        unsigned int w = __float_as_uint(fallback);
+        while (!X.ablate && (w = ld_relaxed_sys_u32(reinterpret_cast<const unsigned int*>(src))) == SENT) {
+          if (clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
         }
-        ge += c;
+        st_sys_f32(src, -0.f);
+        return __uint_as_float(w);
+      };
+      if (reduce_here) {
+        for (int q = 0; q < W; ++q) ge += q == R ? gl : poll1(px_stage(X, R, par, q) + n_late4 + gtid, gl);
+        if (two) {
+          const float res = canon(ge);
+#pragma unroll
+          for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_f32(px_result(X, r, par) + n_late4 + gtid, res);
+        }
+      } else {
+        ge = poll1(px_result(X, R, par) + n_late4 + gtid, gl);
       }
       a.gflat[eidx] = ge;                                // read back by this same thread (small leaves) / after the barrier (losses)
       if (eidx < P) ss = fmaf(ge, ge, ss);

@@ -857,10 +857,10 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     // the local gradient buffer lives inside the exchange allocation so that peers can read it (own cudaMalloc:
     // CUDA IPC exports whole allocations)
     const int np = static_cast<int>((c->P + 2 + 3) / 4 * 4);
-    const size_t floats = 2 * static_cast<size_t>(cfg->world_size) * np + static_cast<size_t>(cfg->world_size) * 256;
+    const size_t floats = 2 * static_cast<size_t>(cfg->world_size) * np + static_cast<size_t>(cfg->world_size) * 256 + 2 * static_cast<size_t>(np);
     ALLOC(c->xchg, floats);
-    // staging words start as the "not yet written" sentinel -0.0f of the Lamport-style exchange (dwopt.cuh)
-    fill_u32_kernel<<<296, 256>>>(reinterpret_cast<uint32_t*>(c->xchg), 2 * static_cast<size_t>(cfg->world_size) * np, 0x80000000u);
+    // staging / result words start as the "not yet written" sentinel -0.0f of the Lamport-style exchange (dwopt.cuh)
+    fill_u32_kernel<<<296, 256>>>(reinterpret_cast<uint32_t*>(c->xchg), floats, 0x80000000u);
     ALLOC(c->xseq, 1);
     c->px.np = np; c->px.world = 0; c->px.rank = cfg->rank; c->px.seq = c->xseq;
   }
@@ -1064,6 +1064,9 @@ int minppo_ctx_set_peers(minppo_ctx* c, const void* handles_host) {
     c->px.base[r] = static_cast<char*>(ptr);
   }
   c->px.world = W;
+  // one-shot push for small worlds (one NVLink latency), reduce-at-owner + result push for W >= 4 (2 (W-1)/W of a
+  // gradient per rank on the links instead of W - 1 gradients); MINPPO_PX_TWO_PHASE=0/1 forces either
+  c->px.two_phase = getenv("MINPPO_PX_TWO_PHASE") ? (atoi(getenv("MINPPO_PX_TWO_PHASE")) != 0) : (W >= 4);
   c->peers_set = true;
   if (c->have_graph) { cudaGraphExecDestroy(c->graph_exec); cudaGraphDestroy(c->graph); c->have_graph = false; }
   return 0;

@@ -17,46 +17,59 @@ namespace minppo {
 
 constexpr int MB_THREADS = 256;
 
-// one block per minibatch; ordered stream compaction in strips of MB_THREADS
-__global__ void __launch_bounds__(MB_THREADS) compact_rows_kernel(const int32_t* __restrict__ perms,
+// one block per minibatch; ordered stream compaction in strips of CR_THREADS x CR_ITEMS consecutive entries (one
+// __syncthreads per strip: the warp totals are double-buffered).  The GLOBAL minibatch grows with the number of ranks
+// (weak scaling: 65,536 entries per minibatch at 8 GPUs), so this scan is sized for that, not for one rank's rows.
+constexpr int CR_THREADS = 1024;
+constexpr int CR_ITEMS = 4;
+__global__ void __launch_bounds__(CR_THREADS) compact_rows_kernel(const int32_t* __restrict__ perms,
                                                                   int32_t* __restrict__ rowidx,
                                                                   int32_t* __restrict__ counts, int M, long long B,
                                                                   int mb, int cap, int N, int n0, int Nl) {
-  __shared__ int warp_tot[MB_THREADS / 32];
-  __shared__ int base_s;
+  __shared__ int warp_tot[2][CR_THREADS / 32];
   const int s = blockIdx.x;                       // e * M + k
   const int e = s / M, k = s % M;
   const int32_t* src = perms + static_cast<size_t>(e) * B + static_cast<size_t>(k) * mb;
   int32_t* dst = rowidx + static_cast<size_t>(s) * cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base_s = 0;
-  __syncthreads();
-  for (int i0 = 0; i0 < mb; i0 += MB_THREADS) {
-    const int i = i0 + threadIdx.x;
-    int local = -1;
-    if (i < mb) {
-      const int flat = src[i];
-      const int t = flat / N, n = flat - t * N;
-      if (n >= n0 && n < n0 + Nl) local = t * Nl + (n - n0);
+  int base = 0;                                   // rows kept so far (identical in every thread)
+  for (int i0 = 0, it = 0; i0 < mb; i0 += CR_THREADS * CR_ITEMS, ++it) {
+    int loc[CR_ITEMS];
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < CR_ITEMS; ++j) {
+      const int i = i0 + static_cast<int>(threadIdx.x) * CR_ITEMS + j;
+      loc[j] = -1;
+      if (i < mb) {
+        const int flat = src[i];
+        const int t = flat / N, n = flat - t * N;
+        if (n >= n0 && n < n0 + Nl) { loc[j] = t * Nl + (n - n0); ++c; }
+      }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, local >= 0);
-    if (lane == 0) warp_tot[warp] = __popc(m);
-    __syncthreads();
-    int off = base_s;
-    for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    const int pos = off + __popc(m & ((1u << lane) - 1u));
-    if (local >= 0 && pos < cap) dst[pos] = local;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int w = 0; w < MB_THREADS / 32; ++w) tot += warp_tot[w];
-      base_s += tot;
+    int inc = c;                                  // inclusive scan of the per-thread counts over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
     }
+    if (lane == 31) warp_tot[it & 1][warp] = inc;
     __syncthreads();
+    const int wv = warp_tot[it & 1][lane];        // CR_THREADS / 32 == 32 warp totals, one per lane
+    const int before = __reduce_add_sync(0xffffffffu, lane < warp ? wv : 0);
+    const int total = __reduce_add_sync(0xffffffffu, wv);
+    int pos = base + before + inc - c;
+#pragma unroll
+    for (int j = 0; j < CR_ITEMS; ++j) {
+      if (loc[j] >= 0) {
+        if (pos < cap) dst[pos] = loc[j];
+        ++pos;
+      }
+    }
+    base += total;
   }
-  const int count = base_s;
+  const int count = base;
   if (threadIdx.x == 0) counts[s] = count;          // > cap is reported by the host-visible check
-  for (int j = min(count, cap) + threadIdx.x; j < cap; j += MB_THREADS) dst[j] = 0;
+  for (int j = min(count, cap) + static_cast<int>(threadIdx.x); j < cap; j += CR_THREADS) dst[j] = 0;
 }
 
 // pass 0: stats[s] = sum adv ; pass 1: stats[EM+s] = sum (adv - stats[s]/mb)^2   (owned rows)
@@ -87,7 +100,7 @@ __global__ void __launch_bounds__(MB_THREADS) adv_stats_kernel(const float* __re
 
 int compact_rows_launch(const int32_t* perms, int32_t* rowidx, int32_t* counts, int E, int M, long long B, int mb,
                         int cap, int N, int n0, int Nl, cudaStream_t stream) {
-  compact_rows_kernel<<<E * M, MB_THREADS, 0, stream>>>(perms, rowidx, counts, M, B, mb, cap, N, n0, Nl);
+  compact_rows_kernel<<<E * M, CR_THREADS, 0, stream>>>(perms, rowidx, counts, M, B, mb, cap, N, n0, Nl);
   return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }
 
