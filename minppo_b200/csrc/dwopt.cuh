@@ -398,7 +398,28 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
         return __uint_as_float(w);
       };
       if (reduce_here) {
-        for (int q = 0; q < W; ++q) ge += q == R ? gl : poll1(px_stage(X, R, par, q) + n_late4 + gtid, gl);
+        // all W - 1 contributions polled together (one L2 round trip per sweep, not one per rank)
+        float ev[MINPPO_MAX_RANKS];
+        unsigned int pending = X.ablate ? 0u : ((1u << W) - 1u) & ~(1u << R);
+#pragma unroll
+        for (int q = 0; q < MINPPO_MAX_RANKS; ++q) ev[q] = gl;
+        while (pending) {
+#pragma unroll
+          for (int q = 0; q < MINPPO_MAX_RANKS; ++q) {
+            if ((pending >> q) & 1u) {
+              const unsigned int w = ld_relaxed_sys_u32(reinterpret_cast<const unsigned int*>(px_stage(X, R, par, q) + n_late4 + gtid));
+              if (w != SENT) { ev[q] = __uint_as_float(w); pending &= ~(1u << q); }
+            }
+          }
+          if (pending && clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
+        }
+#pragma unroll
+        for (int q = 0; q < MINPPO_MAX_RANKS; ++q) {
+          if (q < W) {
+            ge += ev[q];
+            if (q != R) st_sys_f32(px_stage(X, R, par, q) + n_late4 + gtid, -0.f);
+          }
+        }
         if (two) {
           const float res = canon(ge);
 #pragma unroll

@@ -107,16 +107,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(SortArgs a) {
     uint32_t kin[2] = {a.key_in_dev[0], a.key_in_dev[1]};
     round_subkey(kin, a.mode, a.epoch_first + epoch * a.epoch_step, a.round, sub);
   }
-  uint32_t key[RS_ITEMS], rank[RS_ITEMS];
-  bool valid[RS_ITEMS];
+  // counts only (the ranks are the scatter kernel's business): per-warp shared-memory atomics
   const uint32_t base = static_cast<uint32_t>(tile) * RS_TILE + warp * (32 * RS_ITEMS) + lane_id();
 #pragma unroll
   for (int s = 0; s < RS_ITEMS; ++s) {
     const uint32_t i = base + s * 32;
-    valid[s] = i < a.n;
-    key[s] = valid[s] ? rs_load_key(a, epoch, i, sub) : 0u;
+    if (i < a.n) atomicAdd(&wc[warp][(rs_load_key(a, epoch, i, sub) >> a.shift) & 0xFFu], 1u);
   }
-  rs_rank(key, valid, a.shift, wc[warp], rank);
   __syncthreads();
   for (int d = threadIdx.x; d < 256; d += RS_THREADS) {
     uint32_t c = 0;
@@ -205,9 +202,36 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(SortArgs a) {
     dscan[threadIdx.x] = wbase + inc - tot;
   }
   __syncthreads();
-  // per digit: exclusive prefix over warps, plus the digit's and the tile's global base
-  for (int d = threadIdx.x; d < 256; d += RS_THREADS) {
-    uint32_t run = dscan[d] + a.hist[(static_cast<size_t>(epoch) * 256 + d) * a.tiles + tile];
+  // per digit d (thread d): tbase[d] = elements of this tile with a smaller digit (exclusive scan over digits of the
+  // tile's counts), gdst[d] = where the tile's run of digit d starts in the output; wc[w][d] becomes the LOCAL start of
+  // warp w's elements of digit d.  Elements are first placed in shared memory in (digit, original order) order --
+  // which is exactly their order in the output -- and then written out by consecutive threads: the elements of one
+  // digit go to consecutive addresses instead of one 4-byte store per 32-byte sector.
+  __shared__ uint32_t tbase[256];
+  __shared__ uint32_t gdst[256];
+  __shared__ uint32_t skey[RS_TILE];
+  __shared__ int32_t sval[RS_TILE];
+  {
+    const int d = threadIdx.x;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) cnt += wc[w][d];
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane_id() >= static_cast<uint32_t>(o)) inc += v;
+    }
+    __syncthreads();                                   // dws is reused (the digit-total scan above has been consumed)
+    if (lane_id() == 31) dws[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) if (w < warp) wbase += dws[w];
+    const uint32_t excl = wbase + inc - cnt;
+    tbase[d] = excl;
+    gdst[d] = dscan[d] + a.hist[(static_cast<size_t>(epoch) * 256 + d) * a.tiles + tile];
+    uint32_t run = excl;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
       const uint32_t c = wc[w][d];
@@ -220,10 +244,19 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(SortArgs a) {
   for (int s = 0; s < RS_ITEMS; ++s) {
     if (valid[s]) {
       const uint32_t d = (key[s] >> a.shift) & 0xFFu;
-      const size_t pos = static_cast<size_t>(epoch) * a.n + wc[warp][d] + rank[s];
-      a.keys_out[pos] = key[s];
-      a.vals_out[pos] = val[s];
+      const uint32_t lp = wc[warp][d] + rank[s];
+      skey[lp] = key[s];
+      sval[lp] = val[s];
     }
+  }
+  __syncthreads();
+  const uint32_t tile_n = min(static_cast<uint32_t>(RS_TILE), a.n - static_cast<uint32_t>(tile) * RS_TILE);
+  for (uint32_t i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+    const uint32_t k = skey[i];
+    const uint32_t d = (k >> a.shift) & 0xFFu;
+    const size_t pos = static_cast<size_t>(epoch) * a.n + gdst[d] + (i - tbase[d]);
+    a.keys_out[pos] = k;
+    a.vals_out[pos] = sval[i];
   }
 }
 
