@@ -443,6 +443,25 @@ def run_ours(args):
                     "peak_source": peak_src}
         del r_, v_, d_, lv_, gm
 
+        # ---- the rollout's policy step (minppo_policy_step, train.py:157-160) on this config's env count ---------
+        pol = None
+        try:
+            pobs = torch.randn(hp.num_envs // world, OBS_DIM, device=dev)
+            for _ in range(5):
+                learner.policy_step(ts.params, pobs, rng, weights_current=True)
+            torch.cuda.synchronize(dev)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(50):
+                learner.policy_step(ts.params, pobs, rng, weights_current=True)
+            p1.record()
+            torch.cuda.synchronize(dev)
+            pol = {"us_per_env_step": p0.elapsed_time(p1) / 50 * 1e3, "envs": hp.num_envs // world,
+                   "note": "eager launches incl. the host call path (obs image + L GEMM launches + head/sampler kernel), "
+                           "weights current"}
+        except Exception as e:  # a measurement extra must never lose the bench line
+            pol = {"error": str(e)[:200]}
+
         # ---- CPU baseline beside it (N == 1 only) ---------------------------------------------------
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -464,7 +483,7 @@ def run_ours(args):
                     "ms_per_step": float(et.item()) * 1e3},
             "gpu_launches": learner.launches_per_update() * args.steps,
             "launches_per_update": learner.launches_per_update(),
-            "roofline": roofline, "gae_roofline": gae_roof, "kernel_classes": prof,
+            "roofline": roofline, "gae_roofline": gae_roof, "kernel_classes": prof, "policy_step": pol,
             "final_loss": [float(x) for x in final_losses[-1, -1]],
         }
         if cpu is not None:
