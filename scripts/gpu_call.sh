@@ -9,7 +9,7 @@ has() { [[ " $WHAT " == *" $1 "* ]]; }
 nvidia-smi > gpurun_out/nvidia_smi.txt 2>&1
 nproc > gpurun_out/nproc.txt
 if has tests; then
-  for f in gae perm gemm update; do
+  for f in gae perm gemm update policy; do
     timeout 900 python -m pytest tests/test_gpu_$f.py -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/pytest_$f.log 2>&1
     echo "exit $?" >> gpurun_out/pytest_$f.log
   done

@@ -9,7 +9,7 @@ for m in 0 1 2 3; do
   timeout 120 python scripts/gemm_probe.py $m > gpurun_out/gemm_probe_$m.log 2>&1
   echo "exit $?" >> gpurun_out/gemm_probe_$m.log
 done
-for f in gae perm gemm update; do
+for f in gae perm gemm update policy; do
   timeout 900 python -m pytest tests/test_gpu_$f.py -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/pytest_$f.log 2>&1
   echo "exit $?" >> gpurun_out/pytest_$f.log
 done
