@@ -82,16 +82,20 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) opt_kernel(const OptArgs a) {
 // for the initial weight images.
 __global__ void f32_to_bf16_image_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                          long long rows, int cols, int ld) {
-  const long long pairs_per_row = ld / 2;
-  const long long total = rows * pairs_per_row;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / pairs_per_row;
-    const int c = static_cast<int>(i % pairs_per_row) * 2;
+  // one warp per row, lanes along the row: coalesced 256-byte loads / 128-byte stores, no index division
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int pairs = ld >> 1;
+  for (long long r = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; r < rows; r += nwarps) {
     const float* s = src + r * cols;
-    const float x0 = c < cols ? s[c] : 0.f;
-    const float x1 = c + 1 < cols ? s[c + 1] : 0.f;
-    reinterpret_cast<uint32_t*>(dst)[i] = pack_bf16x2(x0, x1);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + r * ld);
+#pragma unroll 4
+    for (int p = lane; p < pairs; p += 32) {
+      const int c = 2 * p;
+      const float x0 = c < cols ? __ldcs(s + c) : 0.f;          // the fp32 trajectory is read once per update
+      const float x1 = c + 1 < cols ? __ldcs(s + c + 1) : 0.f;
+      d[p] = pack_bf16x2(x0, x1);
+    }
   }
 }
 
@@ -118,8 +122,7 @@ int weight_images_launch(const OptArgs& a, cudaStream_t stream) {
 }
 
 int obs_image_launch(const float* obs, __nv_bfloat16* img, long long rows, int cols, int ld, cudaStream_t stream) {
-  const long long total = rows * (ld / 2);
-  long long blocks = (total + 255) / 256;
+  long long blocks = (rows + 7) / 8;                      // 8 warps per block, one row per warp and pass
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   if (blocks < 1) blocks = 1;
   f32_to_bf16_image_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(obs, img, rows, cols, ld);

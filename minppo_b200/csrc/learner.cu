@@ -267,6 +267,8 @@ struct minppo_ctx {
   int opt_blocks;
   // graph cache
   cudaStream_t cap_stream;
+  cudaStream_t side_stream;    // fork/join branch of an update: operand staging (observation + weight images) runs beside
+  cudaEvent_t ev_fork, ev_join;  // the GAE -> permutation -> row-list chain (independent until the first minibatch step)
   cudaGraph_t graph;
   cudaGraphExec_t graph_exec;
   UpdatePtrs graph_ptrs;
@@ -625,6 +627,22 @@ static int enqueue_update(minppo_ctx* c, const UpdatePtrs& u, cudaStream_t strea
   const float gamma = static_cast<float>(cfg.gamma);
   const float gl = static_cast<float>(cfg.gamma * cfg.gae_lambda);      // python-float product, then f32 (train.py:194)
   c->prof_used = 0;
+  // Fork: the bf16 images of the observations and of the weights depend on nothing the GAE -> permutation -> row-list
+  // chain produces (and vice versa) until the first minibatch step, so they run on a side branch (captured as a
+  // parallel branch of the graph).  The permutation chain is 25+ tiny dependent launches, the observation image one
+  // bandwidth-bound pass over the trajectory: side by side they cost the longer of the two.  Eager profiling runs keep
+  // everything on one stream so that the per-class event times stay attributable.
+  const bool fork = !c->profiling && !(getenv("MINPPO_NO_FORK") && atoi(getenv("MINPPO_NO_FORK")) != 0);
+  if (fork) {
+    CK(cudaEventRecord(c->ev_fork, stream));
+    CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+    RET(obs_image_launch(u.obs, c->obs_img, c->Bl, c->D, c->Dp, c->side_stream));
+    OptArgs o;
+    fill_opt_args(c, u, &o);
+    RET(weight_images_launch(o, c->side_stream));
+    CK(cudaEventRecord(c->ev_join, c->side_stream));
+    c->launches += 2;
+  }
   {
     PROF(PC_GAE);
     RET(gae_launch(u.reward, u.value, u.done, u.last_val, c->adv, c->tgt, c->T, c->Nl, gamma, gl, c->sm_count, 0, stream));
@@ -664,18 +682,22 @@ static int enqueue_update(minppo_ctx* c, const UpdatePtrs& u, cudaStream_t strea
     if (cfg.world_size > 1) RET(nccl_allreduce(c, c->stats + EM, EM, stream));
     c->launches += 3 + (cfg.world_size > 1 ? 2 : 0);
   }
-  {
-    PROF(PC_OBS_IMAGE);
-    RET(obs_image_launch(u.obs, c->obs_img, c->Bl, c->D, c->Dp, stream));
-    c->launches++;
-  }
-  // the weight images must match the caller's params at entry (they may have been replaced)
-  {
-    OptArgs o;
-    fill_opt_args(c, u, &o);
-    PROF(PC_WEIGHT_IMAGES);
-    RET(weight_images_launch(o, stream));
-    c->launches++;
+  if (fork) {
+    CK(cudaStreamWaitEvent(stream, c->ev_join, 0));              // join
+  } else {
+    {
+      PROF(PC_OBS_IMAGE);
+      RET(obs_image_launch(u.obs, c->obs_img, c->Bl, c->D, c->Dp, stream));
+      c->launches++;
+    }
+    // the weight images must match the caller's params at entry (they may have been replaced)
+    {
+      OptArgs o;
+      fill_opt_args(c, u, &o);
+      PROF(PC_WEIGHT_IMAGES);
+      RET(weight_images_launch(o, stream));
+      c->launches++;
+    }
   }
   for (int s = 0; s < EM; ++s) RET(enqueue_step(c, u, s, stream));
   return 0;
@@ -755,6 +777,9 @@ int minppo_ctx_destroy(minppo_ctx* c) {
   if (c->have_graph) { cudaGraphExecDestroy(c->graph_exec); cudaGraphDestroy(c->graph); }
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->have_comm) nccl_api()->CommDestroy(c->comm);
   for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]);
   for (void* p : c->allocs) cudaFree(p);
@@ -768,6 +793,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   minppo_ctx* c = new minppo_ctx();
   c->cfg = *cfg;
   c->have_graph = false; c->have_comm = false; c->cap_stream = nullptr; c->launches = 0;
+  c->side_stream = nullptr; c->ev_fork = nullptr; c->ev_join = nullptr;
   c->profiling = false; c->prof_used = 0;
   int rc = 0;
   auto fail = [&](int code) { minppo_ctx_destroy(c); return code; };
@@ -939,6 +965,12 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     ncclResult_t r = api->CommInitRank(&c->comm, cfg->world_size, id, cfg->rank);
     if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", api->GetErrorString(r)); return fail(MINPPO_ERR_NCCL); }
     c->have_comm = true;
+  }
+  if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("side stream / event creation failed");
+    return fail(MINPPO_ERR_CUDA);
   }
   if (cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
