@@ -6,10 +6,11 @@ It is the file a maintainer of kscalelabs/minppo imports where JAX exists; INTEG
 shows the splice into /root/reference/minppo/train.py:185-281.  Everything that IS tested
 here goes through the same C ABI (include/minppo_b200.h) via ctypes (minppo_b200/_lib.py).
 
-Two custom calls (minppo_b200/csrc/xla_ffi_shim.cc):
+Three custom calls (minppo_b200/csrc/xla_ffi_shim.cc):
 
-* ``minppo_gae``     replaces ``_calculate_gae``                     (train.py:185-207)
-* ``minppo_update``  replaces GAE + the epoch / minibatch scans      (train.py:185-281)
+* ``minppo_gae``          replaces ``_calculate_gae``                     (train.py:185-207)
+* ``minppo_update``       replaces GAE + the epoch / minibatch scans      (train.py:185-281)
+* ``minppo_policy_step``  replaces network.apply / split / sample / log_prob of the rollout (train.py:157-160)
 
 The params pytree of the reference (checkpoint layout, train.py:86-89) is carried as ONE flat
 fp32 arena in JAX's sorted flatten order; ``ravel`` / ``unravel`` below convert at the seam
@@ -43,6 +44,7 @@ def register() -> None:
     lib = ctypes.CDLL(_SHIM)
     jax.ffi.register_ffi_target("minppo_gae", jax.ffi.pycapsule(lib.MinppoGae), platform="CUDA")
     jax.ffi.register_ffi_target("minppo_update", jax.ffi.pycapsule(lib.MinppoUpdate), platform="CUDA")
+    jax.ffi.register_ffi_target("minppo_policy_step", jax.ffi.pycapsule(lib.MinppoPolicyStep), platform="CUDA")
     _registered = True
 
 
@@ -98,3 +100,34 @@ def learner_update(flat_params, mu, nu, count, mem_batch, last_val, rng, config,
         max_grad_norm=np.float32(config.opt.max_grad_norm), gamma=np.float32(config.rl.gamma),
         gae_lambda=np.float32(config.rl.gae_lambda), clip_eps=np.float32(config.rl.clip_eps),
         ent_coef=np.float32(config.rl.ent_coef), vf_coef=np.float32(config.rl.vf_coef))
+
+
+def _static_attrs(config, prng_mode):
+    """The attribute block shared by ``minppo_update`` and ``minppo_policy_step`` (one context for both)."""
+    return dict(
+        num_minibatches=np.int32(config.training.num_minibatches), update_epochs=np.int32(config.training.update_epochs),
+        total_timesteps=np.int64(config.training.total_timesteps), anneal_lr=bool(config.training.anneal_lr),
+        hidden_size=np.int32(config.model.hidden_size), num_layers=np.int32(config.model.num_layers),
+        use_tanh=bool(config.model.use_tanh), prng_mode=np.int32(prng_mode),
+        training_lr=np.float32(config.training.lr), opt_lr=np.float32(config.opt.lr),
+        max_grad_norm=np.float32(config.opt.max_grad_norm), gamma=np.float32(config.rl.gamma),
+        gae_lambda=np.float32(config.rl.gae_lambda), clip_eps=np.float32(config.rl.clip_eps),
+        ent_coef=np.float32(config.rl.ent_coef), vf_coef=np.float32(config.rl.vf_coef))
+
+
+def policy_step(flat_params, last_obs, rng, config, act_dim: int, weights_current: bool = False,
+                prng_mode: int | None = None):
+    """Drop-in for the network evaluation of ``_env_step`` (train.py:157-160).
+
+    flat_params: f32[P]; last_obs: f32[N, D]; rng: raw uint32[2] key data.
+    Returns (action f32[N, A], log_prob f32[N], value f32[N], rng' uint32[2]) with rng' = split(rng)[0]."""
+    register()
+    if prng_mode is None:
+        prng_mode = int(bool(jax.config.jax_threefry_partitionable))
+    n = last_obs.shape[0]
+    f32 = jnp.float32
+    outs = (jax.ShapeDtypeStruct((n, act_dim), f32), jax.ShapeDtypeStruct((n,), f32), jax.ShapeDtypeStruct((n,), f32),
+            jax.ShapeDtypeStruct((2,), jnp.uint32))
+    return jax.ffi.ffi_call("minppo_policy_step", outs)(
+        flat_params, last_obs, rng, num_steps=np.int32(config.training.num_steps), act_dim=np.int32(act_dim),
+        weights_current=bool(weights_current), **_static_attrs(config, prng_mode))
