@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(CR_THREADS) compact_rows_kernel(const int32_t*
                                                                   int32_t* __restrict__ counts, int M, long long B,
                                                                   int mb, int cap, int N, int n0, int Nl) {
   __shared__ int warp_tot[2][CR_THREADS / 32];
+  griddep_wait();                                 // launched with programmatic serialization (launch_chain)
+  griddep_launch();
   const int s = blockIdx.x;                       // e * M + k
   const int e = s / M, k = s % M;
   const int32_t* src = perms + static_cast<size_t>(e) * B + static_cast<size_t>(k) * mb;
@@ -79,6 +81,10 @@ __global__ void __launch_bounds__(MB_THREADS) adv_stats_kernel(const float* __re
                                                                float* __restrict__ stats, int EM, int cap,
                                                                int mb, int pass) {
   __shared__ float wsum[MB_THREADS / 32];
+  // No early griddep_launch() here: this is the LAST kernel of the per-update chain, and the step kernels that follow
+  // read "update-static" data (row lists, statistics) before their own griddepcontrol.wait -- they may only start once
+  // this kernel (and, transitively, the whole chain) has completed.
+  griddep_wait();
   const int s = blockIdx.x;
   const int count = min(counts[s], cap);
   const int32_t* idx = rowidx + static_cast<size_t>(s) * cap;
@@ -100,13 +106,13 @@ __global__ void __launch_bounds__(MB_THREADS) adv_stats_kernel(const float* __re
 
 int compact_rows_launch(const int32_t* perms, int32_t* rowidx, int32_t* counts, int E, int M, long long B, int mb,
                         int cap, int N, int n0, int Nl, cudaStream_t stream) {
-  compact_rows_kernel<<<E * M, CR_THREADS, 0, stream>>>(perms, rowidx, counts, M, B, mb, cap, N, n0, Nl);
+  launch_chain(compact_rows_kernel, dim3(E * M), dim3(CR_THREADS), 0, stream, perms, rowidx, counts, M, B, mb, cap, N, n0, Nl);
   return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }
 
 int adv_stats_launch(const float* adv, const int32_t* rowidx, const int32_t* counts, float* stats, int EM, int cap,
                      int mb, int pass, cudaStream_t stream) {
-  adv_stats_kernel<<<EM, MB_THREADS, 0, stream>>>(adv, rowidx, counts, stats, EM, cap, mb, pass);
+  launch_chain(adv_stats_kernel, dim3(EM), dim3(MB_THREADS), 0, stream, adv, rowidx, counts, stats, EM, cap, mb, pass);
   return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }
 

@@ -144,6 +144,24 @@ inline cudaError_t launch_kernel(Kern kern, unsigned grid, unsigned block, size_
   return cudaLaunchKernelEx(&cfg, kern, arg);
 }
 
+// Variadic form for the small per-update kernels (sort passes, row lists, advantage statistics): always launched with
+// the programmatic-serialization attribute; each of them starts with griddep_wait(); griddep_launch(); so the launch
+// latency of kernel K + 1 hides behind kernel K while every read still follows K's completion.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- error plumbing (learner.cu) -----------------------------------------------------------
 void set_error(const char* fmt, ...);
 

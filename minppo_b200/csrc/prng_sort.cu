@@ -34,6 +34,8 @@ __host__ __device__ inline void round_subkey(const uint32_t key_in[2], int mode,
 
 __global__ void key_advance_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_out, int mode,
                                    int epochs) {
+  griddep_wait();
+  griddep_launch();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     uint32_t rng[2] = {key_in[0], key_in[1]}, a[2], b[2];
     for (int e = 0; e < epochs; ++e) {
@@ -101,6 +103,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(SortArgs a) {
   __shared__ uint32_t wc[RS_WARPS][256];
   const int epoch = blockIdx.y, tile = blockIdx.x, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wc[0][0])[i] = 0;
+  griddep_wait();                                   // launched with programmatic serialization (launch_chain)
+  griddep_launch();
   __syncthreads();
   uint32_t sub[2] = {0, 0};
   if (!a.keys_in) {
@@ -129,6 +133,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(SortArgs a) {
 // epoch in ONE block: 58 us per pass at B = 2^18 and linear in B, i.e. milliseconds for env-sharded global batches.
 __global__ void __launch_bounds__(RS_THREADS) rs_scan_kernel(uint32_t* hist, uint32_t* totals, int tiles) {
   __shared__ uint32_t wsum[RS_WARPS];
+  griddep_wait();
+  griddep_launch();
   const int d = blockIdx.x, epoch = blockIdx.y;
   uint32_t* h = hist + (static_cast<size_t>(epoch) * 256 + d) * tiles;
   const int per = (tiles + RS_THREADS - 1) / RS_THREADS;
@@ -164,6 +170,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(SortArgs a) {
   __shared__ uint32_t wc[RS_WARPS][256];
   const int epoch = blockIdx.y, tile = blockIdx.x, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wc[0][0])[i] = 0;
+  griddep_wait();
+  griddep_launch();
   __syncthreads();
   uint32_t sub[2] = {0, 0};
   if (!a.keys_in) {
@@ -274,7 +282,7 @@ int perm_launch(const uint32_t* key_in_dev, uint32_t* key_out_dev, int mode, int
                 int key_epochs) {
   if (key_epochs < 0) key_epochs = epochs;
   if (epochs == 0) {
-    if (key_out_dev) key_advance_kernel<<<1, 32, 0, stream>>>(key_in_dev, key_out_dev, mode, key_epochs);
+    if (key_out_dev) launch_chain(key_advance_kernel, dim3(1), dim3(32), 0, stream, key_in_dev, key_out_dev, mode, key_epochs);
     return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
   }
   if (B <= 0 || B > 0x7fffffffLL || epochs < 0) return MINPPO_ERR_ARG;
@@ -311,12 +319,12 @@ int perm_launch(const uint32_t* key_in_dev, uint32_t* key_out_dev, int mode, int
       a.totals = totals;
       a.shift = pass * 8;
       a.tiles = tiles;
-      rs_hist_kernel<<<grid, RS_THREADS, 0, stream>>>(a);
-      rs_scan_kernel<<<dim3(256, epochs), RS_THREADS, 0, stream>>>(hist, totals, tiles);
-      rs_scatter_kernel<<<grid, RS_THREADS, 0, stream>>>(a);
+      launch_chain(rs_hist_kernel, grid, dim3(RS_THREADS), 0, stream, a);
+      launch_chain(rs_scan_kernel, dim3(256, epochs), dim3(RS_THREADS), 0, stream, hist, totals, tiles);
+      launch_chain(rs_scatter_kernel, grid, dim3(RS_THREADS), 0, stream, a);
     }
   }
-  if (key_out_dev) key_advance_kernel<<<1, 32, 0, stream>>>(key_in_dev, key_out_dev, mode, key_epochs);
+  if (key_out_dev) launch_chain(key_advance_kernel, dim3(1), dim3(32), 0, stream, key_in_dev, key_out_dev, mode, key_epochs);
   return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }
 
