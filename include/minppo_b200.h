@@ -119,8 +119,11 @@ int minppo_ctx_destroy(minppo_ctx* ctx);
 
 /* ---- gradient exchange over NVLink peer memory (world_size > 1, optional) ----------------------
  * Default for sharded ranks is ncclAllReduce + a separate optimizer launch per minibatch.  With peer buffers set, the
- * all-reduce is fused INTO the weight-gradient/optimizer kernel: reduce-scatter + all-gather by direct loads / stores
- * on the peers' exchange buffers with flag synchronisation (no NCCL call, no extra launch on the per-minibatch path).
+ * all-reduce is fused INTO the weight-gradient/optimizer kernel: every rank stores its gradient sums straight into the
+ * peers' staging buffers over NVLink and polls its own (the data is its own arrival flag: a sentinel value marks
+ * "not yet written"), sums the contributions in rank order and applies the identical clip + Adam -- no NCCL call, no
+ * extra launch on the per-minibatch path, parameters bit-identical on all ranks.  One-shot (every rank to every rank)
+ * below 4 ranks, two-phase (reduce at one owner per unit, result pushed back) from 4 ranks on.
  * Every rank exports one CUDA-IPC handle (64 bytes); the host framework all-gathers them (rank order) and hands the
  * table back.  All ranks must then issue the same sequence of minppo_update calls. */
 int minppo_ctx_ipc_handle(minppo_ctx* ctx, void* handle64_host);

@@ -27,17 +27,18 @@ namespace minppo {
 // per SM: with 6 warps the dependent divide / sqrt chains of the Adam phase had nothing to hide behind)
 constexpr int DWOPT_THREADS = 512;
 
-// Gradient exchange over NVLink peer memory, ONE-SHOT, Lamport style: every rank pushes its local gradient sums into
+// Gradient exchange over NVLink peer memory, Lamport style.  ONE-SHOT variant: every rank pushes its local gradient sums into
 // a staging slot on every OTHER rank; the staging words themselves are the arrival flags (sentinel -0.0f until written),
 // so an exchange costs one NVLink one-way latency -- no release/acknowledge round and no flag round.  Every rank then
 // sums the W contributions in rank order (same values, same order: bit-identical gradients on all ranks with no
 // broadcast), resets the words it consumed to the sentinel and continues with the norm and Adam like a single GPU.
+// TWO-PHASE variant (W >= 4): see the exchange code in dwopt_kernel.
 // Exchange allocation of one rank (exported by CUDA IPC):
 //   stage [2][W][np] f32   slot (n & 1, q): rank q's local gradient of exchange n (all words start as the sentinel).
 //                          Inside a slot: the 4-element units of the late leaves (16-byte aligned), then the early
 //                          elements and the two loss sums (dwopt job numbering).  The element -> (CTA, thread)
 //                          mapping is the same on every rank: a thread only ever waits for its own unit.
-//   flags [W][256] u32     unused by this protocol (kept for layout compatibility).
+//   (pad)  [W][256] u32    unused (was: the arrival flags of the earlier release/acquire protocol).
 //   result [2][np] f32     two-phase variant: the reduced gradient of exchange n, pushed by the owners of its units.
 struct PeerXchg {
   char* base[MINPPO_MAX_RANKS];  // rank r's allocation as mapped on THIS device
@@ -56,9 +57,6 @@ MINPPO_DEVINL float* px_result(const PeerXchg& x, int r, unsigned int par) {
   return reinterpret_cast<float*>(x.base[r]) + 2 * static_cast<size_t>(x.world) * x.np + static_cast<size_t>(x.world) * 256 +
          static_cast<size_t>(par) * x.np;
 }
-MINPPO_DEVINL unsigned int* px_flags(const PeerXchg& x, int r) {
-  return reinterpret_cast<unsigned int*>(reinterpret_cast<float*>(x.base[r]) + 2 * static_cast<size_t>(x.world) * x.np);
-}
 // system-scope accesses for memory another GPU reads or writes
 MINPPO_DEVINL float4 ld_sys_v4(const float* p) {
   float4 v;
@@ -69,32 +67,11 @@ MINPPO_DEVINL void st_sys_f32(float* p, float v) { asm volatile("st.relaxed.sys.
 MINPPO_DEVINL void st_sys_v4(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-MINPPO_DEVINL void st_release_sys_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-MINPPO_DEVINL unsigned int ld_acquire_sys_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 MINPPO_DEVINL unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// threads [0, world) wait until flags[t * stride] >= n (bounded), then the CTA proceeds
-MINPPO_DEVINL void px_wait_flags(const unsigned int* flags, int stride, int world, unsigned int n, int* err_flag) {
-  if (static_cast<int>(threadIdx.x) < world) {
-    const unsigned int* f = flags + static_cast<size_t>(threadIdx.x) * stride;
-    const long long t0 = clock64();
-    while (static_cast<int>(ld_relaxed_sys_u32(f) - n) < 0) {
-      if (clock64() - t0 > 8000000000LL) { atomicExch(err_flag, MINPPO_ERR_BARRIER); break; }
-    }
-    asm volatile("fence.acquire.sys;" ::: "memory");
-  }
-  __syncthreads();
-}
-
 struct alignas(64) DwOptParams {
   GemmParams gemm;
   OptArgs opt;
@@ -106,7 +83,7 @@ struct alignas(64) DwOptParams {
   float* cs_out[GEMM_MAX_GROUPS];
   int cs_rows, cs_n, cs_chunks;  // cs_chunks == 0: the GEMM CTAs form them on the tensor core instead
   // Gradient exchange over NVLink peer memory (env-sharded ranks; world == 0: not configured).  Every rank exports
-  // one allocation [xbuf | rbuf | ss | flags] (PeerXchg offsets); base[r] is rank r's copy as mapped HERE.
+  // one allocation [stage | pad | result] (PeerXchg above); base[r] is rank r's copy as mapped HERE.
   PeerXchg px;
   // L2 prefetch of the NEXT minibatch's observation rows (the fused step kernel gathers them first thing)
   const int32_t* row_count;      // optional: rows of this minibatch on this rank (device side); partial sums of the

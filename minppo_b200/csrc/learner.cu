@@ -278,7 +278,7 @@ struct minppo_ctx {
   ncclComm_t comm;
   bool have_comm;
   // gradient exchange over peer memory (dwopt.cuh PeerXchg)
-  float* xchg;                // [xbuf | rbuf | ss | flags] (world_size > 1), exported by CUDA IPC
+  float* xchg;                // [stage | pad | result] (world_size > 1; dwopt.cuh PeerXchg), exported by CUDA IPC
   unsigned int* xseq;
   PeerXchg px;
   bool peers_set;
