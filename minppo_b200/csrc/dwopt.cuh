@@ -152,8 +152,12 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   float ss = 0.f;
   DW_STAMP(0);
   __shared__ unsigned int s_seq;
+  __shared__ int s_dead;                                  // error flag already up when this launch started
   const bool px_on = p.px.world > 1;                     // gradient exchange over peer memory fused into this launch
-  if (px_on && t == 0) s_seq = __ldcg(p.px.seq) + 1u;    // number of this exchange
+  if (px_on && t == 0) {
+    s_seq = __ldcg(p.px.seq) + 1u;                       // number of this exchange
+    s_dead = __ldcg(a.err_flag) != 0;
+  }
   leaf_tab_build(T, a, t, NT);
   __syncthreads();
 
@@ -258,6 +262,10 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     const PeerXchg& X = p.px;
     const int R = X.rank;
     const int W = X.ablate == 2 ? 1 : X.world;             // ablation: behave like a lone rank (slot R is never read)
+    // Once the error flag is up (a peer never delivered within the bound, or any earlier device-side guard fired) the
+    // exchange stops waiting: the update is already lost (minppo_ctx_check reports it), and 128 steps x the spin bound
+    // must not turn one dead peer into a quarter of an hour of hung GPUs.
+    const bool nowait = X.ablate != 0 || s_dead != 0;
     const unsigned int n = s_seq, par = n & 1u;
     const int n_late4 = 4 * n_units;
     // early element (or loss sum) of this thread: same job numbering as apply_adam_class<false>
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     if (ul >= 0) {
       if (reduce_here) {
         float4 v[MINPPO_MAX_RANKS];
-        unsigned int pending = X.ablate ? 0u : ((1u << W) - 1u) & ~(1u << R);
+        unsigned int pending = nowait ? 0u : ((1u << W) - 1u) & ~(1u << R);
 #pragma unroll
         for (int q = 0; q < MINPPO_MAX_RANKS; ++q) v[q] = g4;
         while (pending) {
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
       } else {
         float* src = px_result(X, R, par) + 4 * unit;
         float4 v = g4;
-        while (!X.ablate) {
+        while (!nowait) {
           v = ld_sys_v4(src);
           if (is_real4(v)) break;
           if (clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
       float ge = 0.f;
       auto poll1 = [&](float* src, float fallback) {
         unsigned int w = __float_as_uint(fallback);
-        while (!X.ablate && (w = ld_relaxed_sys_u32(reinterpret_cast<const unsigned int*>(src))) == SENT) {
+        while (!nowait && (w = ld_relaxed_sys_u32(reinterpret_cast<const unsigned int*>(src))) == SENT) {
           if (clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
         }
         st_sys_f32(src, -0.f);
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
       if (reduce_here) {
         // all W - 1 contributions polled together (one L2 round trip per sweep, not one per rank)
         float ev[MINPPO_MAX_RANKS];
-        unsigned int pending = X.ablate ? 0u : ((1u << W) - 1u) & ~(1u << R);
+        unsigned int pending = nowait ? 0u : ((1u << W) - 1u) & ~(1u << R);
 #pragma unroll
         for (int q = 0; q < MINPPO_MAX_RANKS; ++q) ev[q] = gl;
         while (pending) {
