@@ -19,10 +19,15 @@ forward/backward + PPO loss + global-norm clip + Adam.
 D = 225 / A = 10 are a DECLARED STAND-IN for stompy_pro (its MJCF is fetched at run time by the
 reference).  `--impl reference`: JAX is not installable in this image, so the
 reference arm times the oracle's PyTorch-CPU restatement of the same update ("kind": "port").
+
+Separation: the product arm (`run_ours`) imports only `minppo_b200` (+ numpy / torch for input generation and device
+memory); `oracle/` is imported by exactly two legs -- `cpu_update_time` (the `cpu_baseline` object at N = 1) and
+`run_reference` (`--impl reference`).
 """
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import subprocess
@@ -57,26 +62,88 @@ def workload(n_gpus: int, which: str = "auto"):
                 num_envs=2048 * n_gpus, num_steps=128, num_minibatches=32, update_epochs=4, scaling="weak")
 
 
-def make_hyper(w):
+@dataclasses.dataclass
+class BenchShape:
+    """The learner shape of one workload (the reference's defaults, config.py:50-84, where not given)."""
+    num_envs: int
+    num_steps: int
+    num_minibatches: int
+    update_epochs: int
+    hidden_size: int = 256
+    num_layers: int = 2
+    use_tanh: bool = True
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+
+    @property
+    def batch_size(self) -> int:
+        return self.num_envs * self.num_steps
+
+    @property
+    def minibatch_size(self) -> int:
+        return self.batch_size // self.num_minibatches
+
+
+def make_shape(w) -> BenchShape:
+    return BenchShape(num_envs=w["num_envs"], num_steps=w["num_steps"], num_minibatches=w["num_minibatches"],
+                      update_epochs=w["update_epochs"])
+
+
+def make_config(hp: BenchShape, fast_tanh: bool):
+    """The product's Config for this shape: anneal_lr=True with the default 1e9 total timesteps (config.py:79, 83)."""
+    from minppo_b200.config import Config
+
+    c = Config()
+    c.model.hidden_size, c.model.num_layers, c.model.use_tanh = hp.hidden_size, hp.num_layers, hp.use_tanh
+    c.rl.num_env_steps, c.rl.gamma, c.rl.gae_lambda = hp.num_steps, hp.gamma, hp.gae_lambda
+    c.training.num_envs, c.training.num_steps = hp.num_envs, hp.num_steps
+    c.training.num_minibatches, c.training.update_epochs, c.training.anneal_lr = hp.num_minibatches, hp.update_epochs, True
+    c.learner.fast_tanh, c.learner.use_graph = fast_tanh, True
+    return c
+
+
+def make_hyper(hp: BenchShape):
+    """CPU arm only: the oracle's hyper-parameter record for the same shape."""
     from oracle import ppo_numpy as P
 
-    # anneal_lr=True with the default 1e9 total timesteps (config.py:79, 83) -- the reference's defaults
-    return P.Hyper(num_envs=w["num_envs"], num_steps=w["num_steps"], num_minibatches=w["num_minibatches"],
-                   update_epochs=w["update_epochs"], anneal_lr=True)
+    return P.Hyper(num_envs=hp.num_envs, num_steps=hp.num_steps, num_minibatches=hp.num_minibatches,
+                   update_epochs=hp.update_epochs, anneal_lr=True)
+
+
+def tree_map(tree, fn):
+    return {k: tree_map(v, fn) if isinstance(v, dict) else fn(v) for k, v in tree.items()}
+
+
+def init_param_tree(hidden: int, num_layers: int, seed: int = 0):
+    """Synthetic parameters in the checkpoint tree layout (train.py:86-89) with the init GAINS of train.py:63/68
+    (sqrt(2) hidden, 0.01 last layer) as plain scaled normals -- random-init weights of the architecture."""
+    g = np.random.default_rng(seed)
+    p = {"params": {}}
+    for mlp, out_dim in (("MLP_0", ACT_DIM), ("MLP_1", 1)):
+        d = {}
+        fan_in = OBS_DIM
+        for i in range(num_layers):
+            d[f"Dense_{i}"] = {"kernel": (g.standard_normal((fan_in, hidden)) * np.sqrt(2.0 / fan_in)).astype(np.float32),
+                               "bias": (0.01 * g.standard_normal(hidden)).astype(np.float32)}
+            fan_in = hidden
+        d[f"Dense_{num_layers}"] = {"kernel": (g.standard_normal((fan_in, out_dim)) * (0.01 / np.sqrt(fan_in))).astype(np.float32),
+                                    "bias": (0.01 * g.standard_normal(out_dim)).astype(np.float32)}
+        p["params"][mlp] = d
+    p["params"]["log_std"] = (0.05 * g.standard_normal(ACT_DIM)).astype(np.float32)
+    return p
 
 
 def synth_shard(hp, rank: int, world: int, seed: int = 0):
     """Synthetic shard [T, N/world, ...] in float32 NumPy.  Params from the init gains; value / log_prob
-    from a forward pass under those params (float32 torch CPU for speed); reward ~ N(0,1); done ~ B(0.01)."""
+    from a forward pass under those params (float32 torch CPU for speed); reward ~ N(0,1); done ~ B(0.01).
+    Input generation only: nothing here touches oracle/ or the product."""
     import torch
 
-    from oracle import ppo_numpy as P
-
     T, Nl = hp.num_steps, hp.num_envs // world
-    params = P.init_params(OBS_DIM, ACT_DIM, hp.hidden_size, hp.num_layers, seed, np.float32)
+    params = init_param_tree(hp.hidden_size, hp.num_layers, seed)
     g = torch.Generator().manual_seed(1234 + rank)
     obs = torch.randn(T * Nl, OBS_DIM, generator=g)
-    pt = P.tree_like(params, lambda x: torch.from_numpy(x))["params"]
+    pt = tree_map(params, lambda x: torch.from_numpy(x))["params"]
 
     def mlp(m, x, tanh):
         for i in range(hp.num_layers):
@@ -170,6 +237,7 @@ def cpu_update_time(hp, sample_minibatches: int, repeats: int = 1):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     params, traj, last_val = synth_shard(hp, 0, 1)
+    hp = make_hyper(hp)                                   # the oracle's record of the same shape
     pt = PT.to_torch(params, torch.float32)
     opt = {"count": 0, "mu": P.tree_like(pt, torch.zeros_like), "nu": P.tree_like(pt, torch.zeros_like)}
     tr = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in traj.items()}
@@ -194,7 +262,7 @@ def run_reference(args):
     if rank != 0:
         return
     w = workload(args.gpus, args.workload)
-    hp = make_hyper(w)
+    hp = make_shape(w)
     B = hp.batch_size
     sample = 4 if B >= (1 << 20) else 8
     for _ in range(args.warmup):
@@ -228,8 +296,7 @@ def run_ours(args):
 
     from minppo_b200 import _lib
     from minppo_b200.learner import HostBatch, Learner, Memory, TrainState, calculate_gae, nccl_unique_id
-    from oracle import ppo_numpy as P
-    from tests.helpers import hyper_to_config
+    from minppo_b200.params import flatten_params
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -254,12 +321,12 @@ def run_ours(args):
         nccl_id = ids[0]
 
     w = workload(world, args.workload)
-    hp = make_hyper(w)
+    hp = make_shape(w)
     B = hp.batch_size
-    cfg = hyper_to_config(hp, fast_tanh=bool(args.fast_tanh), use_graph=True)
+    cfg = make_config(hp, bool(args.fast_tanh))
     learner = Learner(cfg, OBS_DIM, ACT_DIM, dev, world, rank, nccl_id)
     params, traj, last_val = synth_shard(hp, rank, world)
-    flat = P.flatten_params(params, hp.num_layers)
+    flat = flatten_params(params, hp.num_layers)
     t = lambda x: torch.as_tensor(np.ascontiguousarray(x)).to(dev)
     mem = Memory(done=t(traj["done"]), action=t(traj["action"]), value=t(traj["value"]), reward=t(traj["reward"]),
                  log_prob=t(traj["log_prob"]), obs=t(traj["obs"]))
