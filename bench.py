@@ -185,7 +185,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
         except OSError:
             self.proc = None
             return
@@ -204,6 +204,17 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            # the timed region was shorter than one sampling period: one query right after it (clocks have not ramped
+            # down yet) is better than no evidence at all
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=10).stdout
+                self.rows = [l.strip() for l in out.splitlines() if l.strip()]
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
