@@ -5,7 +5,8 @@ ActorCritic forward/backward + PPO loss, global-norm clip + Adam.
 Public surface:
   minppo_b200.config   -- mirror of the rl.* / training.* / opt.* / model.* config keys
   minppo_b200.params   -- checkpoint pickle layout <-> flat fp32 arena
-  minppo_b200.learner  -- Learner.update (the seam of _update_step), calculate_gae, permutations
+  minppo_b200.learner  -- Learner.update (the seam of _update_step), Learner.policy_step, calculate_gae, permutations
+  minppo_b200.infer    -- InferencePolicy: checkpoint pickle -> deterministic / sampled actions (infer.py:17-27)
   minppo_b200._lib     -- ctypes binding of the C ABI (include/minppo_b200.h)
 """
 __version__ = "0.1.0"

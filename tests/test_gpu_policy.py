@@ -150,3 +150,29 @@ def test_rollout_log_prob_matches_first_epoch(cuda_device):
     assert abs(actor_loss) < 1e-5
     assert abs(value_loss - 0.5 * np.mean((v_old - tgt) ** 2)) <= 1e-5 * max(1.0, value_loss)
     learner.close()
+
+
+def test_inference_policy_from_checkpoint(cuda_device, tmp_path):
+    """infer.py:17-27: pickle written in the reference's layout -> InferencePolicy.act == Learner.policy_step."""
+    import torch
+
+    from minppo_b200.infer import InferencePolicy
+    from minppo_b200.params import save_model
+
+    hp, pr, learner, flat, obs = _setup("c1", cuda_device)
+    dobs = torch.as_tensor(obs).to(cuda_device)
+    ref_a, _, ref_v, _, _ = learner.policy_step(flat, dobs, None)
+    path = str(tmp_path / "trained_model.pkl")
+    save_model(P.tree_like(pr["params"], lambda x: x.astype(np.float32)), path)
+    pol = InferencePolicy.from_checkpoint(path, hyper_to_config(hp), hp.num_envs, cuda_device)
+    assert (pol.obs_dim, pol.act_dim) == (CASES["c1"]["D"], CASES["c1"]["A"])
+    a, v = pol.act(dobs)
+    assert torch.equal(a, ref_a) and torch.equal(v, ref_v)
+    a2, v2 = pol.act(dobs)                                     # second call takes the weights-current fast path
+    assert torch.equal(a2, ref_a) and torch.equal(v2, ref_v)
+    rng = torch.as_tensor(pr["rng"].view(np.int32)).to(cuda_device)
+    sa, slp, sv, rng2 = pol.act(dobs, rng)
+    ra, rlp, rv, rrng, _ = learner.policy_step(flat, dobs, rng)
+    assert torch.equal(sa, ra) and torch.equal(slp, rlp) and torch.equal(rng2, rrng)
+    pol.close()
+    learner.close()
