@@ -69,10 +69,13 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) opt_kernel(const OptArgs a) {
       // gflat[P] = sum max(vl, vlc), gflat[P+1] = sum min(l1, l2) over the global minibatch
       const float value_loss = 0.5f * __ldcg(a.gflat + P) * a.inv_mb;
       const float actor_loss = -__ldcg(a.gflat + P + 1) * a.inv_mb;
-      a.losses_out[0] = actor_loss + a.vf_coef * value_loss - a.ent_coef * ent;
-      a.losses_out[1] = value_loss;
-      a.losses_out[2] = actor_loss;
-      a.losses_out[3] = ent;
+      // a raised device-side error flag (row-list overflow, barrier / exchange timeout) poisons the reported losses:
+      // the failure surfaces in the update's own result without a host round trip (minppo_ctx_check names the cause)
+      const float poison = __ldcg(a.err_flag) != 0 ? __int_as_float(0x7fc00000) : 0.f;
+      a.losses_out[0] = actor_loss + a.vf_coef * value_loss - a.ent_coef * ent + poison;
+      a.losses_out[1] = value_loss + poison;
+      a.losses_out[2] = actor_loss + poison;
+      a.losses_out[3] = ent + poison;
       if (a.gnorm_out) *a.gnorm_out = sc.gnorm;
     }
   }

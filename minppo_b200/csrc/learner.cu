@@ -269,10 +269,10 @@ struct minppo_ctx {
   cudaStream_t cap_stream;
   cudaStream_t side_stream;    // fork/join branch of an update: operand staging (observation + weight images) runs beside
   cudaEvent_t ev_fork, ev_join;  // the GAE -> permutation -> row-list chain (independent until the first minibatch step)
-  cudaGraph_t graph;
-  cudaGraphExec_t graph_exec;
-  UpdatePtrs graph_ptrs;
-  bool have_graph;
+  // One instantiated graph per POINTER SET, least recently used first out (a caller that alternates between a few
+  // buffer sets -- ping-pong rng keys, double-buffered trajectories -- replays instead of re-capturing ~290 nodes).
+  struct CachedGraph { cudaGraph_t graph; cudaGraphExec_t exec; UpdatePtrs ptrs; long long launches; };
+  std::vector<CachedGraph> graphs;
   long long launches;
   // nccl
   ncclComm_t comm;
@@ -347,16 +347,15 @@ static int act_kind(const minppo_ctx* c, int net) {
   return c->cfg.fast_tanh ? ACT_TANH_FAST : ACT_TANH;
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device: set on every context creation (a process may hold contexts on
+// several GPUs; the calls are cheap and idempotent).
 static int init_kernel_attrs() {
-  static bool done = false;
-  if (done) return 0;
   CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_DACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_PARTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   if (head_loss_init()) { set_error("head_loss_init failed"); return MINPPO_ERR_CUDA; }
   CK(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
   CK(cudaFuncSetAttribute(dwopt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  done = true;
   return 0;
 }
 
@@ -675,7 +674,7 @@ static int enqueue_update(minppo_ctx* c, const UpdatePtrs& u, cudaStream_t strea
   const int EM = c->E * c->M;
   {
     PROF(PC_PREP);
-    RET(compact_rows_launch(c->perms, c->rowidx, c->counts, c->E, c->M, c->B, c->mb, c->cap, c->N, c->n0, c->Nl, stream));
+    RET(compact_rows_launch(c->perms, c->rowidx, c->counts, c->E, c->M, c->B, c->mb, c->cap, c->N, c->n0, c->Nl, c->err_flag, stream));
     RET(adv_stats_launch(c->adv, c->rowidx, c->counts, c->stats, EM, c->cap, c->mb, 0, stream));
     if (cfg.world_size > 1) RET(nccl_allreduce(c, c->stats, EM, stream));
     RET(adv_stats_launch(c->adv, c->rowidx, c->counts, c->stats, EM, c->cap, c->mb, 1, stream));
@@ -772,9 +771,14 @@ int minppo_nccl_unique_id(void* id128_host) {
   return 0;
 }
 
+static void drop_graphs(minppo_ctx* c) {
+  for (auto& g : c->graphs) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph); }
+  c->graphs.clear();
+}
+
 int minppo_ctx_destroy(minppo_ctx* c) {
   if (!c) return 0;
-  if (c->have_graph) { cudaGraphExecDestroy(c->graph_exec); cudaGraphDestroy(c->graph); }
+  drop_graphs(c);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->side_stream) cudaStreamDestroy(c->side_stream);
@@ -792,7 +796,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   RET(validate_config(*cfg));
   minppo_ctx* c = new minppo_ctx();
   c->cfg = *cfg;
-  c->have_graph = false; c->have_comm = false; c->cap_stream = nullptr; c->launches = 0;
+  c->have_comm = false; c->cap_stream = nullptr; c->launches = 0;
   c->side_stream = nullptr; c->ev_fork = nullptr; c->ev_join = nullptr;
   c->profiling = false; c->prof_used = 0;
   int rc = 0;
@@ -1000,20 +1004,33 @@ int minppo_update(minppo_ctx* c, float* params, float* mu, float* nu, int32_t* c
   const bool was_profiling = c->profiling;
   c->profiling = false;                         // event records are not captured; profile in eager mode
   struct Restore { minppo_ctx* c; bool v; ~Restore() { c->profiling = v; } } restore{c, was_profiling};
-  if (!(c->have_graph && c->graph_ptrs == u)) {
-    if (c->have_graph) { cudaGraphExecDestroy(c->graph_exec); cudaGraphDestroy(c->graph); c->have_graph = false; }
+  size_t hit = c->graphs.size();
+  for (size_t i = 0; i < c->graphs.size(); ++i)
+    if (c->graphs[i].ptrs == u) { hit = i; break; }
+  if (hit == c->graphs.size()) {
+    constexpr size_t kMaxGraphs = 4;
+    if (c->graphs.size() >= kMaxGraphs) {
+      // evict the least recently used set; the exec may still be running on the caller's stream: CUDA defers the release
+      // of an executable graph's resources until its in-flight launches have completed
+      cudaGraphExecDestroy(c->graphs.front().exec); cudaGraphDestroy(c->graphs.front().graph);
+      c->graphs.erase(c->graphs.begin());
+    }
     CK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
     int r = enqueue_update(c, u, c->cap_stream);
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(c->cap_stream, &g);
     if (r != 0) { if (g) cudaGraphDestroy(g); return r; }
     if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
-    c->graph = g;
-    CK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
-    c->graph_ptrs = u;
-    c->have_graph = true;
+    cudaGraphExec_t ge = nullptr;
+    if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { cudaGraphDestroy(g); set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(cudaGetLastError())); return MINPPO_ERR_CUDA; }
+    c->graphs.push_back({g, ge, u, c->launches});
+  } else if (hit + 1 != c->graphs.size()) {
+    const minppo_ctx::CachedGraph cg = c->graphs[hit];         // most recently used goes last
+    c->graphs.erase(c->graphs.begin() + hit);
+    c->graphs.push_back(cg);
   }
-  CK(cudaGraphLaunch(c->graph_exec, stream));
+  c->launches = c->graphs.back().launches;
+  CK(cudaGraphLaunch(c->graphs.back().exec, stream));
   return 0;
 }
 
@@ -1100,7 +1117,7 @@ int minppo_ctx_set_peers(minppo_ctx* c, const void* handles_host) {
   // gradient per rank on the links instead of W - 1 gradients); MINPPO_PX_TWO_PHASE=0/1 forces either
   c->px.two_phase = getenv("MINPPO_PX_TWO_PHASE") ? (atoi(getenv("MINPPO_PX_TWO_PHASE")) != 0) : (W >= 4);
   c->peers_set = true;
-  if (c->have_graph) { cudaGraphExecDestroy(c->graph_exec); cudaGraphDestroy(c->graph); c->have_graph = false; }
+  drop_graphs(c);
   return 0;
 }
 

@@ -25,7 +25,8 @@ constexpr int CR_ITEMS = 4;
 __global__ void __launch_bounds__(CR_THREADS) compact_rows_kernel(const int32_t* __restrict__ perms,
                                                                   int32_t* __restrict__ rowidx,
                                                                   int32_t* __restrict__ counts, int M, long long B,
-                                                                  int mb, int cap, int N, int n0, int Nl) {
+                                                                  int mb, int cap, int N, int n0, int Nl,
+                                                                  int* __restrict__ err_flag) {
   __shared__ int warp_tot[2][CR_THREADS / 32];
   griddep_wait();                                 // launched with programmatic serialization (launch_chain)
   griddep_launch();
@@ -70,7 +71,13 @@ __global__ void __launch_bounds__(CR_THREADS) compact_rows_kernel(const int32_t*
     base += total;
   }
   const int count = base;
-  if (threadIdx.x == 0) counts[s] = count;          // > cap is reported by the host-visible check
+  if (threadIdx.x == 0) {
+    counts[s] = count;
+    // A row list that does not fit its capacity (env-sharded ranks: 1.5 x the mean + 256 rows) would silently bias the
+    // gradient: raise the device-side error flag NOW.  The step kernels' optimizer phase sees it (dwopt.cuh) and writes
+    // NaN into losses_out, so the overflow surfaces asynchronously in the update's own result; minppo_ctx_check reports it.
+    if (count > cap) atomicExch(err_flag, MINPPO_ERR_WORKSPACE);
+  }
   for (int j = min(count, cap) + static_cast<int>(threadIdx.x); j < cap; j += CR_THREADS) dst[j] = 0;
 }
 
@@ -105,8 +112,8 @@ __global__ void __launch_bounds__(MB_THREADS) adv_stats_kernel(const float* __re
 }
 
 int compact_rows_launch(const int32_t* perms, int32_t* rowidx, int32_t* counts, int E, int M, long long B, int mb,
-                        int cap, int N, int n0, int Nl, cudaStream_t stream) {
-  launch_chain(compact_rows_kernel, dim3(E * M), dim3(CR_THREADS), 0, stream, perms, rowidx, counts, M, B, mb, cap, N, n0, Nl);
+                        int cap, int N, int n0, int Nl, int* err_flag, cudaStream_t stream) {
+  launch_chain(compact_rows_kernel, dim3(E * M), dim3(CR_THREADS), 0, stream, perms, rowidx, counts, M, B, mb, cap, N, n0, Nl, err_flag);
   return cudaGetLastError() == cudaSuccess ? 0 : MINPPO_ERR_CUDA;
 }
 

@@ -31,7 +31,7 @@ int perm_launch_count(long long B);
 // rowidx[(e*M+k)*cap + j] = local flat index of the j-th row of minibatch (e,k) that this rank
 // owns, in permutation order; entries j >= count are 0.  counts[e*M+k] = number owned.
 int compact_rows_launch(const int32_t* perms, int32_t* rowidx, int32_t* counts, int E, int M, long long B, int mb,
-                        int cap, int N, int n0, int Nl, cudaStream_t stream);
+                        int cap, int N, int n0, int Nl, int* err_flag, cudaStream_t stream);
 // stats[s] = sum of adv over owned rows of minibatch s = e*M+k (pass 0); stats[EM+s] = sum (adv - mean)^2
 // with mean = stats[s] / mb (pass 1, after the sums have been all-reduced if sharded).
 int adv_stats_launch(const float* adv, const int32_t* rowidx, const int32_t* counts, float* stats, int EM, int cap,

@@ -21,7 +21,7 @@
 #include <map>
 #include <mutex>
 #include <string>
-#include <tuple>
+#include <utility>
 
 #include "minppo_b200.h"
 #include "xla/ffi/api/ffi.h"
@@ -58,16 +58,19 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(MinppoGae, GaeImpl,
                                   .Ret<ffi::Buffer<ffi::F32>>()); // targets
 
 // ---- learner update -------------------------------------------------------------------------
-// One context per (device, shape, hyper-parameters); created on first use, kept for the process.
+// One context per (device, COMPLETE minppo_config); created on first use, kept for the process.  minppo_ctx_create
+// snapshots the whole config (learning rates, gamma, clip_eps, coefficients, anneal_lr, total_timesteps, use_tanh, ...),
+// so the key is every byte of it: a second call with the same shapes but different hyper-parameters gets its own
+// context instead of silently training with the first one's settings.  Callers value-initialise the struct
+// (`minppo_config c = {}`), so padding bytes compare equal.
 namespace {
-using CtxKey = std::tuple<int, int32_t, int32_t, int32_t, int32_t, int32_t, int32_t, int32_t, int32_t, int32_t>;
+using CtxKey = std::pair<int, std::string>;
 std::mutex g_mu;
 std::map<CtxKey, minppo_ctx*> g_ctx;
 
 minppo_ctx* GetCtx(const minppo_config& c, int device, int* err) {
   std::lock_guard<std::mutex> lock(g_mu);
-  CtxKey key{device, c.num_envs, c.num_steps, c.num_minibatches, c.update_epochs, c.hidden_size,
-             c.num_layers, c.obs_dim, c.act_dim, c.prng_mode};
+  CtxKey key{device, std::string(reinterpret_cast<const char*>(&c), sizeof(c))};
   auto it = g_ctx.find(key);
   if (it != g_ctx.end()) return it->second;
   minppo_ctx* ctx = nullptr;

@@ -163,6 +163,11 @@ class Learner:
             _lib.check(self.lib.minppo_ctx_create(C.byref(self.cconf), idbuf, C.byref(handle)))
         self._h = handle
         self.use_graph = bool(config.learner.use_graph)
+        # Persistent device slots for the rng key and the losses: the library caches one CUDA graph per POINTER SET, so the
+        # natural loop `ts, rng, losses = learner.update(ts, mem, last_val, rng)` must present the same pointers every call.
+        self._key_in = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._key_out = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._losses = torch.zeros((self.E, self.M, 4), dtype=torch.float32, device=self.device)
         self.peer_exchange = False
         if world_size > 1 and os.environ.get("MINPPO_NCCL_ALLREDUCE", "0") != "1":
             self._connect_peers()
@@ -210,7 +215,12 @@ class Learner:
     def update(self, train_state: TrainState, mem_batch: Memory, last_val: torch.Tensor, rng: torch.Tensor,
                losses: Optional[torch.Tensor] = None, rng_out: Optional[torch.Tensor] = None):
         """train.py:185-281.  In place on ``train_state``; returns (train_state, rng', losses[E, M, 4])
-        with losses columns (total, value_loss, actor_loss, entropy).  Nothing synchronises."""
+        with losses columns (total, value_loss, actor_loss, entropy).  Nothing synchronises.
+
+        ``rng`` is copied (8 bytes, stream-ordered) into a learner-owned slot; without ``losses`` / ``rng_out`` the
+        results land in learner-owned buffers that the NEXT ``update`` overwrites (pass your own to keep them).  With
+        the trajectory / train-state tensors reused across calls the pointer set is stable and every update is one CUDA
+        graph replay; the library keeps the 4 most recently used pointer sets."""
         dev = self.device
         T, Nl, D, A = self.T, self.Nl, self.obs_dim, self.act_dim
         obs = _check(mem_batch.obs, "obs", torch.float32, (T, Nl, D), dev)
@@ -227,14 +237,18 @@ class Learner:
         if rng.numel() != 2 or rng.element_size() != 4 or rng.device != dev:
             raise ValueError("rng must hold two 32-bit words on the learner's device")
         if losses is None:
-            losses = torch.empty((self.E, self.M, 4), dtype=torch.float32, device=dev)
+            losses = self._losses
+        else:
+            _check(losses, "losses", torch.float32, (self.E, self.M, 4), dev)
         if rng_out is None:
-            rng_out = torch.empty_like(rng)
+            rng_out = self._key_out.view(rng.dtype)
         with torch.cuda.device(dev):
+            if rng.data_ptr() != self._key_in.data_ptr():
+                self._key_in.copy_(rng.reshape(2).view(torch.int32), non_blocking=True)
             _lib.check(self.lib.minppo_update(
                 self._h, _ptr(train_state.params), _ptr(train_state.mu), _ptr(train_state.nu), _ptr(train_state.step),
                 _ptr(obs), _ptr(action), _ptr(value), _ptr(reward), _ptr(log_prob), _ptr(done), _ptr(last_val),
-                _ptr(rng), _ptr(rng_out), _ptr(losses), int(self.use_graph), _stream_ptr(dev)))
+                _ptr(self._key_in), _ptr(rng_out), _ptr(losses), int(self.use_graph), _stream_ptr(dev)))
         return train_state, rng_out, losses
 
     # -- policy / value inference for the rollout -------------------------------------------

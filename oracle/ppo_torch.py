@@ -84,6 +84,16 @@ def loss_fn(params: Dict, mb: Dict, hp: Hyper):
     return total, (value_loss, loss_actor, entropy)
 
 
+_COMPILED = {"on": False, "fn": None}
+
+
+def set_compiled(on: bool) -> None:
+    """bench.py's GPU proxy arm only: evaluate loss_fn through torch.compile (inductor).  Off by default."""
+    _COMPILED["on"] = bool(on)
+    if on and _COMPILED["fn"] is None:
+        _COMPILED["fn"] = torch.compile(loss_fn)
+
+
 def loss_and_grads(params: Dict, mb: Dict, hp: Hyper):
     """jax.value_and_grad(_loss_fn, has_aux=True) (train.py:246-247)."""
     paths = leaf_order(hp.num_layers)
@@ -91,7 +101,7 @@ def loss_and_grads(params: Dict, mb: Dict, hp: Hyper):
     tree = tree_like(params, lambda x: x)
     for p, l in zip(paths, leaves):
         set_leaf(tree, p, l)
-    total, (vl, al, ent) = loss_fn(tree, mb, hp)
+    total, (vl, al, ent) = (_COMPILED["fn"] if _COMPILED["on"] else loss_fn)(tree, mb, hp)
     gs = torch.autograd.grad(total, leaves)
     grads = tree_like(params, lambda x: x)
     for p, g in zip(paths, gs):
@@ -106,7 +116,10 @@ def clip_adam_step(params: Dict, grads: Dict, opt: Dict, hp: Hyper):
     dt = get_leaf(params, paths[0]).dtype
     npdt = np.float32 if dt == torch.float32 else np.float64
     g_norm = torch.sqrt(sum((get_leaf(grads, p) ** 2).sum() for p in paths))
-    trigger = bool(g_norm < hp.max_grad_norm)
+    on_gpu = g_norm.device.type != "cpu"
+    # CPU: a Python bool like optax's lax.select predicate; accelerator (bench.py's GPU proxy): a 0-d tensor and
+    # torch.where below, so that the eager stream is never synchronised mid-update
+    trigger = (g_norm < hp.max_grad_norm) if on_gpu else bool(g_norm < hp.max_grad_norm)
     count = opt["count"]
     lr = float(learning_rate(count, hp, npdt))
     c1 = float(npdt(1) - npdt(hp.b1) ** npdt(count + 1))
@@ -114,7 +127,9 @@ def clip_adam_step(params: Dict, grads: Dict, opt: Dict, hp: Hyper):
     new_p, new_mu, new_nu = (tree_like(params, lambda x: x) for _ in range(3))
     for p in paths:
         g = get_leaf(grads, p)
-        if not trigger:
+        if on_gpu:
+            g = torch.where(trigger, g, (g / g_norm) * hp.max_grad_norm)
+        elif not trigger:
             g = (g / g_norm) * hp.max_grad_norm
         mu = (1 - hp.b1) * g + hp.b1 * get_leaf(opt["mu"], p)
         nu = (1 - hp.b2) * (g * g) + hp.b2 * get_leaf(opt["nu"], p)
@@ -145,7 +160,8 @@ def update(params: Dict, opt: Dict, traj: Dict, last_val, rng, hp: Hyper, perms=
     for e in range(E):
         rng, sub = threefry.split(rng, 2, hp.prng_mode)
         perm = threefry.permutation(sub, B, hp.prng_mode) if perms is None else perms[e]
-        perm_t = torch.from_numpy(np.asarray(perm).astype(np.int64))
+        perm_t = perm if torch.is_tensor(perm) else torch.from_numpy(np.asarray(perm).astype(np.int64))
+        perm_t = perm_t.to(flat["obs"].device)
         # train.py:261: a full shuffled copy of every leaf, then [M, mb, ...] (262-265)
         shuffled = {k: v.index_select(0, perm_t) for k, v in flat.items()}
         for k in range(Mrun):

@@ -93,6 +93,7 @@ def test_update_parity(name, cuda_device):
         "first_loss_gpu": [float(x) for x in got["losses"][0, 0]],
         "first_loss_fp64": [float(x) for x in l64[0, 0]],
         "launches": got["launches"],
+        "param_leaf_rms_vs_bf16_oracle_in_lr": _per_leaf_rms_in_lr(got["params"], pbf, hp, case["D"], case["A"], lr),
     }
     METRICS[name] = m
     assert np.all(np.isfinite(got["losses"])) and np.all(np.isfinite(got["params"]))
@@ -102,6 +103,94 @@ def test_update_parity(name, cuda_device):
     nsteps = hp.update_epochs * hp.num_minibatches
     assert m["param_absdiff_vs_fp64_oracle_in_lr"] < 2.0 + 0.15 * nsteps, m
     assert m["param_rms_vs_fp64_oracle_in_lr"] < 1.0, m
+    # per leaf (a wrong small leaf would vanish in the global figures): rms <= 1 lr against the emulated oracle
+    assert max(m["param_leaf_rms_vs_bf16_oracle_in_lr"].values()) < 1.0, m
+
+
+# ---- the benchmarked shapes (BASELINE.json configs[1] and configs[3]) -----------------------------------
+BENCH_CASES = {
+    # configs[1]: what bench.py times at N = 1 (mb = 8192: 64 row tiles per net, split-K over 128 k-blocks)
+    "configs1": dict(hp=dict(num_envs=2048, num_steps=128, num_minibatches=32, update_epochs=4, anneal_lr=True), D=225, A=10),
+    # configs[3] on ONE GPU (mb = 32768: 256 row tiles per net = several waves of the fused step kernel)
+    "configs3": dict(hp=dict(num_envs=16384, num_steps=64, num_minibatches=32, update_epochs=4, anneal_lr=True), D=225, A=10),
+}
+
+
+def _per_leaf_rms_in_lr(got_flat, ref_tree, hp, D, A, lr):
+    out, off = {}, 0
+    ref = P.flatten_params(ref_tree, hp.num_layers, np.float64)
+    for pth, shp in zip(P.leaf_order(hp.num_layers), P.leaf_shapes(D, A, hp.hidden_size, hp.num_layers)):
+        n = int(np.prod(shp))
+        d = got_flat[off:off + n].astype(np.float64) - ref[off:off + n]
+        out["/".join(pth)] = float(np.sqrt(np.mean(d * d)) / lr)
+        off += n
+    assert off == ref.size
+    return out
+
+
+@pytest.mark.parametrize("name", list(BENCH_CASES))
+def test_update_parity_at_bench_shape(name, cuda_device):
+    """ONE full update (E x M = 128 sequential minibatch steps) at the shapes bench.py reports, against the
+    oracle run with the same bf16 rounding points (float32, gemm="bf16").  Tolerances: permutations / rng / step
+    count bit-exact; advantages and targets 1e-5 relative; every one of the 128 losses 2e-3 of the largest loss;
+    every gradient norm 2e-2; parameters PER LEAF rms <= 1 lr (Adam moves a parameter ~lr per step, 128 steps)."""
+    case = BENCH_CASES[name]
+    hp = P.Hyper(**case["hp"])
+    D, A = case["D"], case["A"]
+    pr = synth.make_problem(hp, D, A, seed=11, done_p=0.01)
+    got = run_gpu_update(hp, pr, cuda_device)
+    pbf, obf, rngbf, lbf, auxbf = _oracle(hp, pr, np.float32, "bf16")
+
+    assert np.array_equal(got["perms"], auxbf["perms"])
+    assert np.array_equal(got["rng"], rngbf)
+    assert got["step"] == hp.update_epochs * hp.num_minibatches == obf["count"]
+    assert np.abs(got["advantages"] - auxbf["advantages"]).max() <= 1e-5 * np.abs(auxbf["advantages"]).max()
+    assert np.abs(got["targets"] - auxbf["targets"]).max() <= 1e-5 * np.abs(auxbf["targets"]).max()
+    lr = hp.training_lr
+    leaf_rms = _per_leaf_rms_in_lr(got["params"], pbf, hp, D, A, lr)
+    m = {
+        "loss_vs_bf16_oracle": rel_err(got["losses"], lbf),
+        "loss_vs_bf16_oracle_per_column": [rel_err(got["losses"][..., j], lbf[..., j]) for j in (0, 1, 3)],
+        "gnorm_vs_bf16_oracle": float(np.abs(got["grad_norms"] - auxbf["grad_norms"]).max() / np.abs(auxbf["grad_norms"]).max()),
+        "param_leaf_rms_in_lr": leaf_rms,
+        "param_absdiff_vs_bf16_oracle_in_lr": float(np.abs(got["params"] - P.flatten_params(pbf, hp.num_layers, np.float64)).max() / lr),
+        "last_loss_gpu": [float(x) for x in got["losses"][-1, -1]],
+        "last_loss_oracle": [float(x) for x in lbf[-1, -1]],
+        "launches": got["launches"],
+    }
+    METRICS["bench_shape_" + name] = m
+    assert np.all(np.isfinite(got["losses"])) and np.all(np.isfinite(got["params"]))
+    assert m["loss_vs_bf16_oracle"] < 2e-3, m
+    assert m["gnorm_vs_bf16_oracle"] < 2e-2, m
+    assert max(leaf_rms.values()) < 1.0, m
+
+
+def test_update_parity_negative_lr_schedule(cuda_device):
+    """SURVEY F8 on the GPU: with training.total_timesteps = num_steps * num_envs (one update) the reference's
+    schedule (train.py:98-101) divides the step count by minibatch_size * update_epochs = 20, so over the 128
+    steps of config 1 frac = 1, 0, -1, ..., -5: the learning rate hits zero at step 20 and is NEGATIVE after."""
+    hp = P.Hyper(num_envs=16, num_steps=10, num_minibatches=32, update_epochs=4, anneal_lr=True, total_timesteps=160)
+    assert hp.num_updates == 1 and hp.minibatch_size * hp.update_epochs == 20
+    lrs = [float(P.learning_rate(k, hp, np.float32)) for k in range(128)]
+    assert lrs[0] == np.float32(hp.training_lr) and lrs[20] == 0.0 and lrs[40] < 0 and lrs[127] == np.float32(hp.training_lr) * -5
+    pr = synth.make_problem(hp, 225, 10, seed=7, done_p=0.02)
+    got = run_gpu_update(hp, pr, cuda_device)
+    p64, o64, rng64, l64, aux64 = _oracle(hp, pr, np.float64, "exact")
+    pbf, obf, _, lbf, auxbf = _oracle(hp, pr, np.float32, "bf16", perms=aux64["perms"])
+    assert np.array_equal(got["perms"], aux64["perms"])
+    assert got["step"] == 128
+    lr = hp.training_lr
+    m = {"loss_vs_bf16_oracle": rel_err(got["losses"], lbf), "loss_vs_fp64_oracle": rel_err(got["losses"], l64),
+         "param_leaf_rms_in_lr": _per_leaf_rms_in_lr(got["params"], pbf, hp, 225, 10, lr)}
+    METRICS["c1_negative_lr"] = m
+    assert m["loss_vs_bf16_oracle"] < 2e-3, m
+    assert m["loss_vs_fp64_oracle"] < 3e-2, m
+    # the schedule itself, observable: a run with the SAME inputs but a constant learning rate must differ
+    hp_const = P.Hyper(num_envs=16, num_steps=10, num_minibatches=32, update_epochs=4, anneal_lr=False)
+    got_const = run_gpu_update(hp_const, pr, cuda_device)
+    assert np.abs(got_const["params"] - got["params"]).max() > 10 * lr
+    # sum_k |lr_k| = (20 + 0 + 20 + 40 + 60 + 80 + 8 * 5) lr = 260 lr of possible travel (128 lr at constant lr)
+    assert max(m["param_leaf_rms_in_lr"].values()) < 5.0, m
 
 
 @pytest.mark.parametrize("name", ["medium", "ragged", "deep"])
