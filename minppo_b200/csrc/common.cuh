@@ -271,10 +271,11 @@ MINPPO_DEVINL void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
   hi = __bfloat16_as_ushort(h);
   lo = __bfloat16_as_ushort(l);
 }
-// byte offset of element (row rr, column c) inside a [32][ncols] bf16 SW128 tile set (4 KB per 64 columns).
-// The 16-wide head operands are stored as a bf16 hi / lo pair stacked along the rows: rr = part * 16 + j.
-MINPPO_DEVINL uint32_t sw32_off(int rr, int c) {
-  return static_cast<uint32_t>((c >> 6) * 4096 + rr * 128 + ((((c & 63) >> 3) ^ (rr & 7)) << 4) + (c & 7) * 2);
+// byte offset of element (row rr, column c) inside a [2 ap][ncols] bf16 SW128 tile set: one panel of 2 ap rows x 128 B per
+// 64 columns.  The head operands (width padded to ap = 16 or 32) are stored as a bf16 hi / lo pair stacked along the rows:
+// rr = part * ap + j.
+MINPPO_DEVINL uint32_t swp_off(int ap, int rr, int c) {
+  return static_cast<uint32_t>((c >> 6) * (ap * 256) + rr * 128 + ((((c & 63) >> 3) ^ (rr & 7)) << 4) + (c & 7) * 2);
 }
 MINPPO_DEVINL float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 MINPPO_DEVINL float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }

@@ -77,11 +77,6 @@ struct alignas(64) DwOptParams {
   OptArgs opt;
   int gemm_ctas;                 // CTAs [0, gemm_ctas) run the GEMM; the others pre-reduce the small leaves
   long long* trace;              // debug: [grid][16] clock64 stamps (null = off)
-  // bias gradients on the otherwise idle extra CTAs: column sums of dz (bf16 [cs_rows][cs_n]) of GEMM group i
-  // -> cs_out[i] as [cs_chunks][cs_n] partials (row chunk c of extra CTA e = c * ngroups + i)
-  const __nv_bfloat16* cs_src[GEMM_MAX_GROUPS];
-  float* cs_out[GEMM_MAX_GROUPS];
-  int cs_rows, cs_n, cs_chunks;  // cs_chunks == 0: the GEMM CTAs form them on the tensor core instead
   // Gradient exchange over NVLink peer memory (env-sharded ranks; world == 0: not configured).  Every rank exports
   // one allocation [stage | pad | result] (PeerXchg above); base[r] is rank r's copy as mapped HERE.
   PeerXchg px;
@@ -95,49 +90,10 @@ struct alignas(64) DwOptParams {
   const int32_t* next_count;     // optional: valid entries of next_ridx (device side)
 };
 
-// column sums of rows [r0, r1) of a bf16 [rows][n] matrix (n <= 256): one warp per row, 16-byte loads,
-// fixed summation order (rows within a warp, then warps)
-MINPPO_DEVINL void colsum_rows(const __nv_bfloat16* __restrict__ src, int n, int r0, int r1, float* __restrict__ out,
-                               float* scratch /* [DWOPT_THREADS / 32][256] */) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NW = DWOPT_THREADS / 32;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const bool on = lane * 8 < n;
-  int r = r0 + warp;
-#pragma unroll 1
-  for (; r + 7 * NW < r1; r += 8 * NW) {
-    uint4 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      v[u] = on ? __ldcg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + u * NW) * n) + lane) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { acc[2 * j] += bf16_lo(w[j]); acc[2 * j + 1] += bf16_hi(w[j]); }
-    }
-  }
-#pragma unroll 1
-  for (; r < r1; r += NW) {
-    const uint4 v = on ? __ldcg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * n) + lane) : make_uint4(0, 0, 0, 0);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[2 * j] += bf16_lo(w[j]); acc[2 * j + 1] += bf16_hi(w[j]); }
-  }
-  __syncthreads();                       // scratch reuse across calls
-#pragma unroll
-  for (int j = 0; j < 8; ++j) scratch[warp * 256 + lane * 8 + j] = acc[j];
-  __syncthreads();
-  for (int c = threadIdx.x; c < n; c += DWOPT_THREADS) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) s += scratch[w * 256 + c];
-    out[c] = s;
-  }
-}
-
+// MAXU = 4-element units of the hidden kernels a thread may own (fast path: reduced gradient and optimizer state stay in
+// registers across the second barrier).  MAXU = 1 covers P_late <= 4 * grid * 512 (303k parameters on 148 SMs: the
+// stand-in shape); larger observation widths take MAXU = 2 or 4.
+template <int MAXU>
 __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_constant__ DwOptParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float scratch[32];
@@ -205,55 +161,55 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     const int e = b - p.gemm_ctas, ne = G - p.gemm_ctas;
     const int live_tiles = p.row_count ? (max(__ldcg(p.row_count), 0) + p.part_rows - 1) / p.part_rows : 0x7fffffff;
     ss = reduce_leaves<false>(a, T, e * NT + t, ne * NT, live_tiles);
-    if (p.cs_chunks > 0 && e < p.cs_chunks * p.gemm.ngroups) {
-      const int i = e % p.gemm.ngroups, c = e / p.gemm.ngroups;
-      const int per = (p.cs_rows + p.cs_chunks - 1) / p.cs_chunks;
-      colsum_rows(p.cs_src[i], p.cs_n, min(p.cs_rows, c * per), min(p.cs_rows, (c + 1) * per),
-                  p.cs_out[i] + static_cast<size_t>(c) * p.cs_n, reinterpret_cast<float*>(smem_raw));
-    }
   }
   DW_STAMP(1);
   grid_barrier(a.barrier, a.err_flag);
   DW_STAMP(2);
 
   // ---- phase 2 ----------------------------------------------------------------------------------
-  // Fast path (every shape the fused step supports): at most one 4-element unit of a hidden kernel / bias per
-  // thread, so the reduced gradient and the optimizer state of those elements stay in registers across the second
-  // barrier and only the few small leaves go through gflat.
+  // Fast path: at most MAXU 4-element units of a hidden kernel per thread, so the reduced gradient and the optimizer
+  // state of those elements stay in registers across the second barrier and only the small leaves go through gflat.
   int n_units = 0;
   for (int l = 0; l < T.nleaves; ++l)
     if (T.leaf[l].late) n_units += T.size[l] >> 2;
-  const bool fast = n_units <= G * NT;
+  const int GT_ = G * NT;
+  const bool fast = n_units <= GT_ * MAXU;
   const int gtid = b * NT + t;
-  float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float pv[4], mv[4], nv[4];
-  int ul = -1, ui = 0;                                   // leaf and first arena index of this thread's unit
-  if (!has_extra) ss += reduce_leaves<false>(a, T, gtid, G * NT, p.row_count ? (max(__ldcg(p.row_count), 0) + p.part_rows - 1) / p.part_rows : 0x7fffffff);
+  float4 g4[MAXU];
+  float pv[MAXU][4], mv[MAXU][4], nv[MAXU][4];
+  int ul[MAXU], ui[MAXU];                                // leaf and first arena index of each of this thread's units
+  if (!has_extra) ss += reduce_leaves<false>(a, T, gtid, GT_, p.row_count ? (max(__ldcg(p.row_count), 0) + p.part_rows - 1) / p.part_rows : 0x7fffffff);
   // units dealt to warps round-robin over the CTAs (balanced, 512 contiguous bytes per warp and partial)
-  const int unit = (((t >> 5) * G + b) << 5) + (t & 31);
-  if (fast) {
-    if (unit < n_units) {
-      int x = unit, l = 0;
-      for (; l < T.nleaves; ++l) {
-        if (!T.leaf[l].late) continue;
-        const int n = T.size[l] >> 2;
-        if (x < n) break;
-        x -= n;
-      }
-      const OptLeaf& L = T.leaf[l];
-      ul = l; ui = L.offset + 4 * x;
-      if (a.do_apply) {
+  const int unit0 = (((t >> 5) * G + b) << 5) + (t & 31);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { pv[u] = __ldcg(a.params + ui + u); mv[u] = __ldcg(a.mu + ui + u); nv[u] = __ldcg(a.nu + ui + u); }
-      }
-      g4 = sum_partials16_v4(L.grad_src + L.src_offset + 4 * x, L.nparts, L.part_stride);
-      if (!px_on) {
-        if (!a.do_apply || a.keep_gflat) { float* dst = a.gflat + ui; dst[0] = g4.x; dst[1] = g4.y; dst[2] = g4.z; dst[3] = g4.w; }
-        ss = fmaf(g4.x, g4.x, ss); ss = fmaf(g4.y, g4.y, ss); ss = fmaf(g4.z, g4.z, ss); ss = fmaf(g4.w, g4.w, ss);
+  for (int u = 0; u < MAXU; ++u) { ul[u] = -1; ui[u] = 0; g4[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  if (fast) {
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int unit = unit0 + u * GT_;
+      if (unit < n_units) {
+        int x = unit, l = 0;
+        for (; l < T.nleaves; ++l) {
+          if (!T.leaf[l].late) continue;
+          const int n = T.size[l] >> 2;
+          if (x < n) break;
+          x -= n;
+        }
+        const OptLeaf& L = T.leaf[l];
+        ul[u] = l; ui[u] = L.offset + 4 * x;
+        if (a.do_apply) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { pv[u][e] = __ldcg(a.params + ui[u] + e); mv[u][e] = __ldcg(a.mu + ui[u] + e); nv[u][e] = __ldcg(a.nu + ui[u] + e); }
+        }
+        g4[u] = sum_partials16_v4(L.grad_src + L.src_offset + 4 * x, L.nparts, L.part_stride);
+        if (!px_on) {
+          if (!a.do_apply || a.keep_gflat) { float* dst = a.gflat + ui[u]; dst[0] = g4[u].x; dst[1] = g4[u].y; dst[2] = g4[u].z; dst[3] = g4[u].w; }
+          ss = fmaf(g4[u].x, g4[u].x, ss); ss = fmaf(g4[u].y, g4[u].y, ss); ss = fmaf(g4[u].z, g4[u].z, ss); ss = fmaf(g4[u].w, g4[u].w, ss);
+        }
       }
     }
   } else {
-    ss += reduce_leaves<true>(a, T, gtid, G * NT);
+    ss += reduce_leaves<true>(a, T, gtid, GT_);
   }
   if (!a.do_apply) return;
 
@@ -294,7 +250,6 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
       return __float_as_uint(v.x) != SENT && __float_as_uint(v.y) != SENT && __float_as_uint(v.z) != SENT && __float_as_uint(v.w) != SENT;
     };
     const float4 sent4 = make_float4(-0.f, -0.f, -0.f, -0.f);
-    g4.x = canon(g4.x); g4.y = canon(g4.y); g4.z = canon(g4.z); g4.w = canon(g4.w);
     float gl = 0.f;
     if (eidx >= 0) gl = canon(__ldcg(a.gflat + eidx));
     // TWO-PHASE (X.two_phase, used for W >= 4): the units of CTA b are reduced by rank b % W only.  A non-owner pushes its
@@ -304,14 +259,19 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     const bool two = X.two_phase != 0;
     const int owner = two ? b % W : R;
     const bool reduce_here = owner == R;
-    if (ul >= 0) {
+    // ---- pushes (all units first: every store is in flight before the first poll) ----
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      if (ul[u] < 0) continue;
+      const int unit = unit0 + u * GT_;
+      g4[u].x = canon(g4[u].x); g4[u].y = canon(g4[u].y); g4[u].z = canon(g4[u].z); g4[u].w = canon(g4[u].w);
       if (reduce_here) {
         if (!two) {
 #pragma unroll
-          for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_v4(px_stage(X, r, par, R) + 4 * unit, g4);
+          for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_v4(px_stage(X, r, par, R) + 4 * unit, g4[u]);
         }
       } else {
-        st_sys_v4(px_stage(X, owner, par, R) + 4 * unit, g4);
+        st_sys_v4(px_stage(X, owner, par, R) + 4 * unit, g4[u]);
       }
     }
     if (eidx >= 0) {
@@ -327,12 +287,15 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     DW_STAMP(13);
     ss = 0.f;
     const long long t0 = clock64();
-    if (ul >= 0) {
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      if (ul[u] < 0) continue;
+      const int unit = unit0 + u * GT_;
       if (reduce_here) {
         float4 v[MINPPO_MAX_RANKS];
         unsigned int pending = nowait ? 0u : ((1u << W) - 1u) & ~(1u << R);
 #pragma unroll
-        for (int q = 0; q < MINPPO_MAX_RANKS; ++q) v[q] = g4;
+        for (int q = 0; q < MINPPO_MAX_RANKS; ++q) v[q] = g4[u];
         while (pending) {
 #pragma unroll
           for (int q = 0; q < MINPPO_MAX_RANKS; ++q) {
@@ -343,34 +306,35 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
           }
           if (pending && clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
         }
-        const float4 own = g4;
-        g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 own = g4[u];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < MINPPO_MAX_RANKS; ++q) {
           if (q < W) {
             const float4 c = q == R ? own : v[q];
-            g4.x += c.x; g4.y += c.y; g4.z += c.z; g4.w += c.w;
+            acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
             if (q != R) st_sys_v4(px_stage(X, R, par, q) + 4 * unit, sent4);
           }
         }
+        g4[u] = acc;
         if (two) {
-          const float4 res = make_float4(canon(g4.x), canon(g4.y), canon(g4.z), canon(g4.w));
+          const float4 res = make_float4(canon(acc.x), canon(acc.y), canon(acc.z), canon(acc.w));
 #pragma unroll
           for (int r = 0; r < MINPPO_MAX_RANKS; ++r) if (r < W && r != R) st_sys_v4(px_result(X, r, par) + 4 * unit, res);
         }
       } else {
         float* src = px_result(X, R, par) + 4 * unit;
-        float4 v = g4;
+        float4 v = g4[u];
         while (!nowait) {
           v = ld_sys_v4(src);
           if (is_real4(v)) break;
           if (clock64() - t0 > 8000000000LL) { atomicExch(a.err_flag, MINPPO_ERR_BARRIER); break; }
         }
-        g4 = v;
+        g4[u] = v;
         st_sys_v4(src, sent4);
       }
-      if (a.keep_gflat) { float* dst = a.gflat + ui; dst[0] = g4.x; dst[1] = g4.y; dst[2] = g4.z; dst[3] = g4.w; }
-      ss = fmaf(g4.x, g4.x, ss); ss = fmaf(g4.y, g4.y, ss); ss = fmaf(g4.z, g4.z, ss); ss = fmaf(g4.w, g4.w, ss);
+      if (a.keep_gflat) { float* dst = a.gflat + ui[u]; dst[0] = g4[u].x; dst[1] = g4[u].y; dst[2] = g4[u].z; dst[3] = g4[u].w; }
+      ss = fmaf(g4[u].x, g4[u].x, ss); ss = fmaf(g4[u].y, g4[u].y, ss); ss = fmaf(g4[u].z, g4[u].z, ss); ss = fmaf(g4[u].w, g4[u].w, ss);
     }
     if (eidx >= 0) {
       float ge = 0.f;
@@ -419,7 +383,6 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     DW_STAMP(15);
     if (b == 0 && scal_thread) *X.seq = n;
   }
-  if (!a.do_apply) return;
   const float bs = block_sum<DWOPT_THREADS>(ss, scratch);
   if (t == 0) a.block_ss[b] = bs;
   DW_STAMP(3);
@@ -439,22 +402,24 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   sc.gnorm = s_bcast[0]; sc.lr = s_bcast[1]; sc.c1 = s_bcast[2]; sc.c2 = s_bcast[3];
   sc.trigger = sc.gnorm < a.max_norm;                    // optax.clip_by_global_norm
   if (fast) {
-    if (ul >= 0) {
-      const OptLeaf& L = T.leaf[ul];
-      const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        adam_element(a, sc, gv[u], pv[u], mv[u], nv[u]);
-        a.params[ui + u] = pv[u];
-        a.mu[ui + u] = mv[u];
-        a.nu[ui + u] = nv[u];
+    for (int u = 0; u < MAXU; ++u) {
+      if (ul[u] < 0) continue;
+      const OptLeaf& L = T.leaf[ul[u]];
+      const float gv[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        adam_element(a, sc, gv[e], pv[u][e], mv[u][e], nv[u][e]);
+        a.params[ui[u] + e] = pv[u][e];
+        a.mu[ui[u] + e] = mv[u][e];
+        a.nu[ui[u] + e] = nv[u][e];
       }
       if (L.img_n)             // 4 consecutive bf16 of the kernel image (unit index is a multiple of 4: 8-byte aligned)
-        *reinterpret_cast<uint2*>(L.img_n + (ui - L.offset)) = make_uint2(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]));
+        *reinterpret_cast<uint2*>(L.img_n + (ui[u] - L.offset)) = make_uint2(pack_bf16x2(pv[u][0], pv[u][1]), pack_bf16x2(pv[u][2], pv[u][3]));
     }
-    apply_adam_class<false>(a, T, sc, gtid, G * NT);
+    apply_adam_class<false>(a, T, sc, gtid, GT_);
   } else {
-    apply_adam(a, T, sc, gtid, G * NT);
+    apply_adam(a, T, sc, gtid, GT_);
   }
   __syncthreads();
   DW_STAMP(5);
@@ -476,8 +441,13 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   }
 }
 
-inline cudaError_t dwopt_launch(const DwOptParams& p, int grid, cudaStream_t stream, bool pdl) {
-  return launch_kernel(dwopt_kernel, grid, DWOPT_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
+// largest parameter count of the hidden kernels the register-resident fast path covers on a grid of `grid` CTAs
+inline long long dwopt_fast_capacity(int grid, int maxu) { return 4LL * grid * DWOPT_THREADS * maxu; }
+
+inline cudaError_t dwopt_launch(const DwOptParams& p, int grid, cudaStream_t stream, bool pdl, int maxu) {
+  if (maxu <= 1) return launch_kernel(dwopt_kernel<1>, grid, DWOPT_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
+  if (maxu == 2) return launch_kernel(dwopt_kernel<2>, grid, DWOPT_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
+  return launch_kernel(dwopt_kernel<4>, grid, DWOPT_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
 }
 
 }  // namespace minppo

@@ -5,21 +5,28 @@
 // the gathered observation rows and the layer gradients dZ stays on chip; every contraction runs
 // on the tcgen05 tensor cores with accumulators in TMEM:
 //
-//   gather X (cp.async by row index, SW128)               -> smem R1
-//   L1   acc0 = X  W0^T  (B streamed by TMA)              -> +b0, act, bf16 -> R0 (H1) -> TMA store
-//   L2   acc1 = H1 W1^T                                   -> +b1, act, bf16 -> R1 (H2)
-//   head out  = H2 W2    (N = 16)                         -> +b2 -> Gaussian log-prob / clipped
+//   gather X k-blocks (cp.async by row index, SW128) -> 4 slots in R1 (streamed for obs_dim > 256)
+//   L1   acc0 = X  W0    (W0 half-k-blocks streamed by TMA)     -> +b0, act, bf16 -> R0 (H1) -> TMA store
+//   L2   acc1 = H1 W1                                           -> +b1, act, bf16 -> R1 (H2)
+//   head out  = H2 W2    (N = 2 AP: bf16 hi | lo)               -> +b2 -> Gaussian log-prob / clipped
 //        surrogate (actor CTA) or clipped value loss (critic CTA), train.py:218-243 -> g = dL/dout
-//   bwd  dA2  = g W2^T   (K = 16),  dW2 = H2^T g (N = 16) -> dZ2 = dA2 * f'(H2) in place -> TMA store
-//   dH1  acc1 = dZ2 W1                                    -> * f'(H1), bf16 -> R1 (dZ1) -> TMA store
+//   bwd  dA2  = g W2^T   (K = AP),  dW2 = H2^T g (N = 2 AP)     -> dZ2 = dA2 * f'(H2) in place -> TMA store
+//   dH1  acc1 = dZ2 W1^T (two N halves)                         -> * f'(H1), bf16 -> R1 (dZ1) -> TMA store
+//   bias gradients: column sums of dZ2 / dZ1 as dZ^T x ones (N = 16) MMAs -> per-tile partials
 //
 // The output-head operands W2 and g are fp32 quantities: they enter the tensor cores as a bf16
 // hi/lo pair (x = hi + lo to 2^-17), the cross terms hi*hi + hi*lo + lo*hi are accumulated in
 // fp32, so the heads keep fp32-level accuracy while costing a few dozen tiny UMMAs.
 //
-// Warp roles: warps 0..7 workers (gather, epilogues, loss), two per TMEM lane quadrant; warp 8 TMA
-// producer (weight k-blocks through a 2-stage ring); warp 9 TMEM allocator + MMA issuer.  H1, dZ2 and dZ1 are also written to HBM (bf16, TMA stores) for the split-K
-// weight-gradient GEMM (umma_gemm.cuh, EPI_PARTIAL), which runs as its own launch over all tiles.
+// Shapes: any obs_dim (Dp = ceil(D / 64) * 64 columns, k-blocks streamed through 4 slots), act_dim <= 32
+// (template AP = 16 or 32: padded head width), hidden_size a multiple of 64 up to 256 (two 128 x 256 fp32
+// accumulators fill the 512 TMEM columns; 512-wide layers would need N-halved accumulators and are refused).
+//
+// Warp roles: warps 0..15 workers (gather, epilogues, loss), FOUR per TMEM lane quadrant -- a worker warp owns 16 of every
+// 64 accumulator columns, so each scheduler has four epilogue warps to hide the tcgen05.ld / MUFU / st.shared latencies
+// behind; warp 16 TMA producer (weight stages of 16 KB through a ring); warp 17 TMEM allocator + MMA issuer.
+// H1, dZ2, dZ1 (and, for Dp <= 256, the gathered X rows) are also written to HBM (bf16, TMA stores) for the split-K
+// weight-gradient GEMM (dwopt.cuh), which runs as its own launch over all tiles.
 #pragma once
 
 #include "common.cuh"
@@ -28,44 +35,58 @@
 
 namespace minppo {
 
-constexpr int FS_THREADS = 320;
-constexpr int FS_WORKERS = 256;                         // warps 0..7
-constexpr int FS_TMA_WARP = 8;                          // weight producer
-constexpr int FS_MMA_WARP = 9;                          // TMEM allocator + MMA issuer: the highest warp id wins the
+constexpr int FS_THREADS = 576;
+constexpr int FS_WORKERS = 512;                         // warps 0..15
+constexpr int FS_NWW = 16;
+constexpr int FS_TMA_WARP = 16;                         // weight producer
+constexpr int FS_MMA_WARP = 17;                         // TMEM allocator + MMA issuer: the highest warp id wins the
                                                         // issue arbiter, so the single issuing thread is never starved
-constexpr int FS_AP = 16;                               // padded head width (A <= 16)
-constexpr int FS_R0 = 0;                                // H1                  64 KB
-constexpr int FS_R1 = 65536;                            // X / H2 / dZ2 / dZ1  64 KB
-constexpr int FS_RB = 131072;                           // weight ring   2 x 32 KB
-constexpr int FS_BSTAGE = 32768;
-constexpr int FS_W2T = 196608;                          // head kernel^T bf16 [32][H] SW128: rows 0..15 hi, 16..31 lo; 4 KB per 64 columns
-constexpr int FS_GT = FS_W2T + 16384;                   // g^T bf16 [32][128] SW128: rows 0..15 hi, 16..31 lo; 4 KB per 64 rows
-constexpr int FS_BIAS = FS_GT + 8192;                   // [2][256] f32
-constexpr int FS_HB = FS_BIAS + 2048;                   // f32: head bias [16], log_std [16], 1/scale [16], log-det [1]
-constexpr int FS_RED = FS_HB + 256;                     // [8][40] f32
-constexpr int FS_BARS = FS_RED + 8 * 40 * 4;            // mbarriers + tmem slot
-constexpr int FS_SMEM_BYTES = FS_BARS + 256 + 1024;     // + alignment slack
+constexpr int FS_STAGE = 16384;                         // one weight stage: [32 k][H n] (forward, MN-major B: H/64 boxes of 4 KB)
+                                                        // or [H/2 n][64 k] (dH1, K-major B)
+constexpr int FS_XSLOTS = 4;                            // X k-block slots in R1 (16 KB each)
+constexpr int FS_MAX_AP = 32;
+
+template <int AP>
+struct FsLayout {
+  static constexpr int NS = AP == 16 ? 4 : 2;           // ring stages (L2 / dH1 weight streams)
+  static constexpr int NS1 = NS + 4;                    // L1 only: four more stages parked in R0 (free until epilogue 1)
+  static constexpr int PG = 2 * AP * 128;               // bytes of one 64-column panel of W2T / GT: [2 AP rows][128 B], rows = hi | lo
+  static constexpr int R0 = 0;                          // H1                  64 KB
+  static constexpr int R1 = 65536;                      // X / H2 / dZ2 / dZ1  64 KB
+  static constexpr int RB = 131072;                     // weight ring
+  static constexpr int W2T = RB + NS * FS_STAGE;        // head kernel^T bf16 hi / lo, SW128, 4 panels (H <= 256)
+  static constexpr int GT = W2T + 4 * PG;               // g^T bf16 hi / lo, SW128, 2 panels (128 rows)
+  static constexpr int ONES = GT + 2 * PG;              // all-ones bf16 [16 n][128 k] (K-major B of the bias-gradient MMAs)
+  static constexpr int BIAS = ONES + 4096;              // [2][256] f32
+  static constexpr int HB = BIAS + 2048;                // f32: head bias [AP], log_std [AP], 1/scale [AP], log-det [1]
+  static constexpr int RS = 2 * AP + 8;                 // floats per loss warp in RED
+  static constexpr int RED = HB + 512;                  // [4][RS] f32
+  static constexpr int BARS = RED + 4 * RS * 4;         // mbarriers + tmem slot
+  static constexpr int BYTES = BARS + 512 + 1024;       // + alignment slack
+};
+static_assert(FsLayout<16>::BYTES <= 232448 && FsLayout<32>::BYTES <= 232448, "fused step: shared memory budget");
 
 struct alignas(64) FusedNet {
-  CUtensorMap tm_w0;             // W0 image [Dp][H] (as stored: [in][out])  box {64 out, 64 in}: MN-major B of L1
-  CUtensorMap tm_w1;             // W1 image [H][H]                          box {64 out, 64 in}: MN-major B of L2
-  CUtensorMap tm_w1k;            // W1 image [H][H]                          box {64 out, H in}:  K-major  B of dH1 (n = in, k = out)
+  CUtensorMap tm_w0;             // W0 image [Dp][H] (as stored: [in][out])  box {64 out, 32 in}: MN-major B of L1
+  CUtensorMap tm_w1;             // W1 image [H][H]                          box {64 out, 32 in}: MN-major B of L2
+  CUtensorMap tm_w1k;            // W1 image [H][H]                          box {64 out, H/2 in}: K-major B of dH1 (n = in, k = out)
   CUtensorMap tm_h1;             // act[1] [M_pad][H]    box {64, 128}  (TMA store)
   CUtensorMap tm_dz2;            // dz[2]
   CUtensorMap tm_dz1;            // dz[1]
   const float* b0;               // arena pointers
   const float* b1;
-  const uint4* w2img;            // head kernel^T as bf16 hi / lo, the 16 KB smem image of FS_W2T (written by the optimizer)
+  const uint4* w2img;            // head kernel^T as bf16 hi / lo, the shared-memory image of FsLayout::W2T (written by the optimizer)
   const float* b2;               // head bias [aout]
   int act;                       // ACT_*
   int aout;                      // A (actor) or 1 (critic)
-  int po_w2, po_b2, po_loss;     // offsets of this net's fields inside a head partial
+  int po_w2, po_b2, po_loss;     // offsets of this net's fields inside a per-tile partial
+  int po_db0, po_db1;            // ... hidden bias gradients (column sums of dZ1 / dZ2), H floats each
 };
 
 struct alignas(64) FusedParams {
   FusedNet net[2];
-  CUtensorMap tm_xg;             // gathered observation rows [M_pad][Dp], box {64, 128}: TMA store by the actor CTAs,
-                                 // the A operand of both nets' first-layer weight-gradient GEMM
+  CUtensorMap tm_xg;             // gathered observation rows [M_pad][Dp], box {64, 128}: TMA store by the critic CTAs,
+                                 // the A operand of both nets' first-layer weight-gradient GEMM (store_x only)
   const int32_t* rowidx;         // [cap] (this minibatch)
   const __nv_bfloat16* obs_img;  // [Bl][Dp]
   const int32_t* count;
@@ -77,16 +98,17 @@ struct alignas(64) FusedParams {
   const float* adv;
   const float* tgt;
   const float* log_std;          // arena pointer
-  float* part;                   // head partials [m_tiles][part_stride]
+  float* part;                   // per-tile partials [m_tiles][part_stride]
   int part_stride, po_logstd;
   int H, A, Dp, m_tiles, cap;
+  int store_x;                   // 1: Dp <= 256, the X tile is stored for the dW GEMM (else that GEMM gathers by index itself)
   float inv_mb, clip_eps, vf_coef;
   long long* trace;              // debug: [ctas][32] clock64 stamps (null = off)
 };
 
 #define FS_STAMP(slot) do { if (p.trace) p.trace[static_cast<size_t>(cta_id) * 32 + (slot)] = clock64(); } while (0)
 
-MINPPO_DEVINL void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+MINPPO_DEVINL void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 MINPPO_DEVINL void sts_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<uint16_t>(v)) : "memory");
@@ -102,9 +124,23 @@ MINPPO_DEVINL void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// TMEM -> registers: 32 lanes x 1 column
+MINPPO_DEVINL float tmem_ld_32x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return __uint_as_float(r);
+}
 // byte offset of the 16-byte chunk holding column c of row r inside a [128][H] bf16 SW128 tile set
 MINPPO_DEVINL uint32_t sw_off(int r, int c) {
   return static_cast<uint32_t>((c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4));
+}
+// cp.async.wait_group with a run-time bound (waiting for fewer pending groups than allowed is always safe)
+MINPPO_DEVINL void cp_async_wait_dyn(int n) {
+  if (n <= 0) cp_async_wait<0>();
+  else if (n == 1) cp_async_wait<1>();
+  else if (n == 2) cp_async_wait<2>();
+  else if (n == 3) cp_async_wait<3>();
+  else cp_async_wait<4>();
 }
 template <int ACT>
 MINPPO_DEVINL float act_apply(float x) {
@@ -117,23 +153,23 @@ MINPPO_DEVINL float act_deriv_t(float h) { return ACT == ACT_RELU ? (h > 0.f ? 1
 MINPPO_DEVINL float dclip_f(float x, float lo, float hi) {
   return (x > lo && x < hi) ? 1.f : ((x == lo || x == hi) ? 0.5f : 0.f);
 }
-// accumulator (32 columns per chunk) -> +bias, activation, bf16 -> swizzled smem tile
-// (not inlined: epilogue 1 and 2 share one copy of the code -- the kernel's straight-line worker path is larger than
-//  the instruction cache, and "no instruction" was a quarter of its stall samples)
+// accumulator (16 columns per chunk) -> +bias, activation, bf16 -> swizzled smem tile
+// (not inlined: the epilogues share one copy of the code per activation -- the kernel's straight-line worker path is
+//  larger than the instruction cache otherwise)
 template <int ACT>
 __device__ __noinline__ void epilogue_act_t(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int row, int q, int col0,
-                                  int ncols) {
+                                            int ncols) {
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-  for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
-    float v[32];
-    tmem_ld_32x32(taddr + c0, v);
+  for (int c0 = col0; c0 < col0 + ncols; c0 += 16) {
+    float v[16];
+    tmem_ld_32x16(taddr + c0, v);
     const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);     // broadcast LDS.128
-    float4 bb[8];
+    float4 bb[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) bb[j] = b4[j];
+    for (int j = 0; j < 4; ++j) bb[j] = b4[j];
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2; ++j) {
       uint32_t w[4];
       const float bj[8] = {bb[2 * j].x, bb[2 * j].y, bb[2 * j].z, bb[2 * j].w,
                            bb[2 * j + 1].x, bb[2 * j + 1].y, bb[2 * j + 1].z, bb[2 * j + 1].w};
@@ -157,20 +193,20 @@ MINPPO_DEVINL void epilogue_act(uint32_t tmem_acc, uint32_t dst_base, const floa
 
 // dZ = acc * f'(h): h read from `h_base`, bf16 result written to `dst_base` (may alias h_base:
 // every thread touches only its own 16-byte chunks).  The bias gradients (column sums of dZ) are
-// not formed here: the weight-gradient GEMM gets them from the tensor core as ones x dZ.
+// not formed here: they come from the tensor core as dZ^T x ones.
 template <int ACT>
 __device__ __noinline__ void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, int row, int q, int col0,
-                                   int ncols) {
+                                             int ncols) {
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-  for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
-    float v[32];
-    tmem_ld_32x32(taddr + c0, v);
-    uint4 hh[4];
+  for (int c0 = col0; c0 < col0 + ncols; c0 += 16) {
+    float v[16];
+    tmem_ld_32x16(taddr + c0, v);
+    uint4 hh[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) hh[j] = lds128(h_base + sw_off(row, c0 + 8 * j));
+    for (int j = 0; j < 2; ++j) hh[j] = lds128(h_base + sw_off(row, c0 + 8 * j));
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2; ++j) {
       const uint32_t hw[4] = {hh[j].x, hh[j].y, hh[j].z, hh[j].w};
       uint32_t w[4];
 #pragma unroll
@@ -188,30 +224,38 @@ MINPPO_DEVINL void epilogue_dact(uint32_t tmem_acc, uint32_t h_base, uint32_t ds
   else epilogue_dact_t<ACT_TANH>(tmem_acc, h_base, dst_base, row, q, col0, ncols);
 }
 
+template <int AP>
 __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_constant__ FusedParams p) {
+  using LY = FsLayout<AP>;
+  constexpr int NS = LY::NS, NS1 = LY::NS1, PG = LY::PG, RS = LY::RS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  float* bias_s = reinterpret_cast<float*>(sm + FS_BIAS);       // [0..256) layer 0, [256..512) layer 1
-  float* hb = reinterpret_cast<float*>(sm + FS_HB);             // [0..16) head bias, [16..32) log_std,
-                                                                // [32..48) 1 / scale, [48] sum log|scale|
-  float* red = reinterpret_cast<float*>(sm + FS_RED);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + FS_BARS);
-  uint64_t* full_bar = bars;            // [2]
-  uint64_t* empty_bar = bars + 2;       // [2]
-  uint64_t* accf0 = bars + 4;           // L1 accumulator complete
-  uint64_t* accf1 = bars + 5;           // L2 accumulator complete
-  uint64_t* headf = bars + 6;           // head outputs complete
-  uint64_t* bwdf = bars + 7;            // dA2 and dW2 complete
-  uint64_t* dh1f = bars + 8;            // dH1 accumulator complete
-  uint64_t* xfull = bars + 9;           // workers -> MMA: X tile gathered
-  uint64_t* h2r = bars + 10;            // H2 in R1, acc1 drained
-  uint64_t* gr = bars + 11;             // g^T hi/lo written
-  uint64_t* h1r = bars + 12;            // [4] H1 columns [64 b, 64 b + 64) in R0 (k-block b of the L2 GEMM)
-  uint64_t* dz2r = bars + 16;           // [4] dZ2 columns [64 b, 64 b + 64) in R1 (k-block b of the dH1 GEMM)
-  uint64_t* w0x = bars + 20;            // [2] W0 k-blocks 2, 3 parked in R0 (free until epilogue 1)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  float* bias_s = reinterpret_cast<float*>(sm + LY::BIAS);      // [0..256) layer 0, [256..512) layer 1
+  float* hb = reinterpret_cast<float*>(sm + LY::HB);            // [0, AP) head bias, [AP, 2AP) log_std,
+                                                                // [2AP, 3AP) 1 / scale, [3AP] sum log|scale|
+  float* red = reinterpret_cast<float*>(sm + LY::RED);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + LY::BARS);
+  uint64_t* l1_full = bars;             // [8] W0 half-k-block landed (TMA)
+  uint64_t* l1_empty = bars + 8;        // [8] ... consumed (MMA commit)
+  uint64_t* x_full = bars + 16;         // [4] X k-block gathered (16 worker warps)
+  uint64_t* x_empty = bars + 20;        // [4] ... consumed (MMA commit)
+  uint64_t* full_bar = bars + 24;       // [4] ring stage landed
+  uint64_t* empty_bar = bars + 28;      // [4] ring stage consumed
+  uint64_t* accf0 = bars + 32;          // L1 accumulator complete
+  uint64_t* accf1 = bars + 33;          // L2 accumulator complete
+  uint64_t* headf = bars + 34;          // head outputs complete
+  uint64_t* bwdf = bars + 35;           // dA2 and dW2 complete
+  uint64_t* dh1f = bars + 36;           // dH1 accumulator complete
+  uint64_t* cs2f = bars + 37;           // column sums of dZ2 complete
+  uint64_t* cs1f = bars + 38;           // column sums of dZ1 complete
+  uint64_t* h2r = bars + 39;            // H2 in R1, acc1 drained
+  uint64_t* gr = bars + 40;             // g^T hi/lo written
+  uint64_t* h1r = bars + 41;            // [4] H1 columns [64 b, 64 b + 64) in R0 (k-block b of the L2 GEMM)
+  uint64_t* dz2r = bars + 45;           // [4] dZ2 columns [64 b, 64 b + 64) in R1 (k-block b of the dH1 GEMM)
+  uint64_t* dz1r = bars + 49;           // [4] dZ1 columns [64 b, 64 b + 64) in R1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 56);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA order: (tile, net) with net fastest, so that the LIVE tiles of both nets are the lowest block indices and fit the
@@ -221,8 +265,10 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   const int cta_id = net * p.m_tiles + tile;             // trace row (net-major, scripts/trace_fused.py)
   const FusedNet& G = p.net[net];
   const int H = p.H, nkH = H >> 6, nk0 = p.Dp >> 6;
-  const uint32_t R0 = base + FS_R0, R1 = base + FS_R1, RB = base + FS_RB;
-  const uint32_t W2T = base + FS_W2T, GT = base + FS_GT;
+  const int mtH = (H + 127) >> 7;                        // 128-column tiles of a hidden layer
+  const uint32_t R0 = base + LY::R0, R1 = base + LY::R1, RB = base + LY::RB;
+  const uint32_t W2T = base + LY::W2T, GT = base + LY::GT, ONES = base + LY::ONES;
+  auto l1_stage = [&](int s) -> uint32_t { return s < NS ? RB + s * FS_STAGE : R0 + (s - NS) * FS_STAGE; };
 
   // Env-sharded ranks size the row lists for the worst case (learner.cu: 1.5 x the mean + 256 rows); the tiles
   // beyond this minibatch's actual row count have nothing to do except zeroing their partial sums.
@@ -230,6 +276,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     griddep_wait();                                     // the previous optimizer step may still be reading the partials
     float* part = p.part + static_cast<size_t>(tile) * p.part_stride;
     for (int i = threadIdx.x; i < H * G.aout; i += FS_THREADS) part[G.po_w2 + i] = 0.f;
+    for (int i = threadIdx.x; i < H; i += FS_THREADS) { part[G.po_db0 + i] = 0.f; part[G.po_db1 + i] = 0.f; }
     if (static_cast<int>(threadIdx.x) < G.aout) part[G.po_b2 + threadIdx.x] = 0.f;
     if (net == 0 && static_cast<int>(threadIdx.x) < G.aout) part[p.po_logstd + threadIdx.x] = 0.f;
     if (threadIdx.x == 0) part[G.po_loss] = 0.f;
@@ -237,13 +284,15 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   }
   if (threadIdx.x == FS_WORKERS) {
     FS_STAMP(16);
-    mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
-    mbar_init(&empty_bar[0], 1); mbar_init(&empty_bar[1], 1);
+    for (int s = 0; s < 8; ++s) { mbar_init(&l1_full[s], 1); mbar_init(&l1_empty[s], 1); }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&x_full[s], FS_NWW); mbar_init(&x_empty[s], 1);
+      mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
+      mbar_init(&h1r[s], FS_NWW); mbar_init(&dz2r[s], FS_NWW); mbar_init(&dz1r[s], FS_NWW);
+    }
     mbar_init(accf0, 1); mbar_init(accf1, 1); mbar_init(headf, 1); mbar_init(bwdf, 1); mbar_init(dh1f, 1);
-    mbar_init(xfull, FS_WORKERS);
-    mbar_init(h2r, 8); mbar_init(gr, 8);
-    for (int b = 0; b < 4; ++b) { mbar_init(&h1r[b], 8); mbar_init(&dz2r[b], 8); }
-    mbar_init(&w0x[0], 1); mbar_init(&w0x[1], 1);
+    mbar_init(cs2f, 1); mbar_init(cs1f, 1);
+    mbar_init(h2r, FS_NWW); mbar_init(gr, FS_NWW);
     fence_mbar_init();
   }
   if (warp == FS_MMA_WARP) {
@@ -255,193 +304,261 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256;
-  const uint32_t acc_head = acc1;               // [256, 288): head outputs, hi | lo halves (after acc1 is drained)
-  const uint32_t acc_dw = acc1 + 32;            // [288, 288 + 32 * ceil(H/128)): head-kernel gradient, hi | lo halves
+  const uint32_t acc_head = acc1;               // [256, 256 + 2AP): head outputs, hi | lo halves (after acc1 is drained)
+  const uint32_t acc_dw = acc1 + 2 * AP;        // + 2AP per 128-column tile of H: head-kernel gradient, hi | lo halves
+  const uint32_t acc_cs2 = acc0;                // + 16 per 128-column tile: column sums of dZ2 (after acc0 = dA2 is drained)
+  const uint32_t acc_cs1 = acc0 + 32;           // + 16 per 128-column tile: column sums of dZ1
 
   if (warp == FS_TMA_WARP) {
-    // ===================== weight producer: W0^T, W1^T, W1 k-blocks through the ring ==========
+    // ===================== weight producer ======================================================================
     if (elect_one()) {
       tma_prefetch_desc(&G.tm_w0); tma_prefetch_desc(&G.tm_w1); tma_prefetch_desc(&G.tm_w1k);
       griddep_wait();                 // the weight images are rewritten by the previous optimizer step
-      const uint32_t bytes = static_cast<uint32_t>(H) * 128u;
-      // Ring items: W0 k-blocks 0, 1, then W1 (L2), then W1 (dH1).  W0 k-blocks 2.. do not wait for a ring slot:
-      // they are parked in R0, which nothing touches before epilogue 1, so the whole L1 GEMM is fed up front.
-      const int nring0 = nk0 < 2 ? nk0 : 2;
-      const int total = nring0 + 2 * nkH;
+      const uint32_t bytes = static_cast<uint32_t>(H) * 64u;
+      // ---- L1: W0 half-k-blocks j = 0 .. 2 nk0 - 1 through NS1 stages (the ring + four stages parked in R0, which nothing
+      //      touches before epilogue 1: for Dp <= 256 the whole L1 GEMM is fed up front)
+      const int n1 = 2 * nk0;
+      for (int j = 0; j < n1; ++j) {
+        const int s = j % NS1;
+        if (j >= NS1) mbar_wait(&l1_empty[s], ((j / NS1) - 1) & 1);
+        mbar_arrive_expect_tx(&l1_full[s], bytes);
+        const uint32_t dst = l1_stage(s);
+        for (int c = 0; c < nkH; ++c) tma_load_2d(dst + c * 4096, &G.tm_w0, &l1_full[s], c * 64, j * 32);
+      }
+      // ---- ring: W1 half-k-blocks of L2 (MN-major), then W1 (k-block, N half) items of dH1 (K-major)
+      const int n2 = 2 * nkH, total = 4 * nkH;
       for (int i = 0; i < total; ++i) {
-        const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        if (i < nring0 + nkH) {         // forward: k-block of W0 / W1 as stored, one {64 out, 64 in} box per 64 outputs
-          const CUtensorMap* m = i < nring0 ? &G.tm_w0 : &G.tm_w1;
-          const int kb = i < nring0 ? i : i - nring0;
-          for (int c = 0; c < nkH; ++c) tma_load_2d(RB + s * FS_BSTAGE + c * 8192, m, &full_bar[s], c * 64, kb * 64);
-        } else {                        // dH1: k-block (64 outputs) of W1 for all H inputs
-          tma_load_2d(RB + s * FS_BSTAGE, &G.tm_w1k, &full_bar[s], (i - nring0 - nkH) * 64, 0);
+        const int s = i % NS;
+        if (i < NS) {
+          // first pass over the ring: stage s may still hold a W0 half-k-block -- wait for L1's LAST use of it
+          int jl = -1;
+          for (int j = s; j < n1; j += NS1) jl = j;
+          if (jl >= 0) mbar_wait(&l1_empty[s], (jl / NS1) & 1);
+        } else {
+          mbar_wait(&empty_bar[s], ((i / NS) - 1) & 1);
         }
-        if (i == nring0 - 1) {
-          for (int kb = 2; kb < nk0; ++kb) {
-            mbar_arrive_expect_tx(&w0x[kb - 2], bytes);
-            for (int c = 0; c < nkH; ++c) tma_load_2d(R0 + (kb - 2) * FS_BSTAGE + c * 8192, &G.tm_w0, &w0x[kb - 2], c * 64, kb * 64);
-          }
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        const uint32_t dst = RB + s * FS_STAGE;
+        if (i < n2) {
+          for (int c = 0; c < nkH; ++c) tma_load_2d(dst + c * 4096, &G.tm_w1, &full_bar[s], c * 64, i * 32);
+        } else {
+          const int ii = i - n2;
+          tma_load_2d(dst, &G.tm_w1k, &full_bar[s], (ii >> 1) * 64, (ii & 1) * (H >> 1));
         }
       }
     }
   } else if (warp == FS_MMA_WARP) {
-    // ===================== MMA issuer ==========================================================
+    // ===================== MMA issuer ===========================================================================
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(H), 0u, 0u);
-      int i = 0;
-      // a_ready: per-k-block barriers of the A operand (the epilogue that produces A publishes it in
-      // 64-column blocks, so this GEMM starts while the previous epilogue is still running)
       const uint32_t idesc_bmn = umma_idesc_bf16(128, static_cast<uint32_t>(H), 0u, 1u);     // B as stored: MN-major
-      auto gemm = [&](uint32_t a_base, int nk, uint32_t acc, uint64_t* a_ready, bool b_mn) {
-        for (int kb = 0; kb < nk; ++kb, ++i) {
-          const int s = i & 1;
-          const uint32_t ph = (i >> 1) & 1;
-          if (a_ready) mbar_wait_spin(&a_ready[kb], 0);
-          mbar_wait_spin(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = a_base + kb * 16384, sb = RB + s * FS_BSTAGE;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            umma_bf16(acc, umma_smem_desc(sa + j * 32, 16, 1024),
-                      b_mn ? umma_smem_desc(sb + j * 2048, 8192, 1024) : umma_smem_desc(sb + j * 32, 16, 1024),
-                      b_mn ? idesc_bmn : idesc, (kb > 0 || j > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
-        }
-      };
       FS_STAMP(17);
-      mbar_wait_spin(xfull, 0);
-      tc_fence_after();
-      FS_STAMP(18);
-      gemm(R1, nk0 < 2 ? nk0 : 2, acc0, nullptr, true);    // L1: X W0, k-blocks 0, 1 from the ring
-      for (int kb = 2; kb < nk0; ++kb) {                   // ... k-blocks 2, 3 parked in R0
-        mbar_wait_spin(&w0x[kb - 2], 0);
-        tc_fence_after();
-        const uint32_t sa = R1 + kb * 16384, sb = R0 + (kb - 2) * FS_BSTAGE;
+      // ---- L1: acc0 = X W0 -------------------------------------------------------------------------------------
+      for (int kb = 0; kb < nk0; ++kb) {
+        const int xs = kb & 3;
+        mbar_wait_spin(&x_full[xs], (kb >> 2) & 1);
+        if (kb == 0) FS_STAMP(18);
+        for (int hb2 = 0; hb2 < 2; ++hb2) {
+          const int j = 2 * kb + hb2, s = j % NS1;
+          mbar_wait_spin(&l1_full[s], (j / NS1) & 1);
+          tc_fence_after();
+          const uint32_t sa = R1 + xs * 16384 + hb2 * 64, sb = l1_stage(s);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          umma_bf16(acc0, umma_smem_desc(sa + j * 32, 16, 1024), umma_smem_desc(sb + j * 2048, 8192, 1024), idesc_bmn, 1u);
+          for (int jj = 0; jj < 2; ++jj)
+            umma_bf16(acc0, umma_smem_desc(sa + jj * 32, 16, 1024), umma_smem_desc(sb + jj * 2048, 4096, 1024), idesc_bmn,
+                      (j > 0 || jj > 0) ? 1u : 0u);
+          umma_commit(&l1_empty[s]);
+        }
+        umma_commit(&x_empty[xs]);
       }
       umma_commit(accf0);
       FS_STAMP(19);
-      FS_STAMP(20);
-      gemm(R0, nkH, acc1, h1r, true);        // L2: H1 W1
+      // ---- L2: acc1 = H1 W1; the A k-blocks are published by epilogue 1 in 64-column blocks ---------------------------
+      int i = 0;
+      for (int kb = 0; kb < nkH; ++kb) {
+        mbar_wait_spin(&h1r[kb], 0);
+        for (int hb2 = 0; hb2 < 2; ++hb2, ++i) {
+          const int s = i % NS;
+          mbar_wait_spin(&full_bar[s], (i / NS) & 1);
+          tc_fence_after();
+          const uint32_t sa = R0 + kb * 16384 + hb2 * 64, sb = RB + s * FS_STAGE;
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+            umma_bf16(acc1, umma_smem_desc(sa + jj * 32, 16, 1024), umma_smem_desc(sb + jj * 2048, 4096, 1024), idesc_bmn,
+                      (i > 0 || jj > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+      }
       umma_commit(accf1);
       FS_STAMP(21);
-      // ---- head forward: [out_hi | out_lo][128 x 32] = H2 [W2_hi | W2_lo]; A = H2 K-major, B = W2^T K-major with the
-      //      bf16 hi / lo halves stacked along N (the workers add the two 16-column halves)
+      // ---- head forward: [out_hi | out_lo][128 x 2AP] = H2 [W2_hi | W2_lo]; A = H2 K-major, B = W2T K-major with the
+      //      bf16 hi / lo halves stacked along N (the workers add the two halves)
       mbar_wait_spin(h2r, 0);
       tc_fence_after();
       {
-        const uint32_t idesc_h = umma_idesc_bf16(128, 32u, 0u, 0u);
+        const uint32_t idesc_h = umma_idesc_bf16(128, 2u * AP, 0u, 0u);
         uint32_t accum = 0;
         for (int kb = 0; kb < nkH; ++kb)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             umma_bf16(acc_head, umma_smem_desc(R1 + kb * 16384 + j * 32, 16, 1024),
-                      umma_smem_desc(W2T + kb * 4096 + j * 32, 16, 1024), idesc_h, accum);
+                      umma_smem_desc(W2T + kb * PG + j * 32, 16, 1024), idesc_h, accum);
             accum = 1;
           }
         umma_commit(headf);
       }
       FS_STAMP(24);
-      // ---- backward through the head --------------------------------------------------------------
+      // ---- backward through the head ---------------------------------------------------------------------------------
       mbar_wait_spin(gr, 0);
       tc_fence_after();
       {
-        // dA2[128 x H] = g W2^T, K = 16: A = g^T (MN-major, 64-row panels 4 KB apart), B = W2^T (MN-major, 64-column
-        // panels 4 KB apart); the lo halves sit 16 rows = 2 KB into each panel
+        // dA2[128 x H] = g W2^T, K = AP: A = g^T (MN-major, 64-row panels PG apart), B = W2T (MN-major, 64-column
+        // panels PG apart); 16 rows of K per MMA (2 KB); the lo halves sit AP rows into each panel
         const uint32_t idesc_a = umma_idesc_bf16(128, static_cast<uint32_t>(H), 1u, 1u);
-        umma_bf16(acc0, umma_smem_desc(GT, 4096, 1024), umma_smem_desc(W2T, 4096, 1024), idesc_a, 0u);            // hi * hi
-        umma_bf16(acc0, umma_smem_desc(GT, 4096, 1024), umma_smem_desc(W2T + 2048, 4096, 1024), idesc_a, 1u);     // hi * lo
-        umma_bf16(acc0, umma_smem_desc(GT + 2048, 4096, 1024), umma_smem_desc(W2T, 4096, 1024), idesc_a, 1u);     // lo * hi
-        // [dW2_hi | dW2_lo][c][j] = sum_r H2[r][c] g[r][j]: A = H2 (MN-major: M = c, K = rows), B = g^T (K-major, N = 32)
-        const uint32_t idesc_w = umma_idesc_bf16(128, 32u, 1u, 0u);
-        for (int mh = 0; mh < (H + 127) / 128; ++mh) {
+        uint32_t accum = 0;
+#pragma unroll
+        for (int ks = 0; ks < AP / 16; ++ks) {
+          const uint32_t ghi = GT + ks * 2048, glo = GT + AP * 128 + ks * 2048;
+          const uint32_t whi = W2T + ks * 2048, wlo = W2T + AP * 128 + ks * 2048;
+          umma_bf16(acc0, umma_smem_desc(ghi, PG, 1024), umma_smem_desc(whi, PG, 1024), idesc_a, accum);       // hi * hi
+          umma_bf16(acc0, umma_smem_desc(ghi, PG, 1024), umma_smem_desc(wlo, PG, 1024), idesc_a, 1u);          // hi * lo
+          umma_bf16(acc0, umma_smem_desc(glo, PG, 1024), umma_smem_desc(whi, PG, 1024), idesc_a, 1u);          // lo * hi
+          accum = 1;
+        }
+        // [dW2_hi | dW2_lo][c][j] = sum_r H2[r][c] g[r][j]: A = H2 (MN-major: M = c, K = rows), B = g^T (K-major, N = 2AP)
+        const uint32_t idesc_w = umma_idesc_bf16(128, 2u * AP, 1u, 0u);
+        for (int mh = 0; mh < mtH; ++mh) {
 #pragma unroll
           for (int t = 0; t < 8; ++t)
-            umma_bf16(acc_dw + 32 * mh, umma_smem_desc(R1 + 2 * mh * 16384 + t * 2048, 16384, 1024),
-                      umma_smem_desc(GT + (t >> 2) * 4096 + (t & 3) * 32, 16, 1024), idesc_w, t > 0 ? 1u : 0u);
+            umma_bf16(acc_dw + 2 * AP * mh, umma_smem_desc(R1 + 2 * mh * 16384 + t * 2048, 16384, 1024),
+                      umma_smem_desc(GT + (t >> 2) * PG + (t & 3) * 32, 16, 1024), idesc_w, t > 0 ? 1u : 0u);
         }
         umma_commit(bwdf);
       }
       FS_STAMP(25);
-      FS_STAMP(22);
-      // accumulates into acc1: every worker warp has read the head / dW2 columns of acc1 before its first
-      // arrival on dz2r[0], while acc0 (dA2) is still being drained by the dZ2 epilogue
-      gemm(R1, nkH, acc1, dz2r, false);      // dH1: dZ2 W1^T
-      umma_commit(dh1f);
+      // ---- dH1: acc1 = dZ2 W1^T in two N halves.  Accumulates into acc1: every worker warp has read the head / dW2
+      //      columns of acc1 before its first arrival on dz2r[0], while acc0 (dA2) is still being drained by the dZ2 epilogue
+      {
+        const uint32_t idesc_h2 = umma_idesc_bf16(128, static_cast<uint32_t>(H >> 1), 0u, 0u);
+        for (int kb = 0; kb < nkH; ++kb) {
+          mbar_wait_spin(&dz2r[kb], 0);
+          for (int nh = 0; nh < 2; ++nh, ++i) {
+            const int s = i % NS;
+            mbar_wait_spin(&full_bar[s], (i / NS) & 1);
+            tc_fence_after();
+            const uint32_t sa = R1 + kb * 16384, sb = RB + s * FS_STAGE;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              umma_bf16(acc1 + nh * (H >> 1), umma_smem_desc(sa + jj * 32, 16, 1024), umma_smem_desc(sb + jj * 32, 16, 1024),
+                        idesc_h2, (kb > 0 || jj > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[s]);
+          }
+        }
+        umma_commit(dh1f);
+      }
       FS_STAMP(23);
+      // ---- bias gradients: column sums of dZ as dZ^T x ones.  A = dZ (MN-major: M = 128 columns c, K = the 128 rows),
+      //      B = ones [16 n][128 k] (K-major); every one of the 16 accumulator columns of row c holds sum_r dZ[r][c].
+      //      dZ2: all of dz2r has been waited for above, so acc0 (dA2) is drained and dZ2 is complete in R1.
+      const uint32_t idesc_cs = umma_idesc_bf16(128, 16u, 1u, 0u);
+      for (int mh = 0; mh < mtH; ++mh)
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          umma_bf16(acc_cs2 + 16 * mh, umma_smem_desc(R1 + 2 * mh * 16384 + t * 2048, 16384, 1024),
+                    umma_smem_desc(ONES + (t >> 2) * 2048 + (t & 3) * 32, 16, 1024), idesc_cs, t > 0 ? 1u : 0u);
+      umma_commit(cs2f);
+      // dZ1: epilogue 3 overwrites R1 block by block (after dh1f: the MMAs above have retired by then)
+      for (int mh = 0; mh < mtH; ++mh) {
+        mbar_wait_spin(&dz1r[2 * mh], 0);
+        if (2 * mh + 1 < nkH) mbar_wait_spin(&dz1r[2 * mh + 1], 0);
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          umma_bf16(acc_cs1 + 16 * mh, umma_smem_desc(R1 + 2 * mh * 16384 + t * 2048, 16384, 1024),
+                    umma_smem_desc(ONES + (t >> 2) * 2048 + (t & 3) * 32, 16, 1024), idesc_cs, t > 0 ? 1u : 0u);
+      }
+      umma_commit(cs1f);
     }
   } else {
-    // ===================== workers ==============================================================
-    const int wt = static_cast<int>(threadIdx.x);               // 0..255
-    const int ww = warp;                                         // 0..7
-    const int q = warp & 3, hf = ww >> 2;
+    // ===================== workers ================================================================================
+    const int wt = static_cast<int>(threadIdx.x);               // 0..511
+    const int q = warp & 3, sub = warp >> 2;                     // TMEM lane quadrant, column share
     const int erow = q * 32 + lane;                              // epilogue row == TMEM lane
     const int act = G.act, aout = G.aout;
-    const int gchunk = wt & 7, grow0 = wt >> 3;                  // gather mapping: 8 lanes per 128-byte line, rows grow0 + 32 g
+    const int gchunk = wt & 7, grow0 = wt >> 3;                  // gather mapping: 8 lanes per 128-byte line, rows grow0 + 64 g
     if (wt == 0) FS_STAMP(0);
 
-    // ---- gather the observation rows of this tile into R1 ---------------------------------------
-    int src_g[4];
+    // ---- gather the observation rows of this tile into the X slots of R1 ---------------------------------------
+    int src_g[2];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) src_g[g] = p.rowidx[tile * 128 + grow0 + 32 * g];
-    const int lrow = tile * 128 + erow;                          // loss row of this thread (hf == 0 warps)
+    for (int g = 0; g < 2; ++g) src_g[g] = p.rowidx[tile * 128 + grow0 + 64 * g];
+    const int lrow = tile * 128 + erow;                          // loss row of this thread (sub == 0 warps)
     const int count = min(*p.count, p.cap);
-    const bool live = (hf == 0) && (lrow < count);
+    const bool live = (sub == 0) && (lrow < count);
     const int src_l = live ? p.rowidx[lrow] : 0;
     // one warp instruction copies 4 rows x 128 contiguous bytes (4 L1 wavefronts; a lane-per-row mapping needed 32)
+    auto gather_block = [&](int kb) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int row = grow0 + 32 * g;
-      const __nv_bfloat16* src = p.obs_img + static_cast<size_t>(src_g[g]) * p.Dp + gchunk * 8;
-      const uint32_t dst = R1 + row * 128 + ((gchunk ^ (row & 7)) << 4);
-      for (int kb = 0; kb < nk0; ++kb) cp_async_16(dst + kb * 16384, src + kb * 64);
-    }
-    cp_async_commit();
+      for (int g = 0; g < 2; ++g) {
+        const int row = grow0 + 64 * g;
+        const __nv_bfloat16* src = p.obs_img + static_cast<size_t>(src_g[g]) * p.Dp + kb * 64 + gchunk * 8;
+        cp_async_16(R1 + (kb & 3) * 16384 + row * 128 + ((gchunk ^ (row & 7)) << 4), src);
+      }
+      cp_async_commit();
+    };
+    const int nb0 = nk0 < FS_XSLOTS ? nk0 : FS_XSLOTS;
+    for (int kb = 0; kb < nb0; ++kb) gather_block(kb);
     if (wt == 0) FS_STAMP(26);
     const float adv_sum = *p.adv_sum, adv_sq = *p.adv_sq;
-    if (wt == 0) FS_STAMP(27);
     // ---- everything below reads what the previous optimizer step wrote (PDL: see common.cuh) -------
     griddep_wait();
     if (wt == 0) griddep_launch();
     if (wt == 0) FS_STAMP(28);
     // ---- small operands: biases, head bias / log_std, head kernel^T image (bf16 hi / lo, swizzled) --
     // (all global loads first: the st.shared wrappers are ordering barriers for the compiler)
-    const float b0v = wt < H ? __ldcg(G.b0 + wt) : 0.f;             // H <= 256 == FS_WORKERS
-    const float b1v = wt < H ? __ldcg(G.b1 + wt) : 0.f;
+    float bv = 0.f;
+    if (wt < 256) bv = wt < H ? __ldcg(G.b0 + wt) : 0.f;
+    else bv = wt - 256 < H ? __ldcg(G.b1 + wt - 256) : 0.f;
     float hbv = 0.f;
-    if (wt < 16) hbv = wt < aout ? __ldcg(G.b2 + wt) : 0.f;
-    else if (wt < 32) hbv = (net == 0 && wt - 16 < aout) ? __ldcg(p.log_std + wt - 16) : 0.f;
-    for (int i = wt; i < 1024; i += FS_WORKERS) cp_async_16(W2T + i * 16, G.w2img + i);
+    if (wt < AP) hbv = wt < aout ? __ldcg(G.b2 + wt) : 0.f;
+    else if (wt < 2 * AP) hbv = (net == 0 && wt - AP < aout) ? __ldcg(p.log_std + wt - AP) : 0.f;
+    for (int i = wt; i < (H * AP) >> 2; i += FS_WORKERS) cp_async_16(W2T + i * 16, G.w2img + i);   // H/64 panels of PG bytes
     cp_async_commit();
-    if (wt == 0) FS_STAMP(29);
-    // the L1 GEMM needs only the gathered rows: publish them before the (slower) staging of the small operands
-    cp_async_wait<1>();
-    fence_proxy_async_smem();
-    mbar_arrive(xfull);
-    if (wt == 0) FS_STAMP(31);
-    if (wt < H) { bias_s[wt] = b0v; bias_s[256 + wt] = b1v; }
-    if (wt < 32) hb[wt] = hbv;
-    if (wt >= 16 && wt < 32) hb[16 + wt] = 1.f / expf(hbv);          // 1 / scale (unused columns: 1)
-    if (net == 0 && wt == 32) {
-      // distrax: log|det| = sum log|scale|, scale = exp(log_std); summed in index order (train.py:223)
-      float ls[FS_AP], logdet = 0.f;
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) ls[j] = j < aout ? __ldcg(p.log_std + j) : 0.f;
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) if (j < aout) logdet += logf(fabsf(expf(ls[j])));
-      hb[48] = logdet;
+    // the L1 GEMM needs only the gathered rows: publish them block by block, before the staging of the small operands;
+    // for Dp > 256 the slots are refilled as the MMAs release them
+    {
+      int issued = nb0 + 1;                                      // cp.async groups committed so far (X blocks, then W2T)
+      for (int kb = 0; kb < nk0; ++kb) {
+        const int idx = kb < FS_XSLOTS ? kb : kb + 1;            // commit order: X0..X3, W2T, X4, X5, ...
+        cp_async_wait_dyn(issued - idx - 1);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_full[kb & 3]);
+        // refill the slot of block kb - 1 (one block behind, so that publishing block kb never waits for an MMA)
+        if (kb >= 1 && kb - 1 + FS_XSLOTS < nk0) {
+          mbar_wait(&x_empty[(kb - 1) & 3], ((kb - 1) >> 2) & 1);
+          gather_block(kb - 1 + FS_XSLOTS);
+          ++issued;
+        }
+      }
     }
+    if (wt == 0) FS_STAMP(31);
+    bias_s[wt] = bv;                                             // [0, 256) layer 0, [256, 512) layer 1
+    if (wt < 2 * AP) hb[wt] = hbv;
+    if (wt >= AP && wt < 2 * AP) hb[AP + wt] = 1.f / expf(hbv);   // 1 / scale (unused columns: 1)
+    if (net == 0 && wt == 2 * AP) {
+      // distrax: log|det| = sum log|scale|, scale = exp(log_std); summed in index order (train.py:223)
+      float logdet = 0.f;
+      for (int j = 0; j < aout; ++j) logdet += logf(fabsf(expf(__ldcg(p.log_std + j))));
+      hb[3 * AP] = logdet;
+    }
+    if (wt >= 256) sts128(ONES + (wt - 256) * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));   // bf16 1.0
     if (wt == 0) FS_STAMP(30);
     cp_async_wait<0>();
+    fence_proxy_async_smem();                                    // W2T / ones -> async proxy (UMMA)
     worker_bar();                                                // biases / hb / W2T visible to all workers; X complete
     if (wt == 0) FS_STAMP(1);
-    if (net == 0 && ww == 0 && lane == 0) {
+    const bool x_store = p.store_x && net == 1 && wt == 0;       // the critic CTA (relu epilogues: the shorter chain) stores X
+    if (x_store) {
       for (int kb = 0; kb < nk0; ++kb) tma_store_2d(R1 + kb * 16384, &p.tm_xg, kb * 64, tile * 128);
       tma_store_commit();
     }
@@ -451,16 +568,16 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     if (wt == 0) FS_STAMP(2);
     // the X store has read R1 before this warp's h1r arrivals let the L2 GEMM (and then epilogue 2, which
     // overwrites R1) proceed
-    if (net == 0 && ww == 0 && lane == 0) tma_store_wait_read0();
+    if (x_store) tma_store_wait_read0();
     for (int b = 0; b < nkH; ++b) {
-      epilogue_act(acc0, R0, bias_s, act, erow, q, b * 64 + hf * 32, 32);
+      epilogue_act(acc0, R0, bias_s, act, erow, q, b * 64 + sub * 16, 16);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&h1r[b]);
     }
     if (wt == 0) FS_STAMP(3);
-    if (ww == 0 && lane == 0) {
+    if (wt == 32) {                                               // warp 1 lane 0: its own arrivals are done
       for (int b = 0; b < nkH; ++b) {
         mbar_wait(&h1r[b], 0);
         tma_store_2d(R0 + b * 16384, &G.tm_h1, b * 64, tile * 128);
@@ -468,75 +585,66 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       tma_store_commit();
     }
 
-    // per-row loss inputs, requested here, in the shadow of the L2 GEMM's tail (32 distinct lines per load
-    // instruction: ~2.5k cycles of load/store-unit time that must not sit in front of a GEMM or an epilogue)
-    float in0 = 0.f, in1 = 0.f, actn[FS_AP];
+    // ---- epilogue 2: H2 = act(acc1 + b1) -> R1 -------------------------------------------------------
+    mbar_wait(accf1, 0);
+    tc_fence_after();
+    if (wt == 0) FS_STAMP(4);
+    epilogue_act(acc1, R1, bias_s + 256, act, erow, q, sub * (H >> 2), H >> 2);
+    fence_proxy_async_smem();                                    // H2 -> async proxy for the head MMAs
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(h2r);
+    if (wt == 0) FS_STAMP(5);
+
+    // per-row loss inputs, requested here, in the shadow of the head MMAs (32 distinct lines per load instruction)
+    float in0 = 0.f, in1 = 0.f, zz[AP];
 #pragma unroll
-    for (int j = 0; j < FS_AP; ++j) actn[j] = 0.f;
+    for (int j = 0; j < AP; ++j) zz[j] = 0.f;
     if (live) {
       if (net == 0) {
         in0 = p.logp_old[src_l]; in1 = p.adv[src_l];
         const float* ap = p.action + static_cast<size_t>(src_l) * aout;
         if ((aout & 1) == 0) {                                     // rows are 8-byte aligned: half the load wavefronts
 #pragma unroll
-          for (int j = 0; j < FS_AP; j += 2)
-            if (j < aout) { const float2 v = *reinterpret_cast<const float2*>(ap + j); actn[j] = v.x; actn[j + 1] = v.y; }
+          for (int j = 0; j < AP; j += 2)
+            if (j < aout) { const float2 v = *reinterpret_cast<const float2*>(ap + j); zz[j] = v.x; zz[j + 1] = v.y; }
         } else {
 #pragma unroll
-          for (int j = 0; j < FS_AP; ++j) if (j < aout) actn[j] = ap[j];
+          for (int j = 0; j < AP; ++j) if (j < aout) zz[j] = ap[j];
         }
       } else {
         in0 = p.v_old[src_l]; in1 = p.tgt[src_l];
       }
     }
 
-
-    // ---- epilogue 2: H2 = act(acc1 + b1) -> R1 -------------------------------------------------------
-    mbar_wait(accf1, 0);
-    tc_fence_after();
-    if (wt == 0) FS_STAMP(4);
-    epilogue_act(acc1, R1, bias_s + 256, act, erow, q, hf * (H >> 1), H >> 1);
-    fence_proxy_async_smem();                                    // H2 (and W2T) -> async proxy for the head MMAs
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(h2r);
-    if (wt == 0) FS_STAMP(5);
-
-    // ---- loss and gradient seed g = dL/dout: thread = row (hf == 0 warps) ---------------------------
+    // ---- loss and gradient seed g = dL/dout: thread = row (sub == 0 warps) ---------------------------
     mbar_wait(headf, 0);
     tc_fence_after();
     if (wt == 0) FS_STAMP(6);
-    float dls[FS_AP], g[FS_AP];
-    float s_loss = 0.f;
+    if (sub == 0) {
+      const uint32_t th = acc_head + (static_cast<uint32_t>(q * 32) << 16);
+      const float inv_n = p.inv_mb;
+      float s_loss = 0.f, g_logp = 0.f, g0 = 0.f;
+      if (net == 0) {
+        // distrax MultivariateNormalDiag: z = (a - loc) * (1/scale); train.py:223, 234-239.  zz: action -> z in place
+        float quad = 0.f;
 #pragma unroll
-    for (int j = 0; j < FS_AP; ++j) { dls[j] = 0.f; g[j] = 0.f; }
-    if (hf == 0) {
-      float out[FS_AP];
-      {
-        float o2[32];
-        tmem_ld_32x32(acc_head + (static_cast<uint32_t>(q * 32) << 16), o2);
-        tmem_ld_wait();
+        for (int c = 0; c < AP / 16; ++c) {
+          float ohi[16], olo[16];
+          tmem_ld_32x16(th + 16 * c, ohi);
+          tmem_ld_32x16(th + AP + 16 * c, olo);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < FS_AP; ++j) out[j] = o2[j] + o2[FS_AP + j];      // W2_hi and W2_lo contributions
-      }
-      if (live) {
-        const float inv_n = p.inv_mb;
-        if (net == 0) {
-          // distrax MultivariateNormalDiag: z = (a - loc) * (1/scale); train.py:223, 234-239
-          float z[FS_AP], inv_s[FS_AP];
-          float quad = 0.f;
-#pragma unroll
-          for (int j = 0; j < FS_AP; ++j) {
-            z[j] = 0.f; inv_s[j] = 0.f;
-            if (j < aout) {
-              inv_s[j] = hb[32 + j];
-              const float mean = out[j] + hb[j];
-              z[j] = (actn[j] - mean) * inv_s[j];
-              quad += -0.5f * z[j] * z[j] - 0.91893853320467274178f;
-            }
+          for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * c + jj;
+            const float mean = (ohi[jj] + olo[jj]) + hb[j];                 // W2_hi and W2_lo contributions
+            const float z = j < aout ? (zz[j] - mean) * hb[2 * AP + j] : 0.f;
+            zz[j] = z;
+            if (j < aout) quad += -0.5f * z * z - 0.91893853320467274178f;
           }
-          const float logdet = hb[48];
-          const float logp = quad - logdet;
+        }
+        if (live) {
+          const float logp = quad - hb[3 * AP];
           const float ratio = expf(logp - in0);
           const float adv_mean = adv_sum * inv_n;
           const float adv_std = sqrtf(adv_sq * inv_n);
@@ -547,54 +655,73 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
           s_loss = fminf(l1, l2);
           const float w1 = l1 < l2 ? 1.f : (l1 == l2 ? 0.5f : 0.f);
           const float dmin = (w1 + (1.f - w1) * dclip_f(ratio, lo, hi)) * adv;
-          const float g_logp = -inv_n * dmin * ratio;
-#pragma unroll
-          for (int j = 0; j < FS_AP; ++j) {
-            g[j] = g_logp * (z[j] * inv_s[j]);
-            dls[j] = j < aout ? g_logp * (z[j] * z[j] - 1.f) : 0.f;
-          }
-        } else {
+          g_logp = -inv_n * dmin * ratio;
+        }
+      } else {
+        const float ohi = tmem_ld_32x1(th);
+        const float olo = tmem_ld_32x1(th + AP);
+        tmem_ld_wait();
+        if (live) {
           // clipped value loss, train.py:226-231
-          const float v = out[0] + hb[0];
+          const float v = (ohi + olo) + hb[0];
           const float dvv = v - in0;
           const float v_clip = in0 + fminf(fmaxf(dvv, -p.clip_eps), p.clip_eps);
           const float e1 = v - in1, e2 = v_clip - in1;
           const float vl = e1 * e1, vlc = e2 * e2;
           s_loss = fmaxf(vl, vlc);
           const float wa = vl > vlc ? 1.f : (vl == vlc ? 0.5f : 0.f);
-          g[0] = p.vf_coef * 0.5f * inv_n * (wa * 2.f * e1 + (1.f - wa) * 2.f * e2 * dclip_f(dvv, -p.clip_eps, p.clip_eps));
+          g0 = p.vf_coef * 0.5f * inv_n * (wa * 2.f * e1 + (1.f - wa) * 2.f * e2 * dclip_f(dvv, -p.clip_eps, p.clip_eps));
         }
       }
-      // g^T as bf16 hi/lo, [16 j][128 rows] SW128 (the MN-major A of dA2 and the K-major B of dW2)
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) {
+      // g^T as bf16 hi/lo, [2AP j][128 rows] SW128 (the MN-major A of dA2 and the K-major B of dW2); tile sums of
+      // dlog_std and of the head-bias gradient g through a 32 x 32 transpose-reduce (lane j ends with column j)
+      const uint32_t gcol = GT + (erow >> 6) * PG + ((erow & 7) << 1);
+      const int gch = (erow & 63) >> 3;
+      auto put_g = [&](int j, float gj) {
         uint32_t hi, lo;
-        split_bf16(g[j], hi, lo);
-        sts_u16(GT + sw32_off(j, erow), hi);
-        sts_u16(GT + sw32_off(16 + j, erow), lo);
+        split_bf16(gj, hi, lo);
+        sts_u16(gcol + j * 128 + ((gch ^ (j & 7)) << 4), hi);
+        sts_u16(gcol + (AP + j) * 128 + ((gch ^ ((AP + j) & 7)) << 4), lo);
+      };
+      float* rw = red + q * RS;
+      if (AP == 16) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float gj = net == 0 ? g_logp * (zz[j] * hb[2 * AP + j]) : (j == 0 ? g0 : 0.f);
+          put_g(j, gj);
+          v[j] = (net == 0 && j < aout) ? g_logp * (zz[j] * zz[j] - 1.f) : 0.f;
+          v[16 + j] = gj;
+        }
+        rw[lane] = warp_colsum32(v);                               // [0, 16) dlog_std, [16, 32) head bias
+      } else {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (net == 0 && j < aout) ? g_logp * (zz[j] * zz[j] - 1.f) : 0.f;
+        rw[lane] = warp_colsum32(v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float gj = net == 0 ? g_logp * (zz[j] * hb[2 * AP + j]) : (j == 0 ? g0 : 0.f);
+          put_g(j, gj);
+          v[j] = gj;
+        }
+        rw[32 + lane] = warp_colsum32(v);
       }
+      s_loss = warp_sum(s_loss);
+      if (lane == 0) rw[2 * AP] = s_loss;
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(gr);
-    // tile sums (fixed order: lanes, then warps): dlog_std, head bias gradient, loss term
-#pragma unroll
-    for (int j = 0; j < FS_AP; ++j) { dls[j] = warp_sum(dls[j]); g[j] = warp_sum(g[j]); }
-    s_loss = warp_sum(s_loss);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < FS_AP; ++j) { red[ww * 40 + j] = dls[j]; red[ww * 40 + 16 + j] = g[j]; }
-      red[ww * 40 + 32] = s_loss;
-    }
     worker_bar();
     if (wt == 0) FS_STAMP(7);
     float* part = p.part + static_cast<size_t>(tile) * p.part_stride;
-    if (wt <= 32) {
+    if (wt <= 2 * AP) {
       float s = 0.f;
-      for (int w = 0; w < 4; ++w) s += red[w * 40 + wt];         // hf == 0 warps are ww 0..3
-      if (wt == 32) part[G.po_loss] = s;
-      else if (wt >= 16) { if (wt - 16 < aout) part[G.po_b2 + wt - 16] = s; }
+      for (int w = 0; w < 4; ++w) s += red[w * RS + wt];         // fixed order: the four loss warps
+      if (wt == 2 * AP) part[G.po_loss] = s;
+      else if (wt >= AP) { if (wt - AP < aout) part[G.po_b2 + wt - AP] = s; }
       else if (net == 0 && wt < aout) part[p.po_logstd + wt] = s;
     }
 
@@ -602,30 +729,31 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     mbar_wait(bwdf, 0);
     tc_fence_after();
     if (wt == 0) FS_STAMP(8);
-    if (hf * 128 < H) {                                          // warp (q, hf) reads the c-tile mh = hf
-      float dw[FS_AP];
-      {
-        float d2[32];
-        tmem_ld_32x32(acc_dw + 32 * hf + (static_cast<uint32_t>(q * 32) << 16), d2);
+    if (sub < mtH) {                                             // warp (q, sub) reads the 128-column tile mh = sub
+      const uint32_t td = acc_dw + 2 * AP * sub + (static_cast<uint32_t>(q * 32) << 16);
+      const int c = sub * 128 + erow;
+#pragma unroll
+      for (int ch = 0; ch < AP / 16; ++ch) {
+        float dhi[16], dlo[16];
+        tmem_ld_32x16(td + 16 * ch, dhi);
+        tmem_ld_32x16(td + AP + 16 * ch, dlo);
         tmem_ld_wait();
+        if (c < H) {
 #pragma unroll
-        for (int j = 0; j < FS_AP; ++j) dw[j] = d2[j] + d2[FS_AP + j];       // g_hi and g_lo contributions
-      }
-      const int c = hf * 128 + erow;
-      if (c < H) {
-#pragma unroll
-        for (int j = 0; j < FS_AP; ++j) if (j < aout) part[G.po_w2 + c * aout + j] = dw[j];
+          for (int jj = 0; jj < 16; ++jj)
+            if (16 * ch + jj < aout) part[G.po_w2 + c * aout + 16 * ch + jj] = dhi[jj] + dlo[jj];   // g_hi and g_lo contributions
+        }
       }
     }
     for (int b = 0; b < nkH; ++b) {
-      epilogue_dact(acc0, R1, R1, act, erow, q, b * 64 + hf * 32, 32);            // in place: H2 -> dZ2
+      epilogue_dact(acc0, R1, R1, act, erow, q, b * 64 + sub * 16, 16);            // in place: H2 -> dZ2
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&dz2r[b]);
     }
     if (wt == 0) FS_STAMP(9);
-    if (ww == 0 && lane == 0) {
+    if (wt == 32) {
       for (int b = 0; b < nkH; ++b) {
         mbar_wait(&dz2r[b], 0);
         tma_store_2d(R1 + b * 16384, &G.tm_dz2, b * 64, tile * 128);
@@ -634,22 +762,40 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     }
 
     // ---- epilogue 3: dZ1 = acc1 * f'(H1) -> R1 -> TMA store ------------------------------------------
-    mbar_wait(dh1f, 0);                                            // dH1 MMAs done: R1 (dZ2) no longer read by UMMA
+    mbar_wait(dh1f, 0);                                            // dH1 MMAs done: R1 (dZ2) no longer read by those
+    mbar_wait(cs2f, 0);                                            // ... nor by the column-sum MMAs
     tc_fence_after();
     if (wt == 0) FS_STAMP(10);
-    if (ww == 0 && lane == 0) tma_store_wait_read0();              // ... nor by the dZ2 TMA store
+    if (wt == 32) tma_store_wait_read0();                          // ... nor by the dZ2 TMA store
+    float cs2 = 0.f;
+    if (sub < mtH) cs2 = tmem_ld_32x1(acc_cs2 + 16 * sub + (static_cast<uint32_t>(q * 32) << 16));
+    tmem_ld_wait();
     worker_bar();
+    if (sub < mtH && sub * 128 + erow < H) part[G.po_db1 + sub * 128 + erow] = cs2;     // layer-1 bias gradient of this tile
     for (int b = 0; b < nkH; ++b) {                                // 64-column blocks, each stored as soon as it is complete
-      epilogue_dact(acc1, R0, R1, act, erow, q, b * 64 + hf * 32, 32);
+      epilogue_dact(acc1, R0, R1, act, erow, q, b * 64 + sub * 16, 16);
       fence_proxy_async_smem();
-      worker_bar();
-      if (ww == 0 && lane == 0) tma_store_2d(R1 + b * 16384, &G.tm_dz1, b * 64, tile * 128);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dz1r[b]);
     }
     if (wt == 0) FS_STAMP(11);
-    if (ww == 0 && lane == 0) {
+    if (wt == 32) {
+      for (int b = 0; b < nkH; ++b) {
+        mbar_wait(&dz1r[b], 0);
+        tma_store_2d(R1 + b * 16384, &G.tm_dz1, b * 64, tile * 128);
+      }
       tma_store_commit();
-      tma_store_wait_read0();                                      // smem may be released once the bulk stores have read it;
-    }                                                              // their global writes complete with the grid
+    }
+    mbar_wait(cs1f, 0);
+    tc_fence_after();
+    if (sub < mtH) {
+      const float cs1 = tmem_ld_32x1(acc_cs1 + 16 * sub + (static_cast<uint32_t>(q * 32) << 16));
+      tmem_ld_wait();
+      if (sub * 128 + erow < H) part[G.po_db0 + sub * 128 + erow] = cs1;               // layer-0 bias gradient of this tile
+    }
+    if (wt == 32) tma_store_wait_read0();                          // smem may be released once the bulk stores have read it;
+                                                                   // their global writes complete with the grid
     if (wt == 0) FS_STAMP(12);
   }
 

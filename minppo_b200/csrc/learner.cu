@@ -216,6 +216,8 @@ struct NetBufs {
   std::vector<float*> dbias;           // dbias[l], l = 0..L-1 [S][H]: bias-gradient partials from the dW GEMM (ones x dz[l+1])
   std::vector<float*> colsum;          // colsum[l],  l = 1..L-1 [m_tiles][H]  -> bias grad of layer l-1
   std::vector<CUtensorMap> m_act_k, m_act_mn, m_dz_k, m_dz_mn, m_wn_mn, m_wn, m_dw;
+  std::vector<CUtensorMap> m_wn_h;     // m_wn_h[l]: box {64 out, 32 in} -- half-k-block stages of the fused step kernel (MN-major B)
+  CUtensorMap m_w1k_h;                 // wn[1]: box {64 out, H/2 in} -- (k-block, N half) stages of the fused kernel's dH1 GEMM (K-major B)
   // m_wn_mn[l]: box {64 out, 64 in} -- MN-major B of the forward GEMMs;  m_wn[l] (l >= 1): box {64 out, H in} -- K-major B of dX
 };
 
@@ -237,8 +239,8 @@ struct minppo_ctx {
   int T, N, Nl, n0, M, E, L, H, D, Dp, A;
   long long B, Bl, P;
   int mb, cap, M_pad, m_tiles, tiles64, S;
-  int cs_chunks;              // > 0: bias-gradient column sums on the spare CTAs of the dwopt launch, in this many row chunks
-  bool fused;                 // fused step kernel (L == 2, Dp <= 256, A <= 16)
+  int maxu;                   // dwopt fast path: 4-element units of the hidden kernels per thread (1, 2 or 4)
+  bool fused;                 // fused step kernel (L == 2; any obs_dim, act_dim <= 32, hidden_size <= 256)
   int head_parts;             // head partials per minibatch: m_tiles (fused) or tiles64
   std::vector<LeafInfo> leaves;
   // device buffers
@@ -264,6 +266,9 @@ struct minppo_ctx {
   int* err_flag;
   NetBufs net[2];
   int head_stride, po_w3a, po_b3a, po_w3c, po_b3c, po_logstd, po_bh_a, po_bh_c, po_loss;
+  int po_db[2][2];            // fused path: [net][layer] hidden-bias gradient partials (column sums of dZ), H floats each
+  int ap;                     // padded head width of the fused step kernel: 16 (A <= 16) or 32
+  bool store_x;               // fused path, Dp <= 256: the fused kernel stores the gathered X tile for the first-layer dW GEMM
   int opt_blocks;
   // graph cache
   cudaStream_t cap_stream;
@@ -354,8 +359,11 @@ static int init_kernel_attrs() {
   CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_DACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(umma_gemm_kernel<EPI_PARTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   if (head_loss_init()) { set_error("head_loss_init failed"); return MINPPO_ERR_CUDA; }
-  CK(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(dwopt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(fused_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FsLayout<16>::BYTES));
+  CK(cudaFuncSetAttribute(fused_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FsLayout<32>::BYTES));
+  CK(cudaFuncSetAttribute(dwopt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(dwopt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(dwopt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   return 0;
 }
 
@@ -377,20 +385,22 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
     ol.offset = static_cast<int>(lf.offset);
     ol.cols = static_cast<int>(lf.cols);
     ol.grad_bias = 0.f;
-    ol.img_t = nullptr; ol.img_n = nullptr; ol.ld_t = 0; ol.ld_n = 0; ol.img_w2 = nullptr; ol.late = 0;
+    ol.img_t = nullptr; ol.img_n = nullptr; ol.ld_t = 0; ol.ld_n = 0; ol.img_w2 = nullptr; ol.late = 0; ol.ap = 16;
     if (lf.net == 2) {                         // log_std
       ol.grad_src = c->head_part; ol.src_offset = c->po_logstd; ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
       ol.grad_bias = cfg.rank == 0 ? -static_cast<float>(cfg.ent_coef) : 0.f;
     } else if (lf.layer == L) {                // output heads
       ol.grad_src = c->head_part; ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
-      if (lf.is_kernel) { ol.src_offset = lf.net == 0 ? c->po_w3a : c->po_w3c; ol.img_w2 = c->fused ? c->net[lf.net].w2img : nullptr; }
+      if (lf.is_kernel) { ol.src_offset = lf.net == 0 ? c->po_w3a : c->po_w3c; ol.img_w2 = c->fused ? c->net[lf.net].w2img : nullptr; ol.ap = c->ap; }
       else ol.src_offset = lf.net == 0 ? c->po_b3a : c->po_b3c;
     } else if (lf.is_kernel) {                 // hidden kernels: split-K partials of the dW GEMM
       const int in_l = lf.layer == 0 ? c->D : H;
       ol.grad_src = c->net[lf.net].dw_part[lf.layer]; ol.src_offset = 0; ol.nparts = c->S; ol.part_stride = in_l * H; ol.late = 1;
       ol.img_n = c->net[lf.net].wn[lf.layer]; ol.ld_n = H;
+    } else if (c->fused) {                     // hidden biases, fused path: per-tile column sums of dz[l+1] from the fused step kernel
+      ol.grad_src = c->head_part; ol.src_offset = c->po_db[lf.net][lf.layer]; ol.nparts = c->head_parts; ol.part_stride = c->head_stride;
     } else {                                   // hidden biases: column sums of dz[l+1], computed by the dW GEMM (ones x dz)
-      ol.grad_src = c->net[lf.net].dbias[lf.layer]; ol.src_offset = 0; ol.nparts = c->cs_chunks > 0 ? c->cs_chunks : c->S;
+      ol.grad_src = c->net[lf.net].dbias[lf.layer]; ol.src_offset = 0; ol.nparts = c->S;
       ol.part_stride = H; ol.late = 1;
     }
   }
@@ -438,7 +448,7 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     for (int net = 0; net < 2; ++net) {
       FusedNet& g = p.net[net];
       NetBufs& nb = c->net[net];
-      g.tm_w0 = nb.m_wn_mn[0]; g.tm_w1 = nb.m_wn_mn[1]; g.tm_w1k = nb.m_wn[1];
+      g.tm_w0 = nb.m_wn_h[0]; g.tm_w1 = nb.m_wn_h[1]; g.tm_w1k = nb.m_w1k_h;
       g.tm_h1 = nb.m_act_k[1]; g.tm_dz2 = nb.m_dz_k[2]; g.tm_dz1 = nb.m_dz_k[1];
       g.b0 = u.params + find_leaf(c, net, 0, 0).offset;
       g.b1 = u.params + find_leaf(c, net, 1, 0).offset;
@@ -449,9 +459,10 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
       g.po_w2 = net == 0 ? c->po_w3a : c->po_w3c;
       g.po_b2 = net == 0 ? c->po_b3a : c->po_b3c;
       g.po_loss = c->po_loss + (net == 0 ? 1 : 0);          // [0] = sum max(vl, vlc), [1] = sum min(l1, l2)
+      g.po_db0 = c->po_db[net][0]; g.po_db1 = c->po_db[net][1];
     }
     p.rowidx = ridx; p.obs_img = c->obs_img; p.count = c->counts + s;
-    p.tm_xg = c->m_xg_k;
+    p.tm_xg = c->m_xg_k; p.store_x = c->store_x ? 1 : 0;
     p.adv_sum = c->stats + s; p.adv_sq = c->stats + c->E * c->M + s;
     p.action = u.action; p.v_old = u.value; p.logp_old = u.log_prob; p.adv = c->adv; p.tgt = c->tgt;
     p.log_std = u.params + c->leaves.back().offset;
@@ -461,7 +472,9 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     p.clip_eps = static_cast<float>(c->cfg.clip_eps); p.vf_coef = static_cast<float>(c->cfg.vf_coef);
     p.trace = c->trace_on ? c->trace : nullptr;
     PROF(PC_FWD_GEMM);
-    const cudaError_t e = launch_kernel(fused_step_kernel, 2 * c->m_tiles, FS_THREADS, FS_SMEM_BYTES, stream, pdl, p);
+    const cudaError_t e = c->ap == 16
+        ? launch_kernel(fused_step_kernel<16>, 2 * c->m_tiles, FS_THREADS, FsLayout<16>::BYTES, stream, pdl, p)
+        : launch_kernel(fused_step_kernel<32>, 2 * c->m_tiles, FS_THREADS, FsLayout<32>::BYTES, stream, pdl, p);
     if (e != cudaSuccess) { set_error("fused_step launch failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
     c->launches++;
   } else {
@@ -552,15 +565,14 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
         g.cta_begin = cta;
         const int in_l = l == 0 ? c->D : H;
         const int in_pad = l == 0 ? c->Dp : H;
-        if (l == 0 && c->fused && !(c->skip_mask & 1)) { g.amode = A_TMA_MN; g.tmA = c->m_xg_mn; }   // rows gathered by the fused kernel
+        if (l == 0 && c->fused && c->store_x && !(c->skip_mask & 1)) { g.amode = A_TMA_MN; g.tmA = c->m_xg_mn; }   // rows gathered by the fused kernel
         else if (l == 0) { g.amode = A_GATHER_MN; g.rowidx = ridx; g.gimage = c->obs_img; g.ldg = c->Dp; }
         else { g.amode = A_TMA_MN; g.tmA = nb.m_act_mn[l]; }
         g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
         g.kb_total = c->M_pad / 64;
         g.k_count = c->padded ? c->counts + s : nullptr;
         g.tmC = nb.m_dw[l];
-        g.colsum_out = c->cs_chunks > 0 ? nullptr : nb.dbias[l];
-        dp.cs_src[ng - 1] = nb.dz[l + 1]; dp.cs_out[ng - 1] = nb.dbias[l];
+        g.colsum_out = c->fused ? nullptr : nb.dbias[l];      // fused path: the bias gradients come from the fused step kernel
         g.N = H; g.m_tiles = (in_pad + 127) / 128; g.splits = c->S; g.m_store = in_l;
         cta += g.m_tiles * g.splits;
       }
@@ -575,17 +587,16 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
   const bool merged = c->merged_opt && c->skip_mask == 0 && cta <= c->sm_count;
   if (merged) {
     dp.gemm_ctas = cta;
-    dp.cs_rows = c->M_pad; dp.cs_n = H; dp.cs_chunks = c->cs_chunks;
     if (s + 1 < c->E * c->M) { dp.next_ridx = ridx + c->cap; dp.obs_img = c->obs_img; dp.next_rows = c->cap; dp.obs_ld = c->Dp; }
     if (c->padded) { dp.row_count = c->counts + s; dp.next_count = c->counts + s + 1; dp.part_rows = c->fused ? 128 : 64; }
     dp.trace = c->trace_on ? c->trace2 : nullptr;
     // all-reduce fused into this launch (peer memory); needs the one-unit-per-thread fast path of the kernel
-    const bool px_on = sharded && c->peers_set && c->P / 4 <= static_cast<long long>(c->sm_count) * DWOPT_THREADS;
+    const bool px_on = sharded && c->peers_set && c->P <= dwopt_fast_capacity(c->sm_count, c->maxu);
     if (px_on) { dp.px = c->px; dp.px.ablate = getenv("MINPPO_PX_ABLATE") ? atoi(getenv("MINPPO_PX_ABLATE")) : 0; }
     o.do_reduce = 1; o.do_apply = (sharded && !px_on) ? 0 : 1;
     {
       PROF(PC_DW_GEMM);
-      const cudaError_t e = dwopt_launch(dp, c->sm_count, stream, pdl);
+      const cudaError_t e = dwopt_launch(dp, c->sm_count, stream, pdl, c->maxu);
       if (e != cudaSuccess) { set_error("dwopt launch failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
       c->launches++;
     }
@@ -831,9 +842,12 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   c->cap = c->M_pad;                                  // row lists are padded to whole GEMM tiles
   c->m_tiles = c->M_pad / 128;
   c->tiles64 = c->M_pad / 64;
-  c->fused = !cfg->disable_fused && c->L == 2 && c->Dp <= 256 && c->A <= FS_AP;
+  c->fused = !cfg->disable_fused && c->L == 2;
+  c->ap = c->A <= 16 ? 16 : 32;
+  c->store_x = c->fused && c->Dp <= 256;
   c->head_parts = c->fused ? c->m_tiles : c->tiles64;
   c->P = build_layout(*cfg, &c->leaves);
+  c->maxu = c->P <= dwopt_fast_capacity(c->sm_count, 1) ? 1 : (c->P <= dwopt_fast_capacity(c->sm_count, 2) ? 2 : 4);
   // split-K of the dW GEMMs: fill the SMs once
   {
     int per_split = 0;
@@ -856,10 +870,6 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     // no empty splits: ceil(kb_total / S) * (S - 1) < kb_total
     while (S > 1 && ((kb_total + S - 1) / S) * (S - 1) >= kb_total) --S;
     c->S = S;
-    // spare CTAs of the one-CTA-per-SM dwopt grid: >= one per GEMM group -> they form the bias gradients
-    const int spare = c->sm_count - per_split * S;
-    const bool merged_ok = !(getenv("MINPPO_SPLIT_OPT") && atoi(getenv("MINPPO_SPLIT_OPT")) != 0) && !getenv("MINPPO_SKIP");
-    c->cs_chunks = (merged_ok && spare >= 2 * c->L && getenv("MINPPO_CTA_COLSUM")) ? spare / (2 * c->L) : 0;
   }
   c->opt_blocks = c->sm_count;
   if (c->P > opt_max_params(c->opt_blocks)) { set_error("parameter count %lld exceeds the single-sweep optimizer kernel (%d)", c->P, opt_max_params(c->opt_blocks)); return fail(MINPPO_ERR_UNSUPPORTED); }
@@ -874,6 +884,8 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     c->po_logstd = o; o += A;
     c->po_bh_a = o; o += H;
     c->po_bh_c = o; o += H;
+    for (int net = 0; net < 2; ++net)
+      for (int l = 0; l < 2; ++l) { c->po_db[net][l] = o; o += H; }
     c->po_loss = o; o += 2;
     c->head_stride = (o + 3) / 4 * 4;
   }
@@ -923,9 +935,9 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     NetBufs& nb = c->net[net];
     nb.act.assign(L + 1, nullptr); nb.dz.assign(L + 1, nullptr); nb.wn.assign(L, nullptr);
     nb.dw_part.assign(L, nullptr); nb.colsum.assign(L, nullptr); nb.dbias.assign(L, nullptr);
-    ALLOC(nb.w2img, 16384);
+    ALLOC(nb.w2img, static_cast<size_t>(H) * FS_MAX_AP * 4);       // H/64 panels of [2 AP rows][128 B]
     nb.m_act_k.resize(L + 1); nb.m_act_mn.resize(L + 1); nb.m_dz_k.resize(L + 1); nb.m_dz_mn.resize(L + 1);
-    nb.m_wn_mn.resize(L); nb.m_wn.resize(L); nb.m_dw.resize(L);
+    nb.m_wn_mn.resize(L); nb.m_wn.resize(L); nb.m_dw.resize(L); nb.m_wn_h.resize(L);
     for (int l = 1; l <= L; ++l) {
       ALLOC(nb.act[l], static_cast<size_t>(c->M_pad) * H);
       ALLOC(nb.dz[l], static_cast<size_t>(c->M_pad) * H);
@@ -939,12 +951,14 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
       const int in_l = l == 0 ? c->D : H;
       ALLOC(nb.wn[l], static_cast<size_t>(kp) * H);
       if ((rc = make_tmap(&nb.m_wn_mn[l], nb.wn[l], H, kp, H, 64, 64))) return fail(rc);
+      if ((rc = make_tmap(&nb.m_wn_h[l], nb.wn[l], H, kp, H, 64, 32))) return fail(rc);
+      if (l == 1 && (rc = make_tmap(&nb.m_w1k_h, nb.wn[l], H, H, H, 64, H / 2))) return fail(rc);
       if (l >= 1) {
         if ((rc = make_tmap(&nb.m_wn[l], nb.wn[l], H, H, H, 64, H))) return fail(rc);
         ALLOC(nb.colsum[l], static_cast<size_t>(c->m_tiles) * H);
       }
       ALLOC(nb.dw_part[l], static_cast<size_t>(c->S) * in_l * H);
-      ALLOC(nb.dbias[l], static_cast<size_t>(c->S > c->cs_chunks ? c->S : c->cs_chunks) * H);
+      ALLOC(nb.dbias[l], static_cast<size_t>(c->S) * H);
       if ((rc = make_tmap_f32_3d(&nb.m_dw[l], nb.dw_part[l], H, in_l, c->S))) return fail(rc);
     }
   }

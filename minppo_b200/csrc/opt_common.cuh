@@ -97,8 +97,8 @@ MINPPO_DEVINL void write_images(const OptLeaf& L, int i, float p) {
     const int r = e / L.cols, j = e % L.cols;
     uint32_t hi, lo;
     split_bf16(p, hi, lo);
-    *reinterpret_cast<uint16_t*>(L.img_w2 + sw32_off(j, r)) = static_cast<uint16_t>(hi);
-    *reinterpret_cast<uint16_t*>(L.img_w2 + sw32_off(16 + j, r)) = static_cast<uint16_t>(lo);
+    *reinterpret_cast<uint16_t*>(L.img_w2 + swp_off(L.ap, j, r)) = static_cast<uint16_t>(hi);
+    *reinterpret_cast<uint16_t*>(L.img_w2 + swp_off(L.ap, L.ap + j, r)) = static_cast<uint16_t>(lo);
   }
 }
 

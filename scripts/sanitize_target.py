@@ -45,6 +45,8 @@ def run(name, N, T, M, E, D, A, H=256, L=2, fused=True, tanh=True):
 if which in ("all", "fused"):
     run("fused c1-like (5-row minibatches)", 16, 10, 8, 1, 225, 10)
     run("fused 2 tiles", 32, 16, 2, 1, 225, 10)
+    run("fused wide (D=415: streamed X slots, A=20: 32-wide heads, 2 optimizer units per thread)", 32, 16, 2, 1, 415, 20)
+    run("fused narrow (H=128, D=600, A=17, relu actor)", 32, 8, 2, 1, 600, 17, H=128, tanh=False)
 if which in ("all", "layerwise"):
     run("layer-wise ragged", 24, 16, 3, 1, 37, 3, H=128, L=1, fused=False)
     run("layer-wise deep relu", 32, 16, 2, 1, 256, 16, H=192, L=3, fused=False, tanh=False)

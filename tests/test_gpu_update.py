@@ -52,7 +52,23 @@ CASES = {
     # 3 hidden layers, relu actor (model.use_tanh=false), aligned D, partitionable PRNG
     "deep": dict(hp=dict(num_envs=32, num_steps=16, num_minibatches=2, update_epochs=2, anneal_lr=False,
                          hidden_size=192, num_layers=3, use_tanh=False, prng_mode=threefry.PARTITIONABLE), D=256, A=16),
+    # ---- shape-genericity of the FUSED step kernel (num_layers = 2; SURVEY F9: D, A come from the MJCF at run time) ----
+    # a plausible real humanoid (env.py:245-261 with ~20 actuators): D > 256 streams X k-blocks through the 4 slots,
+    # A > 16 takes the 32-wide head template, P > 303k takes two register-resident units per optimizer thread
+    "wide": dict(hp=dict(num_envs=64, num_steps=32, num_minibatches=4, update_epochs=2, anneal_lr=False), D=415, A=20),
+    # A at the limit, 3 k-blocks of H, D one element past a k-block boundary
+    "a32_h192": dict(hp=dict(num_envs=48, num_steps=16, num_minibatches=2, update_epochs=2, anneal_lr=False,
+                             hidden_size=192), D=321, A=32),
+    # odd A just past the 16-wide template, narrow net, 10 k-blocks of D (slots refilled 6 times)
+    "a17_h128_d600": dict(hp=dict(num_envs=32, num_steps=16, num_minibatches=2, update_epochs=2, anneal_lr=False,
+                                  hidden_size=128, use_tanh=False), D=600, A=17),
+    # one k-block of H, A = 24
+    "a24_h64": dict(hp=dict(num_envs=32, num_steps=8, num_minibatches=2, update_epochs=2, anneal_lr=False,
+                            hidden_size=64, ent_coef=0.01), D=100, A=24),
+    # 16 k-blocks of D, P = 646k: four register-resident units per optimizer thread
+    "d1000": dict(hp=dict(num_envs=32, num_steps=16, num_minibatches=2, update_epochs=1, anneal_lr=False), D=1000, A=10),
 }
+FUSED_SHAPE_CASES = ["wide", "a32_h192", "a17_h128_d600", "a24_h64", "d1000"]
 
 
 def _oracle(hp, pr, dtype, gemm, perms=None):
@@ -193,7 +209,7 @@ def test_update_parity_negative_lr_schedule(cuda_device):
     assert max(m["param_leaf_rms_in_lr"].values()) < 5.0, m
 
 
-@pytest.mark.parametrize("name", ["medium", "ragged", "deep"])
+@pytest.mark.parametrize("name", ["medium", "ragged", "deep"] + FUSED_SHAPE_CASES)
 def test_single_minibatch_gradient(name, cuda_device):
     """E = 1, M = 1: the one minibatch is the whole batch, so the gradient the optimizer saw can
     be read back and compared leaf by leaf with the hand-derived / autograd-checked oracle."""
