@@ -73,35 +73,59 @@ MINPPO_DEVINL unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
   return v;
 }
 struct alignas(64) DwOptParams {
-  GemmParams gemm;
-  OptArgs opt;
+  GemmParams gemm;               // the per-step row list / valid-row count of the groups come from the arrays below
+  OptArgs opt;                   // losses_out / gnorm_out: bases of the per-step arrays (losses_stride floats apart / 1 apart)
   int gemm_ctas;                 // CTAs [0, gemm_ctas) run the GEMM; the others pre-reduce the small leaves
   long long* trace;              // debug: [grid][16] clock64 stamps (null = off)
   // Gradient exchange over NVLink peer memory (env-sharded ranks; world == 0: not configured).  Every rank exports
   // one allocation [stage | pad | result] (PeerXchg above); base[r] is rank r's copy as mapped HERE.
   PeerXchg px;
-  // L2 prefetch of the NEXT minibatch's observation rows (the fused step kernel gathers them first thing)
-  const int32_t* row_count;      // optional: rows of this minibatch on this rank (device side); partial sums of the
-                                 // per-tile (early) leaves and the prefetch stop there
+  // per-update arrays, indexed by the minibatch step s = e * M + k
+  const int32_t* ridx_base;      // [EM][cap] row lists (gather groups of the GEMM; L2 prefetch of the NEXT step's rows)
+  const int32_t* counts;         // [EM] rows of each minibatch on this rank
+  int cap, EM;
+  int padded;                    // 1: row lists are sized for a worst case, counts[] bound the per-minibatch work
+  int losses_stride;             // floats between the losses of consecutive steps (4; 0 = every step writes the scratch slot)
   int part_rows;                 // minibatch rows per early-leaf partial (128: fused step kernel, 64: head_loss kernel)
-  const int32_t* next_ridx;      // [next_rows] or null
+  int prefetch;                  // 1: L2 prefetch of the next minibatch's observation rows by the GEMM CTAs' helper warps
   const __nv_bfloat16* obs_img;  // [Bl][obs_ld]
-  int next_rows, obs_ld;
-  const int32_t* next_count;     // optional: valid entries of next_ridx (device side)
+  int obs_ld;
+  int step;                      // dwopt_kernel: the minibatch step of this launch (the persistent kernel loops)
 };
+
+template <int NTHREADS_MAX = 1024>
+MINPPO_DEVINL float block_sum_dyn(float v, float* scratch /*[32]*/) {
+  const int nw = static_cast<int>(blockDim.x) >> 5;
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x < 32) {
+    s = static_cast<int>(threadIdx.x) < nw ? scratch[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+  }
+  __syncthreads();
+  return s;                                   // valid in warp 0
+}
 
 // MAXU = 4-element units of the hidden kernels a thread may own (fast path: reduced gradient and optimizer state stay in
 // registers across the second barrier).  MAXU = 1 covers P_late <= 4 * grid * 512 (303k parameters on 148 SMs: the
 // stand-in shape); larger observation widths take MAXU = 2 or 4.
+// The whole CTA calls this (any block size that is a multiple of 32 and >= GEMM_THREADS; all CTAs of the grid co-resident).
+// `ext_tmem`: TMEM base of a persistent caller (GEMM_NO_TMEM: the GEMM allocates and frees its own columns).
 template <int MAXU>
-__global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_constant__ DwOptParams p) {
-  extern __shared__ uint8_t smem_raw[];
+MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw, uint32_t ext_tmem, bool build_tab = true) {
   __shared__ float scratch[32];
   __shared__ float s_bcast[4];
   __shared__ LeafTab T;
   const OptArgs& a = p.opt;
   const int P = a.P;
-  const int G = static_cast<int>(gridDim.x), NT = DWOPT_THREADS;
+  const int G = static_cast<int>(gridDim.x), NT = static_cast<int>(blockDim.x);
+  const int32_t* row_count = p.padded ? p.counts + step : nullptr;          // rows of this minibatch on this rank
+  const int32_t* next_ridx = (p.prefetch && step + 1 < p.EM) ? p.ridx_base + static_cast<size_t>(step + 1) * p.cap : nullptr;
+  const int32_t* next_count = p.padded ? p.counts + step + 1 : nullptr;
+  float* losses_out = a.losses_out ? a.losses_out + static_cast<size_t>(step) * p.losses_stride : nullptr;
+  float* gnorm_out = a.gnorm_out ? a.gnorm_out + step : nullptr;
   const int b = static_cast<int>(blockIdx.x), t = static_cast<int>(threadIdx.x);
   const bool has_extra = p.gemm_ctas < G;
 #define DW_STAMP(slot) do { if (p.trace && t == 0) p.trace[static_cast<size_t>(b) * 16 + (slot)] = clock64(); } while (0)
@@ -114,8 +138,9 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     s_seq = __ldcg(p.px.seq) + 1u;                       // number of this exchange
     s_dead = __ldcg(a.err_flag) != 0;
   }
-  leaf_tab_build(T, a, t, NT);
+  if (build_tab) leaf_tab_build(T, a, t, NT);            // a persistent caller builds the table once (it only depends on the launch)
   __syncthreads();
+  DW_STAMP(14);
 
   // Per-step scalars (two powf, A exp/log): computed by the last thread, whose warp has no GEMM role, while the
   // GEMM is in flight (GEMM CTAs) or up front (spare CTAs) -- never between the barriers, never in front of the
@@ -127,7 +152,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     if (scal_thread && a.do_apply) {
       count = __ldcg(a.count);                           // Adam step count BEFORE this step
       step_scalars(a, count, s_bcast[1], s_bcast[2], s_bcast[3]);
-      if (b == 0 && a.losses_out) {
+      if (b == 0 && losses_out) {
         // train.py:240 -- evaluated with the PRE-update log_std (nothing is updated before the second barrier)
         for (int j = 0; j < a.A; ++j) ent += logf(fabsf(expf(__ldcg(a.params + a.off_logstd + j))));
       }
@@ -142,24 +167,25 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     // spare CTAs, whose number depends on the split-K factor.
     auto idle_work = [&]() {
       scalars();
-      if (p.next_ridx) {
-        constexpr int HELPERS = DWOPT_THREADS - GEMM_THREADS;
+      if (next_ridx) {
+        const int HELPERS = NT - GEMM_THREADS;
         const int h = t - GEMM_THREADS;
         const int lines = (p.obs_ld * 2) >> 7;
-        const int nrows = p.next_count ? min(p.next_rows, __ldcg(p.next_count)) : p.next_rows;
+        const int nrows = next_count ? min(p.cap, __ldcg(next_count)) : p.cap;
         for (int j = b * HELPERS + h; j < nrows * lines; j += p.gemm_ctas * HELPERS) {
-          const char* row = reinterpret_cast<const char*>(p.obs_img + static_cast<size_t>(p.next_ridx[j / lines]) * p.obs_ld);
+          const char* row = reinterpret_cast<const char*>(p.obs_img + static_cast<size_t>(next_ridx[j / lines]) * p.obs_ld);
           asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (j % lines) * 128));
         }
       }
     };
-    umma_gemm_body<EPI_PARTIAL>(p.gemm, smem_raw, p.trace ? p.trace + static_cast<size_t>(b) * 16 : nullptr, idle_work);   // PDL wait / trigger inside
+    umma_gemm_body<EPI_PARTIAL>(p.gemm, smem_raw, p.trace ? p.trace + static_cast<size_t>(b) * 16 : nullptr, idle_work, ext_tmem,
+                                p.ridx_base + static_cast<size_t>(step) * p.cap, row_count);   // PDL wait / trigger inside
   } else {
     scalars();
     griddep_wait();                                      // the small-leaf partials come from the fused step kernel
     if (t == 0) griddep_launch();
     const int e = b - p.gemm_ctas, ne = G - p.gemm_ctas;
-    const int live_tiles = p.row_count ? (max(__ldcg(p.row_count), 0) + p.part_rows - 1) / p.part_rows : 0x7fffffff;
+    const int live_tiles = row_count ? (max(__ldcg(row_count), 0) + p.part_rows - 1) / p.part_rows : 0x7fffffff;
     ss = reduce_leaves<false>(a, T, e * NT + t, ne * NT, live_tiles);
   }
   DW_STAMP(1);
@@ -178,7 +204,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   float4 g4[MAXU];
   float pv[MAXU][4], mv[MAXU][4], nv[MAXU][4];
   int ul[MAXU], ui[MAXU];                                // leaf and first arena index of each of this thread's units
-  if (!has_extra) ss += reduce_leaves<false>(a, T, gtid, GT_, p.row_count ? (max(__ldcg(p.row_count), 0) + p.part_rows - 1) / p.part_rows : 0x7fffffff);
+  if (!has_extra) ss += reduce_leaves<false>(a, T, gtid, GT_, row_count ? (max(__ldcg(row_count), 0) + p.part_rows - 1) / p.part_rows : 0x7fffffff);
   // units dealt to warps round-robin over the CTAs (balanced, 512 contiguous bytes per warp and partial)
   const int unit0 = (((t >> 5) * G + b) << 5) + (t & 31);
 #pragma unroll
@@ -211,7 +237,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   } else {
     ss += reduce_leaves<true>(a, T, gtid, GT_);
   }
-  if (!a.do_apply) return;
+  if (!a.do_apply) return;                               // NCCL fallback: gflat = the local gradient sum; opt_kernel applies
 
   if (px_on) {
     // ---- one-shot all-reduce over NVLink peer memory (PeerXchg above; requires the fast path) -----------------
@@ -383,7 +409,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     DW_STAMP(15);
     if (b == 0 && scal_thread) *X.seq = n;
   }
-  const float bs = block_sum<DWOPT_THREADS>(ss, scratch);
+  const float bs = block_sum_dyn(ss, scratch);
   if (t == 0) a.block_ss[b] = bs;
   DW_STAMP(3);
   grid_barrier(a.barrier, a.err_flag);
@@ -394,7 +420,7 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
     // one load per thread (G <= DWOPT_THREADS): a serial loop over the per-block sums cost five dependent
     // L2 round trips on lines every SM is hammering at the same time
     const float v = t < G ? __ldcg(a.block_ss + t) : 0.f;
-    const float tot = block_sum<DWOPT_THREADS>(v, scratch);
+    const float tot = block_sum_dyn(v, scratch);
     if (t == 0) s_bcast[0] = sqrtf(tot);
   }
   __syncthreads();
@@ -425,20 +451,26 @@ __global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_co
   DW_STAMP(5);
   if (b == 0 && scal_thread) {
     *a.count = count + 1;
-    if (a.losses_out) {
+    if (losses_out) {
       // gflat[P] = sum max(vl, vlc), gflat[P+1] = sum min(l1, l2) over the global minibatch
       const float value_loss = 0.5f * __ldcg(a.gflat + P) * a.inv_mb;
       const float actor_loss = -__ldcg(a.gflat + P + 1) * a.inv_mb;
       // a raised device-side error flag (row-list overflow, barrier / exchange timeout) poisons the reported losses:
       // the failure surfaces in the update's own result without a host round trip (minppo_ctx_check names the cause)
       const float poison = __ldcg(a.err_flag) != 0 ? __int_as_float(0x7fc00000) : 0.f;
-      a.losses_out[0] = actor_loss + a.vf_coef * value_loss - a.ent_coef * ent + poison;
-      a.losses_out[1] = value_loss + poison;
-      a.losses_out[2] = actor_loss + poison;
-      a.losses_out[3] = ent + poison;
-      if (a.gnorm_out) *a.gnorm_out = sc.gnorm;
+      losses_out[0] = actor_loss + a.vf_coef * value_loss - a.ent_coef * ent + poison;
+      losses_out[1] = value_loss + poison;
+      losses_out[2] = actor_loss + poison;
+      losses_out[3] = ent + poison;
+      if (gnorm_out) *gnorm_out = sc.gnorm;
     }
   }
+}
+
+template <int MAXU>
+__global__ void __launch_bounds__(DWOPT_THREADS, 1) dwopt_kernel(const __grid_constant__ DwOptParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  dwopt_body<MAXU>(p, p.step, smem_raw, GEMM_NO_TMEM);
 }
 
 // largest parameter count of the hidden kernels the register-resident fast path covers on a grid of `grid` CTAs

@@ -87,11 +87,11 @@ struct alignas(64) FusedParams {
   FusedNet net[2];
   CUtensorMap tm_xg;             // gathered observation rows [M_pad][Dp], box {64, 128}: TMA store by the critic CTAs,
                                  // the A operand of both nets' first-layer weight-gradient GEMM (store_x only)
-  const int32_t* rowidx;         // [cap] (this minibatch)
+  const int32_t* rowidx;         // [E*M][cap] row lists of ALL minibatch steps of the update
   const __nv_bfloat16* obs_img;  // [Bl][Dp]
-  const int32_t* count;
-  const float* adv_sum;
-  const float* adv_sq;
+  const int32_t* count;          // [E*M]
+  const float* adv_sum;          // [E*M]
+  const float* adv_sq;           // [E*M]
   const float* action;
   const float* v_old;
   const float* logp_old;
@@ -102,6 +102,7 @@ struct alignas(64) FusedParams {
   int part_stride, po_logstd;
   int H, A, Dp, m_tiles, cap;
   int store_x;                   // 1: Dp <= 256, the X tile is stored for the dW GEMM (else that GEMM gathers by index itself)
+  int step;                      // minibatch step e * M + k of this launch (fused_step_kernel; the persistent kernel loops)
   float inv_mb, clip_eps, vf_coef;
   long long* trace;              // debug: [ctas][32] clock64 stamps (null = off)
 };
@@ -224,14 +225,13 @@ MINPPO_DEVINL void epilogue_dact(uint32_t tmem_acc, uint32_t h_base, uint32_t ds
   else epilogue_dact_t<ACT_TANH>(tmem_acc, h_base, dst_base, row, q, col0, ncols);
 }
 
+// One (tile, net) unit of one minibatch step.  The whole CTA (FS_THREADS threads) calls this with the SAME arguments;
+// `sm` / `base` = the 1024-byte aligned dynamic shared memory, `tmem_base` = 512 allocated TMEM columns.  The mbarriers
+// are (re-)initialised on entry, so a persistent caller may run any number of units back to back.
 template <int AP>
-__global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_constant__ FusedParams p) {
+MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t* sm, uint32_t base, uint32_t tmem_base) {
   using LY = FsLayout<AP>;
   constexpr int NS = LY::NS, NS1 = LY::NS1, PG = LY::PG, RS = LY::RS;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - raw);
   float* bias_s = reinterpret_cast<float*>(sm + LY::BIAS);      // [0..256) layer 0, [256..512) layer 1
   float* hb = reinterpret_cast<float*>(sm + LY::HB);            // [0, AP) head bias, [AP, 2AP) log_std,
                                                                 // [2AP, 3AP) 1 / scale, [3AP] sum log|scale|
@@ -255,13 +255,14 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
   uint64_t* h1r = bars + 41;            // [4] H1 columns [64 b, 64 b + 64) in R0 (k-block b of the L2 GEMM)
   uint64_t* dz2r = bars + 45;           // [4] dZ2 columns [64 b, 64 b + 64) in R1 (k-block b of the dH1 GEMM)
   uint64_t* dz1r = bars + 49;           // [4] dZ1 columns [64 b, 64 b + 64) in R1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 56);
+  const int32_t* rowidx_s = p.rowidx + static_cast<size_t>(step) * p.cap;     // this step's row list
+  const int32_t* count_s = p.count + step;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA order: (tile, net) with net fastest, so that the LIVE tiles of both nets are the lowest block indices and fit the
   // first wave even when the grid is sized for an env-sharded rank's worst-case row count (dead tiles come last)
-  const int net = static_cast<int>(blockIdx.x) & 1;
-  const int tile = static_cast<int>(blockIdx.x) >> 1;
+  const int net = unit & 1;
+  const int tile = unit >> 1;
   const int cta_id = net * p.m_tiles + tile;             // trace row (net-major, scripts/trace_fused.py)
   const FusedNet& G = p.net[net];
   const int H = p.H, nkH = H >> 6, nk0 = p.Dp >> 6;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
 
   // Env-sharded ranks size the row lists for the worst case (learner.cu: 1.5 x the mean + 256 rows); the tiles
   // beyond this minibatch's actual row count have nothing to do except zeroing their partial sums.
-  if (tile * 128 >= min(*p.count, p.cap)) {
+  if (tile * 128 >= min(*count_s, p.cap)) {
     griddep_wait();                                     // the previous optimizer step may still be reading the partials
     float* part = p.part + static_cast<size_t>(tile) * p.part_stride;
     for (int i = threadIdx.x; i < H * G.aout; i += FS_THREADS) part[G.po_w2 + i] = 0.f;
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     if (threadIdx.x == 0) part[G.po_loss] = 0.f;
     return;
   }
+  __syncthreads();                       // persistent callers: the previous unit / phase is done with this memory
   if (threadIdx.x == FS_WORKERS) {
     FS_STAMP(16);
     for (int s = 0; s < 8; ++s) { mbar_init(&l1_full[s], 1); mbar_init(&l1_empty[s], 1); }
@@ -295,14 +297,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     mbar_init(h2r, FS_NWW); mbar_init(gr, FS_NWW);
     fence_mbar_init();
   }
-  if (warp == FS_MMA_WARP) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256;
   const uint32_t acc_head = acc1;               // [256, 256 + 2AP): head outputs, hi | lo halves (after acc1 is drained)
   const uint32_t acc_dw = acc1 + 2 * AP;        // + 2AP per 128-column tile of H: head-kernel gradient, hi | lo halves
@@ -314,6 +311,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     if (elect_one()) {
       tma_prefetch_desc(&G.tm_w0); tma_prefetch_desc(&G.tm_w1); tma_prefetch_desc(&G.tm_w1k);
       griddep_wait();                 // the weight images are rewritten by the previous optimizer step
+      fence_proxy_async_global();     // persistent caller: they were published through a grid barrier (generic-proxy acquire)
       const uint32_t bytes = static_cast<uint32_t>(H) * 64u;
       // ---- L1: W0 half-k-blocks j = 0 .. 2 nk0 - 1 through NS1 stages (the ring + four stages parked in R0, which nothing
       //      touches before epilogue 1: for Dp <= 256 the whole L1 GEMM is fed up front)
@@ -490,11 +488,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     // ---- gather the observation rows of this tile into the X slots of R1 ---------------------------------------
     int src_g[2];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) src_g[g] = p.rowidx[tile * 128 + grow0 + 64 * g];
+    for (int g = 0; g < 2; ++g) src_g[g] = rowidx_s[tile * 128 + grow0 + 64 * g];
     const int lrow = tile * 128 + erow;                          // loss row of this thread (sub == 0 warps)
-    const int count = min(*p.count, p.cap);
+    const int count = min(*count_s, p.cap);
     const bool live = (sub == 0) && (lrow < count);
-    const int src_l = live ? p.rowidx[lrow] : 0;
+    const int src_l = live ? rowidx_s[lrow] : 0;
     // one warp instruction copies 4 rows x 128 contiguous bytes (4 L1 wavefronts; a lane-per-row mapping needed 32)
     auto gather_block = [&](int kb) {
 #pragma unroll
@@ -508,7 +506,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     const int nb0 = nk0 < FS_XSLOTS ? nk0 : FS_XSLOTS;
     for (int kb = 0; kb < nb0; ++kb) gather_block(kb);
     if (wt == 0) FS_STAMP(26);
-    const float adv_sum = *p.adv_sum, adv_sq = *p.adv_sq;
+    const float adv_sum = p.adv_sum[step], adv_sq = p.adv_sq[step];
     // ---- everything below reads what the previous optimizer step wrote (PDL: see common.cuh) -------
     griddep_wait();
     if (wt == 0) griddep_launch();
@@ -794,14 +792,43 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
       tmem_ld_wait();
       if (sub * 128 + erow < H) part[G.po_db0 + sub * 128 + erow] = cs1;               // layer-0 bias gradient of this tile
     }
-    if (wt == 32) tma_store_wait_read0();                          // smem may be released once the bulk stores have read it;
-                                                                   // their global writes complete with the grid
+    // The bulk stores must have READ shared memory before it is reused, and -- for a persistent caller, whose next phase
+    // reads H1 / dZ / X from other CTAs after a grid barrier, not after a kernel boundary -- their global writes must be
+    // complete and ordered before this thread's later (generic-proxy) barrier arrival.
+    if (wt == 32 || x_store) { tma_store_wait_all0(); fence_proxy_async_global(); }
     if (wt == 0) FS_STAMP(12);
   }
 
+  // all TMEM reads of this unit are complete (tcgen05.wait::ld) before the caller reuses or frees the columns
   tc_fence_before();
   __syncthreads();
-  if (warp == FS_MMA_WARP) tmem_dealloc(tmem_base, 512);
+  tc_fence_after();
+}
+
+// One launch = one minibatch step: CTA blockIdx.x handles unit blockIdx.x.
+template <int AP>
+__global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_constant__ FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5;
+  const int unit = static_cast<int>(blockIdx.x);
+  if ((unit >> 1) * 128 < min(p.count[p.step], p.cap)) {          // live tile: needs the tensor memory
+    if (warp == FS_MMA_WARP) {
+      tmem_alloc(&tmem_slot, 512);
+      tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    fused_tile<AP>(p, unit, p.step, sm, base, tmem_base);
+    if (warp == FS_MMA_WARP) tmem_dealloc(tmem_base, 512);
+  } else {
+    fused_tile<AP>(p, unit, p.step, sm, base, 0u);                // dead tile: zeroes its partials and returns
+  }
 }
 
 }  // namespace minppo

@@ -28,6 +28,7 @@
 #include "umma_gemm.cuh"
 #include "fused_step.cuh"
 #include "dwopt.cuh"
+#include "ppo_steps.cuh"
 
 namespace minppo {
 
@@ -179,7 +180,7 @@ static int validate_config(const minppo_config& c) {
     return MINPPO_ERR_UNSUPPORTED;
   }
   if (c.act_dim > 32) { set_error("act_dim=%d unsupported (<= 32)", c.act_dim); return MINPPO_ERR_UNSUPPORTED; }
-  if (2 * (c.num_layers + 1) * 2 + 1 > MINPPO_MAX_LEAVES) { set_error("too many layers"); return MINPPO_ERR_UNSUPPORTED; }
+  if (2 * (c.num_layers + 1) * 2 + 1 > OPT_TAB_LEAVES) { set_error("too many layers"); return MINPPO_ERR_UNSUPPORTED; }
   if (2 * c.num_layers > GEMM_MAX_GROUPS) { set_error("num_layers=%d unsupported (<= %d)", c.num_layers, GEMM_MAX_GROUPS / 2); return MINPPO_ERR_UNSUPPORTED; }
   const long long B = static_cast<long long>(c.num_envs) * c.num_steps;
   const long long mb = B / c.num_minibatches;
@@ -251,6 +252,8 @@ struct minppo_ctx {
   bool trace_on;
   bool pdl;                   // programmatic dependent launch between step kernels (MINPPO_PDL=0 disables)
   bool merged_opt;            // dW GEMM + reduction + Adam in one launch (MINPPO_SPLIT_OPT=1 disables)
+  bool persistent;            // all E x M minibatch steps in ONE persistent launch (ppo_steps.cuh; MINPPO_PERSISTENT=0 disables)
+  int steps_per_launch;       // development probe (MINPPO_STEPS_PER_LAUNCH): minibatch steps per persistent launch (0 = all)
   int skip_mask;              // debug (MINPPO_SKIP): 1 = no fused step, 2 = no dW GEMM, 4 = no optimizer (timing ablation only)
   int32_t *perms, *rowidx, *counts;
   int32_t* perm_tmp;          // world_size > 1: the epochs THIS rank sorts ([ceil(E / W)][B]); broadcast into perms
@@ -364,6 +367,7 @@ static int init_kernel_attrs() {
   CK(cudaFuncSetAttribute(dwopt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(dwopt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(dwopt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(steps_init_attrs());
   return 0;
 }
 
@@ -434,6 +438,79 @@ static int nccl_allreduce(minppo_ctx* c, float* buf, size_t n, cudaStream_t stre
   return 0;
 }
 
+// ---- parameter blocks of the per-minibatch kernels (shared by the per-step launches and the persistent kernel) ----
+static void fill_fused_params(minppo_ctx* c, const UpdatePtrs& u, FusedParams* pp) {
+  FusedParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  const int H = c->H;
+  for (int net = 0; net < 2; ++net) {
+    FusedNet& g = p.net[net];
+    NetBufs& nb = c->net[net];
+    g.tm_w0 = nb.m_wn_h[0]; g.tm_w1 = nb.m_wn_h[1]; g.tm_w1k = nb.m_w1k_h;
+    g.tm_h1 = nb.m_act_k[1]; g.tm_dz2 = nb.m_dz_k[2]; g.tm_dz1 = nb.m_dz_k[1];
+    g.b0 = u.params + find_leaf(c, net, 0, 0).offset;
+    g.b1 = u.params + find_leaf(c, net, 1, 0).offset;
+    g.w2img = reinterpret_cast<const uint4*>(nb.w2img);
+    g.b2 = u.params + find_leaf(c, net, 2, 0).offset;
+    g.act = act_kind(c, net);
+    g.aout = net == 0 ? c->A : 1;
+    g.po_w2 = net == 0 ? c->po_w3a : c->po_w3c;
+    g.po_b2 = net == 0 ? c->po_b3a : c->po_b3c;
+    g.po_loss = c->po_loss + (net == 0 ? 1 : 0);          // [0] = sum max(vl, vlc), [1] = sum min(l1, l2)
+    g.po_db0 = c->po_db[net][0]; g.po_db1 = c->po_db[net][1];
+  }
+  p.rowidx = c->rowidx; p.obs_img = c->obs_img; p.count = c->counts; p.step = 0;
+  p.tm_xg = c->m_xg_k; p.store_x = c->store_x ? 1 : 0;
+  p.adv_sum = c->stats; p.adv_sq = c->stats + c->E * c->M;
+  p.action = u.action; p.v_old = u.value; p.logp_old = u.log_prob; p.adv = c->adv; p.tgt = c->tgt;
+  p.log_std = u.params + c->leaves.back().offset;
+  p.part = c->head_part; p.part_stride = c->head_stride; p.po_logstd = c->po_logstd;
+  p.H = H; p.A = c->A; p.Dp = c->Dp; p.m_tiles = c->m_tiles; p.cap = c->cap;
+  p.inv_mb = static_cast<float>(1.0 / c->mb);
+  p.clip_eps = static_cast<float>(c->cfg.clip_eps); p.vf_coef = static_cast<float>(c->cfg.vf_coef);
+  p.trace = c->trace_on ? c->trace : nullptr;
+}
+
+// weight-gradient GEMM groups + optimizer block + per-update arrays; returns the number of GEMM CTAs
+static int fill_dwopt_params(minppo_ctx* c, const UpdatePtrs& u, DwOptParams* dpp) {
+  DwOptParams& dp = *dpp;
+  memset(&dp, 0, sizeof(dp));
+  const int L = c->L, H = c->H;
+  GemmParams& p = dp.gemm;
+  int cta = 0, ng = 0;
+  for (int net = 0; net < 2; ++net) {
+    NetBufs& nb = c->net[net];
+    for (int l = 0; l < L; ++l) {
+      GemmGroup& g = p.g[ng++];
+      g.cta_begin = cta;
+      const int in_l = l == 0 ? c->D : H;
+      const int in_pad = l == 0 ? c->Dp : H;
+      if (l == 0 && c->fused && c->store_x && !(c->skip_mask & 1)) { g.amode = A_TMA_MN; g.tmA = c->m_xg_mn; }   // rows gathered by the fused kernel
+      else if (l == 0) { g.amode = A_GATHER_MN; g.rowidx = c->rowidx; g.gimage = c->obs_img; g.ldg = c->Dp; }      // row list: per step
+      else { g.amode = A_TMA_MN; g.tmA = nb.m_act_mn[l]; }
+      g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
+      g.kb_total = c->M_pad / 64;
+      g.k_count = nullptr;                                    // per step (counts[] below)
+      g.tmC = nb.m_dw[l];
+      g.colsum_out = c->fused ? nullptr : nb.dbias[l];      // fused path: the bias gradients come from the fused step kernel
+      g.N = H; g.m_tiles = (in_pad + 127) / 128; g.splits = c->S; g.m_store = in_l;
+      cta += g.m_tiles * g.splits;
+    }
+  }
+  p.ngroups = ng;
+  fill_opt_args(c, u, &dp.opt);
+  dp.opt.losses_out = u.losses_out ? u.losses_out : c->losses_scratch;
+  dp.losses_stride = u.losses_out ? 4 : 0;
+  dp.opt.gnorm_out = c->gnorms;
+  dp.gemm_ctas = cta;
+  dp.ridx_base = c->rowidx; dp.counts = c->counts; dp.cap = c->cap; dp.EM = c->E * c->M;
+  dp.padded = c->padded ? 1 : 0;
+  dp.part_rows = c->fused ? 128 : 64;
+  dp.prefetch = 1; dp.obs_img = c->obs_img; dp.obs_ld = c->Dp;
+  dp.trace = c->trace_on ? c->trace2 : nullptr;
+  return cta;
+}
+
 // ---- one minibatch step --------------------------------------------------------------------
 static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t stream) {
   const int L = c->L, H = c->H;
@@ -444,33 +521,8 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
   } else if (c->fused) {
     // forward + heads + loss + backward-to-dZ of both nets in one launch (fused_step.cuh)
     FusedParams p;
-    memset(&p, 0, sizeof(p));
-    for (int net = 0; net < 2; ++net) {
-      FusedNet& g = p.net[net];
-      NetBufs& nb = c->net[net];
-      g.tm_w0 = nb.m_wn_h[0]; g.tm_w1 = nb.m_wn_h[1]; g.tm_w1k = nb.m_w1k_h;
-      g.tm_h1 = nb.m_act_k[1]; g.tm_dz2 = nb.m_dz_k[2]; g.tm_dz1 = nb.m_dz_k[1];
-      g.b0 = u.params + find_leaf(c, net, 0, 0).offset;
-      g.b1 = u.params + find_leaf(c, net, 1, 0).offset;
-      g.w2img = reinterpret_cast<const uint4*>(nb.w2img);
-      g.b2 = u.params + find_leaf(c, net, 2, 0).offset;
-      g.act = act_kind(c, net);
-      g.aout = net == 0 ? c->A : 1;
-      g.po_w2 = net == 0 ? c->po_w3a : c->po_w3c;
-      g.po_b2 = net == 0 ? c->po_b3a : c->po_b3c;
-      g.po_loss = c->po_loss + (net == 0 ? 1 : 0);          // [0] = sum max(vl, vlc), [1] = sum min(l1, l2)
-      g.po_db0 = c->po_db[net][0]; g.po_db1 = c->po_db[net][1];
-    }
-    p.rowidx = ridx; p.obs_img = c->obs_img; p.count = c->counts + s;
-    p.tm_xg = c->m_xg_k; p.store_x = c->store_x ? 1 : 0;
-    p.adv_sum = c->stats + s; p.adv_sq = c->stats + c->E * c->M + s;
-    p.action = u.action; p.v_old = u.value; p.logp_old = u.log_prob; p.adv = c->adv; p.tgt = c->tgt;
-    p.log_std = u.params + c->leaves.back().offset;
-    p.part = c->head_part; p.part_stride = c->head_stride; p.po_logstd = c->po_logstd;
-    p.H = H; p.A = c->A; p.Dp = c->Dp; p.m_tiles = c->m_tiles; p.cap = c->cap;
-    p.inv_mb = static_cast<float>(1.0 / c->mb);
-    p.clip_eps = static_cast<float>(c->cfg.clip_eps); p.vf_coef = static_cast<float>(c->cfg.vf_coef);
-    p.trace = c->trace_on ? c->trace : nullptr;
+    fill_fused_params(c, u, &p);
+    p.step = s;
     PROF(PC_FWD_GEMM);
     const cudaError_t e = c->ap == 16
         ? launch_kernel(fused_step_kernel<16>, 2 * c->m_tiles, FS_THREADS, FsLayout<16>::BYTES, stream, pdl, p)
@@ -553,44 +605,14 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
   // Default: ONE launch (dwopt.cuh).  MINPPO_SPLIT_OPT=1, a grid that does not fit one CTA per SM or
   // the timing ablation fall back to the two-launch sequence (GEMM kernel, opt_kernel).
   DwOptParams dp;
-  memset(&dp, 0, sizeof(dp));
+  const int cta = fill_dwopt_params(c, u, &dp);
+  dp.step = s;
   GemmParams& p = dp.gemm;
-  int cta = 0;
-  {
-    int ng = 0;
-    for (int net = 0; net < 2; ++net) {
-      NetBufs& nb = c->net[net];
-      for (int l = 0; l < L; ++l) {
-        GemmGroup& g = p.g[ng++];
-        g.cta_begin = cta;
-        const int in_l = l == 0 ? c->D : H;
-        const int in_pad = l == 0 ? c->Dp : H;
-        if (l == 0 && c->fused && c->store_x && !(c->skip_mask & 1)) { g.amode = A_TMA_MN; g.tmA = c->m_xg_mn; }   // rows gathered by the fused kernel
-        else if (l == 0) { g.amode = A_GATHER_MN; g.rowidx = ridx; g.gimage = c->obs_img; g.ldg = c->Dp; }
-        else { g.amode = A_TMA_MN; g.tmA = nb.m_act_mn[l]; }
-        g.bmode = B_TMA_MN; g.tmB = nb.m_dz_mn[l + 1];
-        g.kb_total = c->M_pad / 64;
-        g.k_count = c->padded ? c->counts + s : nullptr;
-        g.tmC = nb.m_dw[l];
-        g.colsum_out = c->fused ? nullptr : nb.dbias[l];      // fused path: the bias gradients come from the fused step kernel
-        g.N = H; g.m_tiles = (in_pad + 127) / 128; g.splits = c->S; g.m_store = in_l;
-        cta += g.m_tiles * g.splits;
-      }
-    }
-    p.ngroups = ng;
-  }
   OptArgs& o = dp.opt;
-  fill_opt_args(c, u, &o);
-  o.losses_out = u.losses_out ? u.losses_out + static_cast<size_t>(s) * 4 : c->losses_scratch;
-  o.gnorm_out = c->gnorms + s;
   const bool sharded = c->cfg.world_size > 1;
   const bool merged = c->merged_opt && c->skip_mask == 0 && cta <= c->sm_count;
   if (merged) {
-    dp.gemm_ctas = cta;
-    if (s + 1 < c->E * c->M) { dp.next_ridx = ridx + c->cap; dp.obs_img = c->obs_img; dp.next_rows = c->cap; dp.obs_ld = c->Dp; }
-    if (c->padded) { dp.row_count = c->counts + s; dp.next_count = c->counts + s + 1; dp.part_rows = c->fused ? 128 : 64; }
-    dp.trace = c->trace_on ? c->trace2 : nullptr;
-    // all-reduce fused into this launch (peer memory); needs the one-unit-per-thread fast path of the kernel
+    // all-reduce fused into this launch (peer memory); needs the register-resident fast path of the kernel
     const bool px_on = sharded && c->peers_set && c->P <= dwopt_fast_capacity(c->sm_count, c->maxu);
     if (px_on) { dp.px = c->px; dp.px.ablate = getenv("MINPPO_PX_ABLATE") ? atoi(getenv("MINPPO_PX_ABLATE")) : 0; }
     o.do_reduce = 1; o.do_apply = (sharded && !px_on) ? 0 : 1;
@@ -602,12 +624,20 @@ static int enqueue_step(minppo_ctx* c, const UpdatePtrs& u, int s, cudaStream_t 
     }
     if (sharded && !px_on) {
       { PROF(PC_ALLREDUCE); RET(nccl_allreduce(c, c->gflat, static_cast<size_t>(c->P) + 2, stream)); }
+      o.losses_out = o.losses_out + static_cast<size_t>(s) * dp.losses_stride; o.gnorm_out = c->gnorms + s;   // opt_kernel: direct pointers
       o.do_reduce = 0; o.do_apply = 1;
       { PROF(PC_OPT); RET(opt_launch(o, c->opt_blocks, stream, pdl)); }
       c->launches += 2;
     }
     return 0;
   }
+  // two-launch fallback (stand-alone GEMM kernel + opt_kernel): per-step pointers go into the blocks directly
+  for (int i = 0; i < p.ngroups; ++i) {
+    if (p.g[i].rowidx) p.g[i].rowidx = ridx;
+    p.g[i].k_count = c->padded ? c->counts + s : nullptr;
+  }
+  o.losses_out = o.losses_out + static_cast<size_t>(s) * dp.losses_stride;
+  o.gnorm_out = c->gnorms + s;
   if (!(c->skip_mask & 2)) {
     PROF(PC_DW_GEMM);
     RET(launch_gemm<EPI_PARTIAL>(p, cta, stream, pdl));
@@ -707,6 +737,29 @@ static int enqueue_update(minppo_ctx* c, const UpdatePtrs& u, cudaStream_t strea
       PROF(PC_WEIGHT_IMAGES);
       RET(weight_images_launch(o, stream));
       c->launches++;
+    }
+  }
+  // The E x M minibatch steps: ONE persistent launch (ppo_steps.cuh) when the fused path applies and the optimizer can
+  // run inside it (single GPU, or env-sharded ranks with the peer-memory exchange); otherwise two launches per step.
+  if (c->persistent && c->fused && c->merged_opt && c->skip_mask == 0 && !c->profiling) {
+    StepsParams sp;
+    memset(&sp, 0, sizeof(sp));
+    fill_fused_params(c, u, &sp.fs);
+    const int cta = fill_dwopt_params(c, u, &sp.dw);
+    const bool sharded = cfg.world_size > 1;
+    const bool px_on = sharded && c->peers_set && c->P <= dwopt_fast_capacity(c->sm_count, c->maxu);
+    if (cta <= c->sm_count && (!sharded || px_on)) {
+      if (px_on) { sp.dw.px = c->px; sp.dw.px.ablate = getenv("MINPPO_PX_ABLATE") ? atoi(getenv("MINPPO_PX_ABLATE")) : 0; }
+      sp.dw.opt.do_reduce = 1; sp.dw.opt.do_apply = 1;
+      sp.units = 2 * c->m_tiles;
+      const int chunk = c->steps_per_launch > 0 ? c->steps_per_launch : EM;
+      for (int s0 = 0; s0 < EM; s0 += chunk) {
+        sp.s0 = s0; sp.s1 = std::min(EM, s0 + chunk);
+        const cudaError_t e = steps_launch(sp, c->sm_count, stream, c->ap, c->maxu);
+        if (e != cudaSuccess) { set_error("ppo_steps launch failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
+        c->launches++;
+      }
+      return 0;
     }
   }
   for (int s = 0; s < EM; ++s) RET(enqueue_step(c, u, s, stream));
@@ -917,6 +970,8 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   c->pdl = !(getenv("MINPPO_PDL") && atoi(getenv("MINPPO_PDL")) == 0);
   c->merged_opt = !(getenv("MINPPO_SPLIT_OPT") && atoi(getenv("MINPPO_SPLIT_OPT")) != 0);
   c->skip_mask = getenv("MINPPO_SKIP") ? atoi(getenv("MINPPO_SKIP")) : 0;
+  c->persistent = !(getenv("MINPPO_PERSISTENT") && atoi(getenv("MINPPO_PERSISTENT")) == 0);
+  c->steps_per_launch = getenv("MINPPO_STEPS_PER_LAUNCH") ? atoi(getenv("MINPPO_STEPS_PER_LAUNCH")) : 0;
   ALLOC(c->perms, static_cast<size_t>(c->E) * c->B);
   c->perm_tmp = nullptr;
   c->share_perm = cfg->world_size > 1 && !(getenv("MINPPO_SHARE_PERM") && atoi(getenv("MINPPO_SHARE_PERM")) == 0);

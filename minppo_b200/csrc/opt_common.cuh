@@ -106,9 +106,10 @@ MINPPO_DEVINL void write_images(const OptLeaf& L, int i, float p) {
 // Kernel parameters live in the constant bank; indexing them with a run-time leaf index costs one
 // dependent LDC per field (the first merged kernel spent most of its optimizer phases there).  Every
 // CTA copies the table to shared memory once and the strided loops below walk it monotonically.
+constexpr int OPT_TAB_LEAVES = 20;   // >= 4 (num_layers + 1) + 1 leaves for num_layers <= 3 (validate_config); static shared memory is scarce
 struct LeafTab {
-  OptLeaf leaf[MINPPO_MAX_LEAVES];
-  int size[MINPPO_MAX_LEAVES];
+  OptLeaf leaf[OPT_TAB_LEAVES];
+  int size[OPT_TAB_LEAVES];
   int nleaves;
   int n_early;                   // elements of the leaves with late == 0
 };

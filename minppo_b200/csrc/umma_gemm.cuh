@@ -97,8 +97,13 @@ MINPPO_DEVINL float warp_colsum32(float (&v)[32]) {
 // in the two CTA-wide barriers.
 struct GemmNoIdle { MINPPO_DEVINL void operator()() const {} };
 // `idle` runs on the helper warps (warps >= 6, if the caller has any) while the GEMM is in flight.
+// Persistent callers (ppo_steps.cuh) pass the TMEM base they allocated once (`ext_tmem`; 0xFFFFFFFF = allocate and free
+// here), per-step overrides of the gather row list / valid-row count, and get the mbarriers re-initialised on every call.
+constexpr uint32_t GEMM_NO_TMEM = 0xFFFFFFFFu;
 template <int EPI, typename IdleFn = GemmNoIdle>
-MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long long* trace = nullptr, IdleFn idle = IdleFn()) {
+MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long long* trace = nullptr, IdleFn idle = IdleFn(),
+                                  uint32_t ext_tmem = GEMM_NO_TMEM, const int32_t* step_rowidx = nullptr,
+                                  const int32_t* step_kcount = nullptr) {
 #define GEMM_STAMP(slot) do { if (trace) trace[(slot)] = clock64(); } while (0)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                      // SWIZZLE_128B: 1024-B aligned tiles
@@ -122,7 +127,8 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
   const int split = rem % G.splits;
   // K extent: all of it, or only the k-blocks holding valid rows (env-sharded minibatches are padded to a worst-case
   // capacity; the count is device data and identical for every CTA of the launch)
-  const int kb_total = G.k_count ? min(G.kb_total, (max(*G.k_count, 0) + GEMM_BK - 1) / GEMM_BK) : G.kb_total;
+  const int32_t* kcount = step_kcount ? step_kcount : G.k_count;
+  const int kb_total = kcount ? min(G.kb_total, (max(*kcount, 0) + GEMM_BK - 1) / GEMM_BK) : G.kb_total;
   const int kb_per = (kb_total + G.splits - 1) / G.splits;
   const int kb0 = split * kb_per;
   const int kb1 = min(kb_total, kb0 + kb_per);
@@ -152,14 +158,14 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
     for (int c = 0; c < GEMM_MAXN / 32; ++c) mbar_init(&chunk_bar[c], 4);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 1 && ext_tmem == GEMM_NO_TMEM) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = ext_tmem == GEMM_NO_TMEM ? *tmem_slot : ext_tmem;
   if (threadIdx.x == 64) GEMM_STAMP(6);                 // prologue done
 
   // EPI_PARTIAL: warps beyond the six role warps (a caller running more warps per CTA, dwopt.cuh) help draining the
@@ -178,6 +184,8 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
       tma_prefetch_desc(&G.tmB);
       griddep_wait();                  // PDL (common.cuh): operands are written by the preceding kernel
       griddep_launch();
+      fence_proxy_async_global();      // persistent callers: the operands were published through a grid barrier (generic-proxy
+                                       // acquire) -- order the TMA (async-proxy) reads below after it
       GEMM_STAMP(7);                   // dependency wait passed
       const uint32_t a_bytes = kTmaA ? GEMM_A_BYTES : 0;
       const uint32_t b_bytes = static_cast<uint32_t>(N) * GEMM_BK * 2;
@@ -255,7 +263,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
     if (kGather) {
       // Row indices are prefetched 8 k-blocks at a time (one dependent global load per batch, not
       // per k-block) and up to GEMM_STAGES - 1 cp.async groups stay in flight before publishing.
-      const int32_t* ridx = G.rowidx;
+      const int32_t* ridx = step_rowidx ? step_rowidx : G.rowidx;
       constexpr int LAG = GEMM_STAGES - 1;
       const int c = et >> 6, kr = et & 63;
       const int row_k = (AMODE == A_GATHER_K) ? ridx[m_tile * GEMM_BM + et] : 0;
@@ -429,7 +437,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1 && ext_tmem == GEMM_NO_TMEM) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 template <int EPI>

@@ -12,9 +12,10 @@ from oracle import ppo_numpy as P
 from tests.helpers import hyper_to_config
 
 dev = torch.device("cuda:0")
-hp = bench.make_hyper(bench.workload(1))
+shape = bench.make_shape(bench.workload(1))
+hp = bench.make_hyper(shape)
 learner = Learner(hyper_to_config(hp, use_graph=False), bench.OBS_DIM, bench.ACT_DIM, dev)
-params, traj, last_val = bench.synth_shard(hp, 0, 1)
+params, traj, last_val = bench.synth_shard(shape, 0, 1)
 t = lambda x: torch.as_tensor(np.ascontiguousarray(x)).to(dev)
 mem = Memory(done=t(traj["done"]), action=t(traj["action"]), value=t(traj["value"]), reward=t(traj["reward"]),
              log_prob=t(traj["log_prob"]), obs=t(traj["obs"]))
@@ -28,11 +29,11 @@ out = torch.empty((n, 32), dtype=torch.int64, device=dev)
 _lib.check(learner.lib.minppo_ctx_read(learner._h, 7, out.data_ptr(), out.numel() * 8, torch.cuda.current_stream(dev).cuda_stream))
 torch.cuda.synchronize()
 tr = out.cpu().numpy()
-names = {26: "w: gather issued", 27: "w: loss inputs requested", 28: "w: griddep wait passed", 29: "w: staging loads issued", 30: "w: staging stored", 31: "w: gather landed, xfull arrive", 16: "kernel start (t0)", 0: "workers start", 1: "gather+stage done, xfull", 17: "mma: start", 18: "mma: xfull seen", 19: "mma: L1 issued",
+names = {26: "w: gather issued", 27: "w: loss inputs requested", 28: "w: griddep wait passed", 29: "w: staging loads issued", 30: "w: staging stored", 31: "w: all X blocks published", 16: "kernel start (t0)", 0: "workers start", 1: "gather+stage done, xfull", 17: "mma: start", 18: "mma: X block 0 seen", 19: "mma: L1 issued",
          2: "w: acc0 ready", 3: "w: epi1 done (h1r)", 20: "mma: h1r seen", 21: "mma: L2 issued", 4: "w: acc1 ready", 5: "w: epi2 done (h2r)",
          24: "mma: head fwd issued", 6: "w: head out ready", 7: "w: loss done + tile sums", 25: "mma: dA2/dW2 issued", 8: "w: bwd accs ready",
          9: "w: dz2 epilogue done (dz2r)", 22: "mma: dz2r seen", 23: "mma: dH1 issued", 10: "w: dh1 acc ready", 11: "w: epi3 done", 12: "w: stores done"}
-order = [16, 0, 17, 26, 27, 28, 29, 31, 30, 1, 18, 19, 2, 3, 20, 21, 4, 5, 24, 6, 7, 25, 8, 9, 22, 23, 10, 11, 12]
+order = [16, 0, 17, 26, 28, 31, 30, 1, 18, 19, 2, 3, 21, 4, 5, 24, 6, 7, 25, 8, 9, 23, 10, 11, 12]
 for cta in (0, 1, n // 2, n - 1):
     t0 = tr[cta, 16]
     print(f"--- CTA {cta} ({'actor' if cta < n // 2 else 'critic'})")
@@ -41,6 +42,14 @@ for cta in (0, 1, n // 2, n - 1):
         d = int(tr[cta, k] - t0)
         print(f"  {names[k]:34s} {d:8d}  (+{d - prev})")
         prev = d
+if os.environ.get("MINPPO_PERSISTENT", "1") != "0":
+    # persistent kernel: cta_id of the tile body is net-major, the loop stamps are in row b = blockIdx.x
+    print("--- persistent loop, last step, cycles (mean over CTAs 0..127 | max): step start -> phase A done -> barrier 1 passed -> dwopt done -> barrier 2 passed")
+    seg = [(13, 14, "phase A (fused tile)"), (14, 15, "grid barrier 1"), (15, 20, "dwopt body (GEMM + 2 barriers + reduce + Adam)"), (20, 22, "grid barrier 2")]
+    for a_, b_, name in seg:
+        d = tr[:n, b_] - tr[:n, a_]
+        print(f"  {name:48s} mean {d.mean():9.0f} min {d.min():9.0f} max {d.max():9.0f}")
+    print(f"  whole step (13 -> 22)                            mean {(tr[:n, 22] - tr[:n, 13]).mean():9.0f}")
 tot = tr[:, 12] - tr[:, 16]
 print("total cycles per CTA: actor mean", tot[:n // 2].mean(), "critic mean", tot[n // 2:].mean(), "max", tot.max())
 
@@ -60,6 +69,7 @@ for k in range(5):
 for gi in range(4):
     seg = d[32 * gi:32 * gi + 32, 0]
     print(f"  phase 1 of GEMM group {gi} (net {gi // 2}, layer {gi % 2}): mean {seg.mean():8.0f} min {seg.min():8.0f} max {seg.max():8.0f}")
+print(f"  leaf table + first CTA barrier (stamp 14): mean {(t2[:, 14] - t2[:, 0]).mean():8.0f}")
 gl = ["prologue done", "dependency wait passed", "first operands landed", "all MMAs issued", "accumulator complete (epilogue)", "tile staged in smem", "partial tile written"]
 print("  GEMM body, cycles since kernel start (mean over GEMM CTAs 32..127):")
 for k in range(7):
