@@ -618,8 +618,25 @@ def run_ours(args):
             p1.record()
             torch.cuda.synchronize(dev)
             pol = {"us_per_env_step": p0.elapsed_time(p1) / 50 * 1e3, "envs": hp.num_envs // world,
-                   "note": "eager launches incl. the host call path (obs image + L GEMM launches + head/sampler kernel), "
-                           "weights current"}
+                   "note": "eager call through the Python host (one fused launch: observation conversion + both hidden "
+                           "layers + heads + sampler), weights current"}
+            # the same call captured once into a CUDA graph and replayed (what a captured T-step rollout pays per env step)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            pg = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(pg, stream=side):
+                    learner.policy_step(ts.params, pobs, rng, weights_current=True)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            for _ in range(5):
+                pg.replay()
+            torch.cuda.synchronize(dev)
+            p0.record()
+            for _ in range(200):
+                pg.replay()
+            p1.record()
+            torch.cuda.synchronize(dev)
+            pol["graph_replay_us_per_env_step"] = p0.elapsed_time(p1) / 200 * 1e3
         except Exception as e:  # a measurement extra must never lose the bench line
             pol = {"error": str(e)[:200]}
 

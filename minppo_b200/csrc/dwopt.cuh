@@ -200,6 +200,9 @@ MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw,
     if (T.leaf[l].late) n_units += T.size[l] >> 2;
   const int GT_ = G * NT;
   const bool fast = n_units <= GT_ * MAXU;
+  // job number of this thread for the per-element work on the SMALL leaves (reduction, exchange, Adam).  (Dealing the jobs
+  // round-robin over the CTAs instead -- t * G + b -- was measured: every CTA's Adam phase then carries one more dependent
+  // load -> divide chain, 6.5k -> 12.5k cycles; concentrated on the first CTAs the chain hides behind the second barrier.)
   const int gtid = b * NT + t;
   float4 g4[MAXU];
   float pv[MAXU][4], mv[MAXU][4], nv[MAXU][4];

@@ -228,7 +228,7 @@ MINPPO_DEVINL void epilogue_dact(uint32_t tmem_acc, uint32_t h_base, uint32_t ds
 // One (tile, net) unit of one minibatch step.  The whole CTA (FS_THREADS threads) calls this with the SAME arguments;
 // `sm` / `base` = the 1024-byte aligned dynamic shared memory, `tmem_base` = 512 allocated TMEM columns.  The mbarriers
 // are (re-)initialised on entry, so a persistent caller may run any number of units back to back.
-template <int AP>
+template <int AP, bool PERSISTENT>
 MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t* sm, uint32_t base, uint32_t tmem_base) {
   using LY = FsLayout<AP>;
   constexpr int NS = LY::NS, NS1 = LY::NS1, PG = LY::PG, RS = LY::RS;
@@ -795,7 +795,10 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     // The bulk stores must have READ shared memory before it is reused, and -- for a persistent caller, whose next phase
     // reads H1 / dZ / X from other CTAs after a grid barrier, not after a kernel boundary -- their global writes must be
     // complete and ordered before this thread's later (generic-proxy) barrier arrival.
-    if (wt == 32 || x_store) { tma_store_wait_all0(); fence_proxy_async_global(); }
+    if (wt == 32 || x_store) {
+      if (PERSISTENT) { tma_store_wait_all0(); fence_proxy_async_global(); }
+      else tma_store_wait_read0();                                 // one launch per step: the writes complete with the grid
+    }
     if (wt == 0) FS_STAMP(12);
   }
 
@@ -824,10 +827,10 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    fused_tile<AP>(p, unit, p.step, sm, base, tmem_base);
+    fused_tile<AP, false>(p, unit, p.step, sm, base, tmem_base);
     if (warp == FS_MMA_WARP) tmem_dealloc(tmem_base, 512);
   } else {
-    fused_tile<AP>(p, unit, p.step, sm, base, 0u);                // dead tile: zeroes its partials and returns
+    fused_tile<AP, false>(p, unit, p.step, sm, base, 0u);                // dead tile: zeroes its partials and returns
   }
 }
 

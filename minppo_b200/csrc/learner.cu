@@ -29,6 +29,7 @@
 #include "fused_step.cuh"
 #include "dwopt.cuh"
 #include "ppo_steps.cuh"
+#include "policy_fused.cuh"
 
 namespace minppo {
 
@@ -368,6 +369,7 @@ static int init_kernel_attrs() {
   CK(cudaFuncSetAttribute(dwopt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(dwopt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(steps_init_attrs());
+  CK(policy_fused_init_attrs());
   return 0;
 }
 
@@ -1111,6 +1113,39 @@ int minppo_policy_step(minppo_ctx* c, const float* params, const float* obs, con
   if (!actor && !value) { set_error("minppo_policy_step: no output requested"); return MINPPO_ERR_ARG; }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int L = c->L, H = c->H;
+  if (c->fused && !(getenv("MINPPO_POLICY_LAYERWISE") && atoi(getenv("MINPPO_POLICY_LAYERWISE")) != 0)) {
+    // 2-hidden-layer nets: ONE launch (policy_fused.cuh) -- observation conversion, both hidden layers, heads, sampler
+    if (!(flags & MINPPO_POLICY_WEIGHTS_CURRENT)) {
+      UpdatePtrs u;
+      memset(&u, 0, sizeof(u));
+      u.params = const_cast<float*>(params);               // weight_images only reads the arena
+      OptArgs o;
+      fill_opt_args(c, u, &o);
+      RET(weight_images_launch(o, stream));
+    }
+    PolicyParams pp;
+    memset(&pp, 0, sizeof(pp));
+    for (int net = 0; net < 2; ++net) {
+      PolicyNet& g = pp.net[net];
+      NetBufs& nb = c->net[net];
+      g.tm_w0 = nb.m_wn_h[0]; g.tm_w1 = nb.m_wn_h[1];
+      g.b0 = params + find_leaf(c, net, 0, 0).offset;
+      g.b1 = params + find_leaf(c, net, 1, 0).offset;
+      g.w2img = reinterpret_cast<const uint4*>(nb.w2img);
+      g.b2 = params + find_leaf(c, net, 2, 0).offset;
+      g.act = act_kind(c, net);
+      g.aout = net == 0 ? c->A : 1;
+    }
+    pp.obs = obs; pp.log_std = params + c->leaves.back().offset;
+    pp.key_in = actor ? key_in : nullptr; pp.key_out = actor ? key_out : nullptr;
+    pp.action = action; pp.log_prob = log_prob; pp.value = value; pp.mean_out = mean;
+    pp.n0 = c->n0; pp.n_total = static_cast<long long>(c->N) * c->A;
+    pp.rows = c->Nl; pp.D = c->D; pp.Dp = c->Dp; pp.H = H; pp.A = c->A; pp.mode = c->cfg.prng_mode;
+    pp.net_first = actor ? 0 : 1;
+    const cudaError_t e = policy_fused_launch(pp, c->pol_tiles, stream, c->ap);
+    if (e != cudaSuccess) { set_error("policy_fused launch failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
+    return 0;
+  }
   // bf16 image of last_obs, zero padded to Dp columns (rows >= Nl of the image stay zero from allocation)
   RET(obs_image_launch(obs, c->pol_img, c->Nl, c->D, c->Dp, stream));
   if (!(flags & MINPPO_POLICY_WEIGHTS_CURRENT)) {

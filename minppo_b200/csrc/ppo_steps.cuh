@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) ppo_steps_kernel(const __grid_c
 #define PS_STAMP(slot) do { if (tr) tr[(slot)] = clock64(); } while (0)
   for (int s = P.s0; s < P.s1; ++s) {
     PS_STAMP(13);
-    for (int u = b; u < P.units; u += G) fused_tile<AP>(P.fs, u, s, sm, base, tmem_base);
+    for (int u = b; u < P.units; u += G) fused_tile<AP, true>(P.fs, u, s, sm, base, tmem_base);
     PS_STAMP(14);
     grid_barrier(P.dw.opt.barrier, P.dw.opt.err_flag);
     PS_STAMP(15);

@@ -150,6 +150,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
   }
 
   if (threadIdx.x == 0) {
+    GEMM_STAMP(13);
     for (int s = 0; s < GEMM_STAGES; ++s) {
       mbar_init(&full_bar[s], 1 + (kGather ? GEMM_EPI_THREADS : 0));
       mbar_init(&empty_bar[s], 1);
@@ -157,6 +158,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
     mbar_init(tmem_full_bar, 1);
     for (int c = 0; c < GEMM_MAXN / 32; ++c) mbar_init(&chunk_bar[c], 4);
     fence_mbar_init();
+    GEMM_STAMP(15);
   }
   if (warp == 1 && ext_tmem == GEMM_NO_TMEM) {
     tmem_alloc(tmem_slot, kTmemCols);

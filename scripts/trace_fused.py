@@ -70,6 +70,7 @@ for gi in range(4):
     seg = d[32 * gi:32 * gi + 32, 0]
     print(f"  phase 1 of GEMM group {gi} (net {gi // 2}, layer {gi % 2}): mean {seg.mean():8.0f} min {seg.min():8.0f} max {seg.max():8.0f}")
 print(f"  leaf table + first CTA barrier (stamp 14): mean {(t2[:, 14] - t2[:, 0]).mean():8.0f}")
+print(f"  GEMM body entered / mbarriers initialised (stamps 13, 15; single GPU only): {(t2[32:128, 13] - t2[32:128, 0]).mean():8.0f} {(t2[32:128, 15] - t2[32:128, 0]).mean():8.0f}")
 gl = ["prologue done", "dependency wait passed", "first operands landed", "all MMAs issued", "accumulator complete (epilogue)", "tile staged in smem", "partial tile written"]
 print("  GEMM body, cycles since kernel start (mean over GEMM CTAs 32..127):")
 for k in range(7):

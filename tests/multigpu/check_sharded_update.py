@@ -81,6 +81,17 @@ def main():
                 "losses": rel_err(got["losses"], ref["losses"]) < 2e-3,
                 "params": float(np.abs(got["params"] - ref["params"]).max()) < lr * (2.0 + 0.15 * nsteps),
             }
+            if name == "small":
+                # ... and against the ORACLE at world > 1 (not only against the single-GPU run of the same kernels): the two
+                # updates of run() restated on the global batch with the same bf16 rounding points
+                p_o = P.tree_like(pr["params"], lambda x: x.astype(np.float32))
+                o_o = P.init_opt_state(p_o)
+                for _ in range(2):
+                    p_o, o_o, rng_o, l_o, aux_o = P.update(p_o, o_o, pr["traj"], pr["last_val"], pr["rng"], hp, dtype=np.float32, gemm="bf16")
+                flat_o = P.flatten_params(p_o, hp.num_layers, np.float64)
+                checks["losses vs oracle (bf16 rounding emulated)"] = rel_err(got["losses"], l_o) < 2e-3
+                checks["perms vs oracle bit-exact"] = bool(np.array_equal(got["perms"], aux_o["perms"]))
+                checks["params vs oracle rms <= 1 lr"] = float(np.sqrt(np.mean((got["params"] - flat_o) ** 2))) < lr
             print(f"[{name}] world={world} rows/rank/minibatch={got['counts'][:4].tolist()} "
                   f"loss rel err {rel_err(got['losses'], ref['losses']):.2e} "
                   f"max |dparam| {np.abs(got['params'] - ref['params']).max():.2e}  {checks}", flush=True)
