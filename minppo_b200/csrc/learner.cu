@@ -972,7 +972,10 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   c->pdl = !(getenv("MINPPO_PDL") && atoi(getenv("MINPPO_PDL")) == 0);
   c->merged_opt = !(getenv("MINPPO_SPLIT_OPT") && atoi(getenv("MINPPO_SPLIT_OPT")) != 0);
   c->skip_mask = getenv("MINPPO_SKIP") ? atoi(getenv("MINPPO_SKIP")) : 0;
-  c->persistent = !(getenv("MINPPO_PERSISTENT") && atoi(getenv("MINPPO_PERSISTENT")) == 0);
+  // Measured (profiles/r02_persistent_vs_per_step.txt): the persistent kernel is 0.3 ms per update SLOWER at 1 GPU and 0.5 ms
+  // at 2 -- a grid barrier (release fence + atomic + acquire poll, ~2.2k cycles before skew) costs as much as a kernel boundary
+  // under programmatic dependent launch, and it needs four per step against two boundaries + two barriers.  Off by default.
+  c->persistent = getenv("MINPPO_PERSISTENT") && atoi(getenv("MINPPO_PERSISTENT")) != 0;
   c->steps_per_launch = getenv("MINPPO_STEPS_PER_LAUNCH") ? atoi(getenv("MINPPO_STEPS_PER_LAUNCH")) : 0;
   ALLOC(c->perms, static_cast<size_t>(c->E) * c->B);
   c->perm_tmp = nullptr;
