@@ -311,7 +311,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     if (elect_one()) {
       tma_prefetch_desc(&G.tm_w0); tma_prefetch_desc(&G.tm_w1); tma_prefetch_desc(&G.tm_w1k);
       griddep_wait();                 // the weight images are rewritten by the previous optimizer step
-      fence_proxy_async_global();     // persistent caller: they were published through a grid barrier (generic-proxy acquire)
+      if (PERSISTENT) fence_proxy_async_global();   // ... published through a grid barrier (generic-proxy acquire)
       const uint32_t bytes = static_cast<uint32_t>(H) * 64u;
       // ---- L1: W0 half-k-blocks j = 0 .. 2 nk0 - 1 through NS1 stages (the ring + four stages parked in R0, which nothing
       //      touches before epilogue 1: for Dp <= 256 the whole L1 GEMM is fed up front)

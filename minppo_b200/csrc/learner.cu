@@ -374,7 +374,9 @@ static int init_kernel_attrs() {
 }
 
 template <int EPI>
-static int launch_gemm(const GemmParams& p, int ctas, cudaStream_t stream, bool pdl = false) {
+static int launch_gemm(const GemmParams& p_in, int ctas, cudaStream_t stream, bool pdl = false) {
+  GemmParams p = p_in;
+  gemm_finalize(p);
   const cudaError_t e = launch_kernel(umma_gemm_kernel<EPI>, ctas, GEMM_THREADS, GEMM_SMEM_BYTES, stream, pdl, p);
   if (e != cudaSuccess) { set_error("umma_gemm launch failed: %s", cudaGetErrorString(e)); return MINPPO_ERR_CUDA; }
   return 0;
@@ -411,6 +413,11 @@ static void fill_opt_args(const minppo_ctx* c, const UpdatePtrs& u, OptArgs* o) 
     }
   }
   o->nleaves = n;
+  o->n_early = 0;
+  for (int i = 0; i < n; ++i) {
+    o->leaf[i].size = (i + 1 < n ? o->leaf[i + 1].offset : static_cast<int>(c->P)) - o->leaf[i].offset;
+    if (!o->leaf[i].late) o->n_early += o->leaf[i].size;
+  }
   o->keep_gflat = 1;                         // minppo_ctx_read(what=3) returns the last reduced gradient
   o->P = static_cast<int>(c->P);
   o->A = c->A;
@@ -500,6 +507,7 @@ static int fill_dwopt_params(minppo_ctx* c, const UpdatePtrs& u, DwOptParams* dp
     }
   }
   p.ngroups = ng;
+  gemm_finalize(p);
   fill_opt_args(c, u, &dp.opt);
   dp.opt.losses_out = u.losses_out ? u.losses_out : c->losses_scratch;
   dp.losses_stride = u.losses_out ? 4 : 0;

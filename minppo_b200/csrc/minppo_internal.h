@@ -100,11 +100,13 @@ struct OptLeaf {
   uint8_t* img_w2;               // output-head kernels: 16 KB bf16 hi / lo image of kernel^T in the fused kernel's
                                  // shared-memory layout (fused_step.cuh FS_W2T), or null
   int late;                      // 1: partials are written by the dW GEMM of the same launch (hidden kernels)
+  int size;                      // elements of this leaf (host-computed: the kernels never walk the table serially)
   int ap;                        // img_w2: padded head width of the image (16 or 32 rows per hi / lo half)
 };
 struct OptArgs {
   OptLeaf leaf[MINPPO_MAX_LEAVES];
   int nleaves, P, A;
+  int n_early;                   // elements of the leaves with late == 0
   int do_reduce, do_apply;
   int keep_gflat;                // also store the reduced gradient when reduce+apply are fused (tests)
   float* gflat;                  // [P + 4]

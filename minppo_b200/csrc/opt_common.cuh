@@ -114,19 +114,14 @@ struct LeafTab {
   int n_early;                   // elements of the leaves with late == 0
 };
 MINPPO_DEVINL void leaf_tab_build(LeafTab& T, const OptArgs& a, int tid, int nthreads) {
+  // every word by a different thread: the constant-bank misses of a cold launch overlap instead of queueing behind one
+  // thread (a serial walk over the leaves by thread 0 cost ~3k cycles at the head of every launch)
   constexpr int WORDS = sizeof(OptLeaf) / 4;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(a.leaf);
   uint32_t* dst = reinterpret_cast<uint32_t*>(T.leaf);
   for (int w = tid; w < a.nleaves * WORDS; w += nthreads) dst[w] = src[w];
-  for (int l = tid; l < a.nleaves; l += nthreads)
-    T.size[l] = (l + 1 < a.nleaves ? a.leaf[l + 1].offset : a.P) - a.leaf[l].offset;
-  if (tid == 0) {
-    T.nleaves = a.nleaves;
-    int n = 0;
-    for (int l = 0; l < a.nleaves; ++l)
-      if (!a.leaf[l].late) n += (l + 1 < a.nleaves ? a.leaf[l + 1].offset : a.P) - a.leaf[l].offset;
-    T.n_early = n;
-  }
+  for (int l = tid; l < a.nleaves; l += nthreads) T.size[l] = a.leaf[l].size;
+  if (tid == nthreads - 1) { T.nleaves = a.nleaves; T.n_early = a.n_early; }
 }
 
 // fixed-order sum of `nparts` partials, 16 loads in flight
@@ -145,6 +140,13 @@ MINPPO_DEVINL float sum_partials16(const float* __restrict__ src, int nparts, si
   for (; p < nparts; ++p) acc += __ldcg(src + static_cast<size_t>(p) * stride);
   return acc;
 }
+// split-K partials: read once, written by another SM just before (L2-resident): no L1 allocation, 256-byte L2 sectors
+// (a warp reads 512 contiguous bytes of every partial)
+MINPPO_DEVINL float4 ld_partial_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
 // same, four consecutive elements at once (16-byte loads; src 16-byte aligned, stride % 4 == 0)
 MINPPO_DEVINL float4 sum_partials16_v4(const float* __restrict__ src, int nparts, size_t stride) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -153,7 +155,7 @@ MINPPO_DEVINL float4 sum_partials16_v4(const float* __restrict__ src, int nparts
   for (; p + 16 <= nparts; p += 16) {
     float4 v[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(p + u) * stride));
+    for (int u = 0; u < 16; ++u) v[u] = ld_partial_v4(src + static_cast<size_t>(p + u) * stride);
 #pragma unroll
     for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
   }

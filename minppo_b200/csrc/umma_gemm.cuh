@@ -63,9 +63,14 @@ struct alignas(64) GemmGroup {
 };
 
 struct alignas(64) GemmParams {
-  GemmGroup g[GEMM_MAX_GROUPS];
   int ngroups;                     // groups occupy consecutive blockIdx.x ranges starting at cta_begin
+  int grp_begin[GEMM_MAX_GROUPS];  // copy of g[i].cta_begin, unused entries INT_MAX (gemm_finalize): one constant-bank line
+                                   // instead of a dependent walk over the 512-byte group records at the head of every launch
+  GemmGroup g[GEMM_MAX_GROUPS];
 };
+inline void gemm_finalize(GemmParams& p) {
+  for (int i = 0; i < GEMM_MAX_GROUPS; ++i) p.grp_begin[i] = i < p.ngroups ? p.g[i].cta_begin : 0x7fffffff;
+}
 
 // ---- row-gather of one 128-byte line into a swizzled tile --------------------------------
 MINPPO_DEVINL void gather_line(uint32_t tile_base, int line, const __nv_bfloat16* src) {
@@ -119,7 +124,8 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
 
   const int warp = threadIdx.x >> 5;
   int grp = 0;
-  while (grp + 1 < p.ngroups && static_cast<int>(blockIdx.x) >= p.g[grp + 1].cta_begin) ++grp;
+#pragma unroll
+  for (int i = 1; i < GEMM_MAX_GROUPS; ++i) grp += static_cast<int>(blockIdx.x) >= p.grp_begin[i] ? 1 : 0;
   const GemmGroup& G = p.g[grp];
   const int rem = static_cast<int>(blockIdx.x) - G.cta_begin;
   const int AMODE = G.amode, BMODE = G.bmode;
@@ -186,8 +192,8 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
       tma_prefetch_desc(&G.tmB);
       griddep_wait();                  // PDL (common.cuh): operands are written by the preceding kernel
       griddep_launch();
-      fence_proxy_async_global();      // persistent callers: the operands were published through a grid barrier (generic-proxy
-                                       // acquire) -- order the TMA (async-proxy) reads below after it
+      if (ext_tmem != GEMM_NO_TMEM)    // persistent callers: the operands were published through a grid barrier (generic-proxy
+        fence_proxy_async_global();    // acquire) -- order the TMA (async-proxy) reads below after it
       GEMM_STAMP(7);                   // dependency wait passed
       const uint32_t a_bytes = kTmaA ? GEMM_A_BYTES : 0;
       const uint32_t b_bytes = static_cast<uint32_t>(N) * GEMM_BK * 2;
