@@ -84,6 +84,16 @@ class BenchShape:
         return self.batch_size // self.num_minibatches
 
 
+def bench_config(w, world: int, dims, hp, fast_tanh: bool):
+    """The `config` object of the JSON line -- identical on every arm (`--impl ours | reference`), so that the driver's
+    same-config check compares like with like."""
+    return {"workload": w["name"], "obs_dim": dims[0], "act_dim": dims[1],
+            "shape_note": f"D={dims[0]}/A={dims[1]} are a declared stand-in for stompy_pro (SURVEY.md F9)",
+            "parallelism": f"env-sharded dp{world}" if world > 1 else "single GPU",
+            "l2_policy": f"inputs larger than L2 (obs {hp.batch_size // world * dims[0] * 4 / 1e6:.0f} MB per update and GPU vs 126 MB L2)",
+            "fast_tanh": bool(fast_tanh)}
+
+
 def make_shape(w) -> BenchShape:
     return BenchShape(num_envs=w["num_envs"], num_steps=w["num_steps"], num_minibatches=w["num_minibatches"],
                       update_epochs=w["update_epochs"])
@@ -292,7 +302,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_upd * 1e3, "higher_is_better": True,
         "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["name"], "obs_dim": dims[0], "act_dim": dims[1], "shape_note": "D/A are a declared stand-in"},
+        "config": bench_config(w, args.gpus, dims, hp, bool(args.fast_tanh)),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": CPU_SAMPLE},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -506,10 +516,37 @@ def run_ours(args):
         learner.update_host(hb)          # blocks until the results are on the host
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    et_block = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(et_block, op=dist.ReduceOp.MAX)
+    e2e_blocking = {"value": B / float(et_block.item()), "unit": UNIT, "ms_per_step": float(et_block.item()) * 1e3,
+                    "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": hb.d2h_bytes(),
+                    "api": "Learner.update_host: blocking round trip, trajectory + FULL train state H2D, train state + losses D2H"}
+
+    # ---- end-to-end, streaming: HostPipeline (train state resident, trajectory H2D + params / losses D2H EVERY update,
+    #      the copy of update i + 1 under the kernels of update i) -----------------------------------------------------------
+    from minppo_b200.learner import HostPipeline
+
+    ts_pipe = TrainState.create(flat, dev)
+    pipe = HostPipeline(learner, ts_pipe, torch.tensor([0, 1337], dtype=torch.int32, device=dev))
+    host_traj = {k: hb.h[k] for k in ("obs", "action", "value", "reward", "log_prob", "done", "last_val")}
+    for _ in range(3):                                   # warm-up: both buffer sets, both cached graphs
+        pipe.submit(host_traj)
+        pipe.result()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        pipe.submit(host_traj)                           # H2D of THIS update's trajectory + the update + D2H of its results
+        if i >= 1:
+            pipe.result()                                # update i - 1 is on the host (losses, params)
+    pipe.result()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
     et = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_val = B / float(et.item())
+    e2e_h2d, e2e_d2h = pipe.h2d_bytes(), pipe.d2h_bytes()
 
     # ---- per-kernel-class timing (eager, CUDA events on the launching stream) ----------------------
     prof = None
@@ -555,8 +592,13 @@ def run_ours(args):
         if fused_path:
             flops = {"fwd_gemm": 2 * rows * ((F_hidden + F_heads) + (F_hidden - 2 * D * H + F_heads) + F_heads),
                      "dw_gemm": 2 * rows * F_hidden}
-            names = {"fwd_gemm": "fused_step_kernel (forward + heads + PPO loss + backward-to-dZ, both nets)",
-                     "dw_gemm": "dwopt_kernel (split-K weight gradients of all layers and both nets + gradient "
+            ap = 16 if A <= 16 else 32
+            n_par = 2 * (D * H + H + (L - 1) * (H * H + H)) + (H * A + A) + (H + 1) + A
+            nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+            maxu = 1 if n_par <= 4 * nsm * 512 else (2 if n_par <= 8 * nsm * 512 else 4)
+            names = {"fwd_gemm": f"fused_step_kernel<{ap}> (forward + heads + PPO loss + backward-to-dZ + bias-gradient column "
+                                 "sums, both nets)",
+                     "dw_gemm": f"dwopt_kernel<{maxu}> (split-K weight gradients of all layers and both nets + gradient "
                                 "reduction + global-norm clip + Adam, one launch)"}
         else:
             flops = {"fwd_gemm": 2 * rows * F_hidden / L, "bwd_gemm": 2 * rows * 2 * H * H, "dw_gemm": 2 * rows * F_hidden}
@@ -598,7 +640,12 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         gms = g0.elapsed_time(g1) / reps
         gbytes = Tg * Ng * 17 + 4 * Ng
-        gae_roof = {"bound": "hbm", "kernel": "gae_single_kernel<4,4>", "shape": [Tg, Ng], "achieved": gbytes / (gms * 1e-3) / 1e9,
+        # the launch plan of gae.cu (gae_plan): VEC = 4 when N % 4 == 0; one pass over T (gae_single_kernel<4, UNROLL>, UNROLL = 8
+        # below 1024 float4 columns per SM, else 4) unless fewer than 384 columns per SM force the T-chunked kernel
+        cols_per_sm = (Ng // 4) / torch.cuda.get_device_properties(dev).multi_processor_count
+        gae_kernel = ("gae_chunked_kernel<4, 4>" if cols_per_sm < 384 else
+                      ("gae_single_kernel<4, 8>" if cols_per_sm < 1024 else "gae_single_kernel<4, 4>"))
+        gae_roof = {"bound": "hbm", "kernel": gae_kernel, "shape": [Tg, Ng], "achieved": gbytes / (gms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": gbytes / (gms * 1e-3) / 1e9 / hbm_peak,
                     "frac_of_8TBs_spec": gbytes / (gms * 1e-3) / 1e9 / 8000.0, "bytes_per_transition": 17, "ms": gms,
                     "peak_source": peak_src}
@@ -680,14 +727,15 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "bf16 tensor-core GEMMs (fp32 accumulate), fp32 elsewhere", "data": "synthetic",
-            "config": {"workload": w["name"], "obs_dim": D_OBS, "act_dim": D_ACT,
-                       "shape_note": f"D={D_OBS}/A={D_ACT} are a declared stand-in for stompy_pro (SURVEY.md F9)",
-                       "parallelism": f"env-sharded dp{world}" if world > 1 else "single GPU",
-                       "l2_policy": f"inputs larger than L2 (obs {hp.batch_size // world * D_OBS * 4 / 1e6:.0f} MB per update and GPU vs 126 MB L2)",
-                       "fast_tanh": bool(args.fast_tanh), "sample_passes_per_s": value * hp.update_epochs},
+            "config": bench_config(w, world, (D_OBS, D_ACT), hp, bool(args.fast_tanh)),
+            "sample_passes_per_s": value * hp.update_epochs,
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": hb.d2h_bytes(),
-                    "ms_per_step": float(et.item()) * 1e3},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h,
+                    "ms_per_step": float(et.item()) * 1e3,
+                    "api": "HostPipeline.submit / result: pinned-host trajectory H2D and params + losses + rng D2H EVERY update, "
+                           "train state resident on the device, two updates in flight (the copy of update i + 1 runs under "
+                           "the kernels of update i)"},
+            "e2e_blocking": e2e_blocking,
             "gpu_launches": learner.launches_per_update() * args.steps,
             "launches_per_update": learner.launches_per_update(),
             "roofline": roofline, "gae_roofline": gae_roof, "kernel_classes": prof, "policy_step": pol,

@@ -16,7 +16,7 @@ from . import config, params  # noqa: F401  (pure Python; importing them never n
 
 def __getattr__(name):
     # learner pulls in torch; import lazily so that `import minppo_b200` stays light
-    if name in ("learner", "Learner", "Memory", "TrainState", "HostBatch", "calculate_gae", "permutations"):
+    if name in ("learner", "Learner", "Memory", "TrainState", "HostBatch", "HostPipeline", "calculate_gae", "permutations"):
         import importlib
 
         mod = importlib.import_module(".learner", __name__)

@@ -357,3 +357,85 @@ class HostBatch:
     def to_host(self) -> None:
         for k in self.OUT:
             self.h[k].copy_(self.d[k], non_blocking=True)
+
+
+class HostPipeline:
+    """Streaming host entry point: trajectories arrive in pinned HOST memory (remote / CPU rollout workers), the train
+    state lives on the device, and every update returns the new parameters and the losses to the host.
+
+    ``submit(traj)`` enqueues, without blocking: the H2D copy of that update's trajectory (+ last_val) on a copy stream
+    into one of two device buffer sets, the update on the compute stream (ordered after the copy by an event), and the
+    D2H copies of params / rng / losses into pinned host memory.  ``result()`` blocks until the OLDEST outstanding update
+    is on the host and returns (losses[E, M, 4], params[P]) views of pinned memory.  With two updates in flight the H2D
+    copy of update i + 1 runs under the kernels of update i -- every update still pays for its own copies, they just no
+    longer serialise with the compute (the reference keeps the trajectory on the device and has no such copy at all).
+    Updates are strictly sequential on the device (update i + 1 starts from update i's parameters and rng)."""
+
+    DEPTH = 2
+
+    def __init__(self, learner: Learner, train_state: TrainState, rng: torch.Tensor):
+        self.lrn = learner
+        self.ts = train_state
+        dev = learner.device
+        T, Nl, D, A, P = learner.T, learner.Nl, learner.obs_dim, learner.act_dim, learner.P
+        f32, u8 = torch.float32, torch.uint8
+        self.spec = {"obs": ((T, Nl, D), f32), "action": ((T, Nl, A), f32), "value": ((T, Nl), f32), "reward": ((T, Nl), f32),
+                     "log_prob": ((T, Nl), f32), "done": ((T, Nl), u8), "last_val": ((Nl,), f32)}
+        self.dev_in = [{k: torch.empty(s, dtype=dt, device=dev) for k, (s, dt) in self.spec.items()} for _ in range(self.DEPTH)]
+        self.dev_losses = [torch.empty((learner.E, learner.M, 4), dtype=f32, device=dev) for _ in range(self.DEPTH)]
+        self.host_out = [{"losses": torch.empty((learner.E, learner.M, 4), dtype=f32).pin_memory(),
+                          "params": torch.empty((P,), dtype=f32).pin_memory(),
+                          "rng": torch.empty((2,), dtype=torch.int32).pin_memory()} for _ in range(self.DEPTH)]
+        # the rng key chain lives on the device: ping-pong pair (update i reads slot i % 2, writes slot (i + 1) % 2)
+        self.rng = [rng.reshape(2).view(torch.int32).clone(), torch.empty(2, dtype=torch.int32, device=dev)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ev_copied = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self.ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]       # update + D2H of slot k finished
+        self.ev_free = [None] * self.DEPTH                                    # device inputs of slot k no longer read
+        self.n_submitted = 0
+        self.n_returned = 0
+
+    def h2d_bytes(self) -> int:
+        return sum(int(np.prod(s)) * torch.empty((), dtype=dt).element_size() for s, dt in self.spec.values())
+
+    def d2h_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.host_out[0].values())
+
+    def submit(self, traj: dict) -> None:
+        """``traj``: pinned host tensors obs, action, value, reward, log_prob, done (uint8 / bool), last_val."""
+        if self.n_submitted - self.n_returned >= self.DEPTH:
+            raise RuntimeError("HostPipeline: call result() before submitting a third update")
+        k = self.n_submitted % self.DEPTH
+        dev = self.lrn.device
+        compute = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(self.copy_stream):
+            if self.ev_free[k] is not None:
+                self.copy_stream.wait_event(self.ev_free[k])          # the update that last read this buffer set is finished
+            for name in self.spec:
+                src = traj[name]
+                if name == "done" and src.dtype == torch.bool:
+                    src = src.view(torch.uint8)
+                self.dev_in[k][name].copy_(src, non_blocking=True)
+            self.ev_copied[k].record(self.copy_stream)
+        compute.wait_event(self.ev_copied[k])
+        d = self.dev_in[k]
+        mem = Memory(d["done"], d["action"], d["value"], d["reward"], d["log_prob"], d["obs"])
+        i = self.n_submitted
+        self.lrn.update(self.ts, mem, d["last_val"], self.rng[i % 2], self.dev_losses[k], self.rng[(i + 1) % 2])
+        ev = torch.cuda.Event()
+        ev.record(compute)
+        self.ev_free[k] = ev
+        h = self.host_out[k]
+        h["losses"].copy_(self.dev_losses[k], non_blocking=True)
+        h["params"].copy_(self.ts.params, non_blocking=True)
+        h["rng"].copy_(self.rng[(i + 1) % 2], non_blocking=True)
+        self.ev_done[k].record(compute)
+        self.n_submitted += 1
+
+    def result(self):
+        if self.n_returned >= self.n_submitted:
+            raise RuntimeError("HostPipeline: nothing outstanding")
+        k = self.n_returned % self.DEPTH
+        self.ev_done[k].synchronize()
+        self.n_returned += 1
+        return self.host_out[k]["losses"].numpy(), self.host_out[k]["params"].numpy()

@@ -12,7 +12,10 @@ from oracle import ppo_numpy as P
 from tests.helpers import hyper_to_config
 
 dev = torch.device("cuda:0")
-shape = bench.make_shape(bench.workload(1))
+w_ = bench.workload(1)
+if os.environ.get("TRACE_ENVS"):                      # probe: fewer (tile, net) CTAs in flight (contention for the shared weights?)
+    w_ = dict(w_, num_envs=int(os.environ["TRACE_ENVS"]))
+shape = bench.make_shape(w_)
 hp = bench.make_hyper(shape)
 learner = Learner(hyper_to_config(hp, use_graph=False), bench.OBS_DIM, bench.ACT_DIM, dev)
 params, traj, last_val = bench.synth_shard(shape, 0, 1)

@@ -73,3 +73,47 @@ def test_update_and_policy_step_replay_from_a_callers_capture(fused, cuda_device
         for i, (g, w) in enumerate(zip(got, want)):
             assert torch.equal(g, w), (rep, i)
     lrn.close()
+
+
+def test_host_pipeline_equals_sequential_updates(cuda_device):
+    """HostPipeline (pinned-host trajectories in, params / losses out, two updates in flight) produces exactly what the
+    same updates give when called one after the other on device-resident inputs."""
+    import torch
+
+    from minppo_b200.learner import HostPipeline, Learner
+
+    hp = P.Hyper(num_envs=64, num_steps=32, num_minibatches=4, update_epochs=2, anneal_lr=True)
+    pr = synth.make_problem(hp, 225, 10, seed=6, done_p=0.02)
+    cfg = hyper_to_config(hp)
+    lrn = Learner(cfg, 225, 10, cuda_device)
+    ts, mem, lv, rng = _state(pr, hp, cuda_device)
+    want = []
+    r = rng
+    for _ in range(3):
+        ts, r_out, losses = lrn.update(ts, mem, lv, r)
+        r = r_out.clone()
+        want.append((losses.cpu().numpy().copy(), ts.params.cpu().numpy().copy()))
+    lrn.check()
+    lrn.close()
+
+    lrn = Learner(cfg, 225, 10, cuda_device)
+    ts, mem, lv, rng = _state(pr, hp, cuda_device)
+    host = {"obs": mem.obs, "action": mem.action, "value": mem.value, "reward": mem.reward, "log_prob": mem.log_prob,
+            "done": mem.done.view(torch.uint8), "last_val": lv}
+    host = {k: v.cpu().pin_memory() for k, v in host.items()}
+    pipe = HostPipeline(lrn, ts, rng)
+    got = []
+    for i in range(3):
+        pipe.submit(host)
+        if i >= 1:
+            l, p = pipe.result()
+            got.append((l.copy(), p.copy()))
+    l, p = pipe.result()
+    got.append((l.copy(), p.copy()))
+    lrn.check()
+    for i, ((lw, pw), (lg, pg)) in enumerate(zip(want, got)):
+        assert np.array_equal(lw, lg), i
+        assert np.array_equal(pw, pg), i
+    with pytest.raises(RuntimeError):
+        pipe.result()
+    lrn.close()
