@@ -61,6 +61,8 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    LIB_PATH = os.environ.get("MINPPO_B200_LIB", LIB_PATH)      # development: A/B a differently compiled build
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: the CUDA library is not built. Run `bash minppo_b200/csrc/build.sh` "

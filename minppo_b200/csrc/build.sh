@@ -2,7 +2,7 @@
 # Build libminppo_b200.so for sm_100a (B200). Usage: build.sh [extra nvcc flags]
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../lib"
+OUT="${MINPPO_OUT:-$HERE/../lib}"      # MINPPO_OUT: build a development variant beside the product library
 mkdir -p "$OUT"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function"

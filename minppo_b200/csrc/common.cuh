@@ -77,32 +77,49 @@ MINPPO_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug (missing arrive / wrong tx count) traps with an error after
-// ~2 s instead of hanging the GPU.
+// ~2 s instead of hanging the GPU.  try_wait suspends the warp in hardware for a bounded time per attempt; the clock is
+// only read every 64 attempts, so that a waiting warp costs its scheduler next to nothing (16 worker warps wait most of
+// the time, on the schedulers the working warps issue from).
 MINPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try_wait(bar, parity)) return;
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 
-// Busy-polling wait (mbarrier.test_wait never suspends the thread): for the single MMA-issuing thread, whose
-// wake-up latency after a suspended try_wait showed up as ~2k idle cycles in front of a GEMM.
+// Wait of the single MMA-issuing thread.  MINPPO_MMA_SPIN = 1: busy-polling mbarrier.test_wait (never suspends: round 1
+// measured ~2k idle cycles in front of a GEMM after a suspended try_wait, with the clock read in every iteration) -- but a
+// busy loop takes issue slots from the four epilogue warps that share its scheduler; 0 (default): the suspending try_wait
+// loop above.  Measured in round 2 (same box, configs[1]): 5.880 ms (spin) vs 5.830 ms (suspend) per update.
+#ifndef MINPPO_MMA_SPIN
+#define MINPPO_MMA_SPIN 0
+#endif
 MINPPO_DEVINL void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+#if MINPPO_MMA_SPIN
   const uint32_t addr = smem_u32(bar);
   const long long t0 = clock64();
   for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred P;\n\t"
+          "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, P;\n\t}\n"
+          : "=r"(ok)
+          : "r"(addr), "r"(parity)
+          : "memory");
+      if (ok) return;
+    }
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+#else
+  mbar_wait(bar, parity);
+#endif
 }
 
 // generic-proxy writes (st.shared / cp.async) -> visible to the async proxy (UMMA / TMA)
