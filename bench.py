@@ -631,14 +631,16 @@ def run_ours(args):
         for _ in range(3):
             calculate_gae(gm, lv_, hp.gamma, hp.gae_lambda)
         torch.cuda.synchronize(dev)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        g0.record()
-        for _ in range(reps):
-            calculate_gae(gm, lv_, hp.gamma, hp.gae_lambda)       # 2.3 GB per call >> 126 MB L2
-        g1.record()
-        torch.cuda.synchronize(dev)
-        gms = g0.elapsed_time(g1) / reps
+        reps, batches = 10, []
+        for _ in range(3):                                       # median of three batches of 10 calls
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(reps):
+                calculate_gae(gm, lv_, hp.gamma, hp.gae_lambda)   # 2.3 GB per call >> 126 MB L2
+            g1.record()
+            torch.cuda.synchronize(dev)
+            batches.append(g0.elapsed_time(g1) / reps)
+        gms = float(np.median(batches))
         gbytes = Tg * Ng * 17 + 4 * Ng
         # the launch plan of gae.cu (gae_plan): VEC = 4 when N % 4 == 0; one pass over T (gae_single_kernel<4, UNROLL>, UNROLL = 8
         # below 1024 float4 columns per SM, else 4) unless fewer than 384 columns per SM force the T-chunked kernel
