@@ -277,30 +277,6 @@ MINPPO_DEVINL float exp_tanh(float x) {
   return fmaf(-2.f, r, 1.f);
 }
 
-// packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 -- two IEEE-rounded fp32 operations per issue slot; the epilogues are
-// instruction-issue bound).  Each lane rounds exactly like the scalar instruction.
-MINPPO_DEVINL uint64_t f2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-MINPPO_DEVINL void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-MINPPO_DEVINL uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-MINPPO_DEVINL uint64_t fmul2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-MINPPO_DEVINL uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
 MINPPO_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

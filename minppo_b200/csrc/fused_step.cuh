@@ -177,9 +177,9 @@ __device__ __noinline__ void epilogue_act_t(uint32_t tmem_acc, uint32_t dst_base
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int e = 8 * j + 2 * t;
-        float z0, z1;
-        f2_unpack(fadd2(f2_pack(v[e], v[e + 1]), f2_pack(bj[2 * t], bj[2 * t + 1])), z0, z1);      // one FADD2 per column pair
-        w[t] = pack_bf16x2(act_apply<ACT>(z0), act_apply<ACT>(z1));
+        const float x0 = act_apply<ACT>(v[e] + bj[2 * t]);
+        const float x1 = act_apply<ACT>(v[e + 1] + bj[2 * t + 1]);
+        w[t] = pack_bf16x2(x0, x1);
       }
       sts128(dst_base + sw_off(row, c0 + 8 * j), make_uint4(w[0], w[1], w[2], w[3]));
     }
@@ -213,16 +213,7 @@ __device__ __noinline__ void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base,
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int e = 8 * j + 2 * t;
-        float d0, d1;
-        if (ACT == ACT_RELU) {
-          d0 = act_deriv_t<ACT>(bf16_lo(hw[t])); d1 = act_deriv_t<ACT>(bf16_hi(hw[t]));
-        } else {                                                       // 1 - h^2 as one FFMA2 per column pair
-          const uint64_t h2 = f2_pack(bf16_lo(hw[t]), bf16_hi(hw[t]));
-          f2_unpack(ffma2(h2 ^ 0x8000000080000000ULL, h2, f2_pack(1.f, 1.f)), d0, d1);
-        }
-        float z0, z1;
-        f2_unpack(fmul2(f2_pack(v[e], v[e + 1]), f2_pack(d0, d1)), z0, z1);
-        w[t] = pack_bf16x2(z0, z1);
+        w[t] = pack_bf16x2(v[e] * act_deriv_t<ACT>(bf16_lo(hw[t])), v[e + 1] * act_deriv_t<ACT>(bf16_hi(hw[t])));
       }
       sts128(dst_base + sw_off(row, c0 + 8 * j), make_uint4(w[0], w[1], w[2], w[3]));
     }
