@@ -72,6 +72,28 @@ MINPPO_DEVINL unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// four consecutive fp32 of an arena (L2-coherent: ld.cg / plain st), by the widest access the address allows
+MINPPO_DEVINL void ld_unit(const float* p, float (&v)[4]) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  if ((a & 15u) == 0) { const float4 q = __ldcg(reinterpret_cast<const float4*>(p)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+  else if ((a & 7u) == 0) {
+    const float2 q0 = __ldcg(reinterpret_cast<const float2*>(p)), q1 = __ldcg(reinterpret_cast<const float2*>(p) + 1);
+    v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = __ldcg(p + e);
+  }
+}
+MINPPO_DEVINL void st_unit(float* p, const float (&v)[4]) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  if ((a & 15u) == 0) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else if ((a & 7u) == 0) { reinterpret_cast<float2*>(p)[0] = make_float2(v[0], v[1]); reinterpret_cast<float2*>(p)[1] = make_float2(v[2], v[3]); }
+  else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) p[e] = v[e];
+  }
+}
+
 struct alignas(64) DwOptParams {
   GemmParams gemm;               // the per-step row list / valid-row count of the groups come from the arrays below
   OptArgs opt;                   // losses_out / gnorm_out: bases of the per-step arrays (losses_stride floats apart / 1 apart)
@@ -227,12 +249,12 @@ MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw,
         const OptLeaf& L = T.leaf[l];
         ul[u] = l; ui[u] = L.offset + 4 * x;
         if (a.do_apply) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { pv[u][e] = __ldcg(a.params + ui[u] + e); mv[u][e] = __ldcg(a.mu + ui[u] + e); nv[u][e] = __ldcg(a.nu + ui[u] + e); }
+          // the arena offset of a leaf is only 4-byte aligned in general (act_dim is arbitrary): widest aligned access
+          ld_unit(a.params + ui[u], pv[u]); ld_unit(a.mu + ui[u], mv[u]); ld_unit(a.nu + ui[u], nv[u]);
         }
         g4[u] = sum_partials16_v4(L.grad_src + L.src_offset + 4 * x, L.nparts, L.part_stride);
         if (!px_on) {
-          if (!a.do_apply || a.keep_gflat) { float* dst = a.gflat + ui[u]; dst[0] = g4[u].x; dst[1] = g4[u].y; dst[2] = g4[u].z; dst[3] = g4[u].w; }
+          if (!a.do_apply || a.keep_gflat) { const float gq[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w}; st_unit(a.gflat + ui[u], gq); }
           ss = fmaf(g4[u].x, g4[u].x, ss); ss = fmaf(g4[u].y, g4[u].y, ss); ss = fmaf(g4[u].z, g4[u].z, ss); ss = fmaf(g4[u].w, g4[u].w, ss);
         }
       }
@@ -362,7 +384,7 @@ MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw,
         g4[u] = v;
         st_sys_v4(src, sent4);
       }
-      if (a.keep_gflat) { float* dst = a.gflat + ui[u]; dst[0] = g4[u].x; dst[1] = g4[u].y; dst[2] = g4[u].z; dst[3] = g4[u].w; }
+      if (a.keep_gflat) { const float gq[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w}; st_unit(a.gflat + ui[u], gq); }
       ss = fmaf(g4[u].x, g4[u].x, ss); ss = fmaf(g4[u].y, g4[u].y, ss); ss = fmaf(g4[u].z, g4[u].z, ss); ss = fmaf(g4[u].w, g4[u].w, ss);
     }
     if (eidx >= 0) {
@@ -437,12 +459,8 @@ MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw,
       const OptLeaf& L = T.leaf[ul[u]];
       const float gv[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        adam_element(a, sc, gv[e], pv[u][e], mv[u][e], nv[u][e]);
-        a.params[ui[u] + e] = pv[u][e];
-        a.mu[ui[u] + e] = mv[u][e];
-        a.nu[ui[u] + e] = nv[u][e];
-      }
+      for (int e = 0; e < 4; ++e) adam_element(a, sc, gv[e], pv[u][e], mv[u][e], nv[u][e]);
+      st_unit(a.params + ui[u], pv[u]); st_unit(a.mu + ui[u], mv[u]); st_unit(a.nu + ui[u], nv[u]);
       if (L.img_n)             // 4 consecutive bf16 of the kernel image (unit index is a multiple of 4: 8-byte aligned)
         *reinterpret_cast<uint2*>(L.img_n + (ui[u] - L.offset)) = make_uint2(pack_bf16x2(pv[u][0], pv[u][1]), pack_bf16x2(pv[u][2], pv[u][3]));
     }
