@@ -550,6 +550,8 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
       hb[3 * AP] = logdet;
     }
     if (wt >= 256) sts128(ONES + (wt - 256) * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));   // bf16 1.0
+    // g^T starts as zeros: the loss below writes only the aout real columns (hi and lo rows), the padding rows stay 0
+    for (int i = wt; i < (2 * PG) >> 4; i += FS_WORKERS) sts128(GT + i * 16, make_uint4(0u, 0u, 0u, 0u));
     if (wt == 0) FS_STAMP(30);
     cp_async_wait<0>();
     fence_proxy_async_smem();                                    // W2T / ones -> async proxy (UMMA)
@@ -687,7 +689,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float gj = net == 0 ? g_logp * (zz[j] * hb[2 * AP + j]) : (j == 0 ? g0 : 0.f);
-          put_g(j, gj);
+          if (j < aout) put_g(j, gj);
           v[j] = (net == 0 && j < aout) ? g_logp * (zz[j] * zz[j] - 1.f) : 0.f;
           v[16 + j] = gj;
         }
@@ -700,7 +702,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float gj = net == 0 ? g_logp * (zz[j] * hb[2 * AP + j]) : (j == 0 ? g0 : 0.f);
-          put_g(j, gj);
+          if (j < aout) put_g(j, gj);
           v[j] = gj;
         }
         rw[32 + lane] = warp_colsum32(v);
