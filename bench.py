@@ -686,6 +686,33 @@ def run_ours(args):
             p1.record()
             torch.cuda.synchronize(dev)
             pol["graph_replay_us_per_env_step"] = p0.elapsed_time(p1) / 200 * 1e3
+            # T = 32 consecutive policy steps (rng chained through two ping-pong keys) captured as ONE graph: what the
+            # network evaluation of a captured rollout costs per env step once the per-launch host cost is amortised
+            Tr = 32
+            keys = [rng.clone(), torch.empty_like(rng)]
+            pact = torch.empty((hp.num_envs // world, D_ACT), dtype=torch.float32, device=dev)
+            plp = torch.empty((hp.num_envs // world,), dtype=torch.float32, device=dev)
+            pval = torch.empty_like(plp)
+            rg = torch.cuda.CUDAGraph()
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(rg, stream=side):
+                    for t_ in range(Tr):
+                        _lib.check(learner.lib.minppo_policy_step(
+                            learner._h, ts.params.data_ptr(), pobs.data_ptr(), keys[t_ % 2].data_ptr(), keys[(t_ + 1) % 2].data_ptr(),
+                            pact.data_ptr(), plp.data_ptr(), pval.data_ptr(), None, _lib.POLICY_WEIGHTS_CURRENT,
+                            torch.cuda.current_stream(dev).cuda_stream))
+            torch.cuda.current_stream(dev).wait_stream(side)
+            for _ in range(3):
+                rg.replay()
+            torch.cuda.synchronize(dev)
+            p0.record()
+            for _ in range(20):
+                rg.replay()
+            p1.record()
+            torch.cuda.synchronize(dev)
+            pol["rollout_graph_us_per_env_step"] = p0.elapsed_time(p1) / (20 * Tr) * 1e3
+            pol["rollout_graph_steps"] = Tr
         except Exception as e:  # a measurement extra must never lose the bench line
             pol = {"error": str(e)[:200]}
 

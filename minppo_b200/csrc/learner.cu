@@ -182,7 +182,7 @@ static int validate_config(const minppo_config& c) {
   }
   if (c.act_dim > 32) { set_error("act_dim=%d unsupported (<= 32)", c.act_dim); return MINPPO_ERR_UNSUPPORTED; }
   if (2 * (c.num_layers + 1) * 2 + 1 > OPT_TAB_LEAVES) { set_error("too many layers"); return MINPPO_ERR_UNSUPPORTED; }
-  if (2 * c.num_layers > GEMM_MAX_GROUPS) { set_error("num_layers=%d unsupported (<= %d)", c.num_layers, GEMM_MAX_GROUPS / 2); return MINPPO_ERR_UNSUPPORTED; }
+  if (2 * c.num_layers > 6) { set_error("num_layers=%d unsupported (<= 3)", c.num_layers); return MINPPO_ERR_UNSUPPORTED; }
   const long long B = static_cast<long long>(c.num_envs) * c.num_steps;
   const long long mb = B / c.num_minibatches;
   if (mb * c.num_minibatches != B) {
@@ -241,6 +241,8 @@ struct minppo_ctx {
   int T, N, Nl, n0, M, E, L, H, D, Dp, A;
   long long B, Bl, P;
   int mb, cap, M_pad, m_tiles, tiles64, S;
+  int dw_nsplit;              // dW GEMM groups per (net, layer): 1 (128 x H tiles) or 2 (N halves: 128 x H/2 tiles, half the
+                              // split-K factor -- half the partial bytes stored and re-read per step; needs H % 128 == 0)
   int maxu;                   // dwopt fast path: 4-element units of the hidden kernels per thread (1, 2 or 4)
   bool fused;                 // fused step kernel (L == 2; any obs_dim, act_dim <= 32, hidden_size <= 256)
   int head_parts;             // head partials per minibatch: m_tiles (fused) or tiles64
@@ -490,6 +492,7 @@ static int fill_dwopt_params(minppo_ctx* c, const UpdatePtrs& u, DwOptParams* dp
   for (int net = 0; net < 2; ++net) {
     NetBufs& nb = c->net[net];
     for (int l = 0; l < L; ++l) {
+      for (int nh = 0; nh < c->dw_nsplit; ++nh) {
       GemmGroup& g = p.g[ng++];
       g.cta_begin = cta;
       const int in_l = l == 0 ? c->D : H;
@@ -502,8 +505,10 @@ static int fill_dwopt_params(minppo_ctx* c, const UpdatePtrs& u, DwOptParams* dp
       g.k_count = nullptr;                                    // per step (counts[] below)
       g.tmC = nb.m_dw[l];
       g.colsum_out = c->fused ? nullptr : nb.dbias[l];      // fused path: the bias gradients come from the fused step kernel
-      g.N = H; g.m_tiles = (in_pad + 127) / 128; g.splits = c->S; g.m_store = in_l;
+      g.N = H / c->dw_nsplit; g.n_off = nh * g.N;
+      g.m_tiles = (in_pad + 127) / 128; g.splits = c->S; g.m_store = in_l;
       cta += g.m_tiles * g.splits;
+      }
     }
   }
   p.ngroups = ng;
@@ -913,8 +918,11 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   c->maxu = c->P <= dwopt_fast_capacity(c->sm_count, 1) ? 1 : (c->P <= dwopt_fast_capacity(c->sm_count, 2) ? 2 : 4);
   // split-K of the dW GEMMs: fill the SMs once
   {
+    // N-halved dW tiles (fused path, H a multiple of 128): half the split-K factor for the same number of GEMM CTAs
+    c->dw_nsplit = (c->fused && c->H % 128 == 0 && 2 * 2 * c->L <= GEMM_MAX_GROUPS &&
+                    !(getenv("MINPPO_DW_NSPLIT") && atoi(getenv("MINPPO_DW_NSPLIT")) == 1)) ? 2 : 1;
     int per_split = 0;
-    for (int l = 0; l < c->L; ++l) per_split += 2 * (((l == 0 ? c->Dp : c->H) + 127) / 128);
+    for (int l = 0; l < c->L; ++l) per_split += 2 * c->dw_nsplit * (((l == 0 ? c->Dp : c->H) + 127) / 128);
     int S = cfg->dw_splits > 0 ? cfg->dw_splits : (c->sm_count / (per_split > 0 ? per_split : 1));
     if (getenv("MINPPO_DW_SPLITS")) S = atoi(getenv("MINPPO_DW_SPLITS"));           // development probe
     // k-blocks (64 minibatch rows each) the splits share.  Padded row lists (env-sharded ranks): size the split for the
@@ -932,6 +940,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     if (S < 1) S = 1;
     // no empty splits: ceil(kb_total / S) * (S - 1) < kb_total
     while (S > 1 && ((kb_total + S - 1) / S) * (S - 1) >= kb_total) --S;
+    if (S > 1 && kb_total % S != 0 && kb_total % (S - 1) == 0) --S;     // equal splits (and a few more spare CTAs) over one ragged split
     c->S = S;
   }
   c->opt_blocks = c->sm_count;

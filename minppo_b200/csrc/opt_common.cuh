@@ -160,8 +160,16 @@ MINPPO_DEVINL float4 sum_partials16_v4(const float* __restrict__ src, int nparts
     for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
   }
 #pragma unroll 1
+  for (; p + 4 <= nparts; p += 4) {                      // remainders in batches of 4 loads in flight (same summation order)
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld_partial_v4(src + static_cast<size_t>(p + u) * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+  }
+#pragma unroll 1
   for (; p < nparts; ++p) {
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(p) * stride));
+    const float4 v = ld_partial_v4(src + static_cast<size_t>(p) * stride);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   return acc;

@@ -31,7 +31,7 @@ constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_EPI_THREADS = 128;
 constexpr int GEMM_ONES_BYTES = 16384;                   // all-ones bf16 [128][64] tile: A operand of the bias-gradient MMAs
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_ONES_BYTES + 1024 /*align*/ + 4 * GEMM_MAXN * 4 /*colsum*/ + 256;
-constexpr int GEMM_MAX_GROUPS = 6;
+constexpr int GEMM_MAX_GROUPS = 8;
 
 enum : int { A_TMA_K = 0, A_GATHER_K = 1, A_TMA_MN = 2, A_GATHER_MN = 3 };
 enum : int { B_TMA_K = 0, B_TMA_MN = 2 };
@@ -59,6 +59,7 @@ struct alignas(64) GemmGroup {
   int splits;                      // split-K factor (EPI_PARTIAL)
   int kb_total;                    // number of 64-wide k-blocks over the whole K
   int m_store;                     // EPI_PARTIAL: rows m < m_store are stored
+  int n_off;                       // B_TMA_MN / EPI_PARTIAL: first column of this group's N range inside B and C (N-split groups)
   const int32_t* k_count;          // optional: number of valid K rows (device side); k-blocks beyond it are skipped
 };
 
@@ -215,7 +216,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
           tma_load_2d(sb, &G.tmB, &full_bar[s], kb * GEMM_BK, 0);                          // box {64 k, N}
         } else {
           for (int c = 0; c < N / 64; ++c)
-            tma_load_2d(sb + c * 8192, &G.tmB, &full_bar[s], c * 64, kb * GEMM_BK);        // box {64 n, 64 k}
+            tma_load_2d(sb + c * 8192, &G.tmB, &full_bar[s], G.n_off + c * 64, kb * GEMM_BK);   // box {64 n, 64 k}
         }
       }
     }
@@ -257,7 +258,7 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
         for (int c = 0; c < N / 32; ++c) {
           mbar_wait(&chunk_bar[c], 0);
           if (c == 0) GEMM_STAMP(11);          // first chunk staged
-          tma_store_3d(base + c * 16384, &G.tmC, c * 32, m_tile * GEMM_BM, split);
+          tma_store_3d(base + c * 16384, &G.tmC, G.n_off + c * 32, m_tile * GEMM_BM, split);
         }
         tma_store_commit();
         tma_store_wait_all0();
