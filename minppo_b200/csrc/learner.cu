@@ -906,6 +906,11 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     if (cap > c->Bl) cap = c->Bl;
     c->cap = static_cast<int>(cap);
   }
+  if (getenv("MINPPO_FORCE_CAP") && atoi(getenv("MINPPO_FORCE_CAP")) > 0) {
+    // test hook (tests/test_gpu_update.py): an undersized row list, to exercise the overflow path on one GPU
+    c->padded = true;
+    c->cap = atoi(getenv("MINPPO_FORCE_CAP"));
+  }
   c->M_pad = (c->cap + 127) / 128 * 128;
   c->cap = c->M_pad;                                  // row lists are padded to whole GEMM tiles
   c->m_tiles = c->M_pad / 128;
@@ -919,11 +924,16 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   // split-K of the dW GEMMs: fill the SMs once
   {
     // N-halved dW tiles (fused path, H a multiple of 128): half the split-K factor for the same number of GEMM CTAs
-    c->dw_nsplit = (c->fused && c->H % 128 == 0 && 2 * 2 * c->L <= GEMM_MAX_GROUPS &&
+    // (only with TMA-fed A operands, i.e. Dp <= 256: the first-layer groups of wider observations gather their rows by index,
+    //  and two N halves would gather every row twice -- measured at D = 415: 10.5 ms halved vs 9.1 ms whole)
+    c->dw_nsplit = (c->fused && c->store_x && c->H % 128 == 0 && 2 * 2 * c->L <= GEMM_MAX_GROUPS &&
                     !(getenv("MINPPO_DW_NSPLIT") && atoi(getenv("MINPPO_DW_NSPLIT")) == 1)) ? 2 : 1;
     int per_split = 0;
     for (int l = 0; l < c->L; ++l) per_split += 2 * c->dw_nsplit * (((l == 0 ? c->Dp : c->H) + 127) / 128);
-    int S = cfg->dw_splits > 0 ? cfg->dw_splits : (c->sm_count / (per_split > 0 ? per_split : 1));
+    // leave ~16 of the one-CTA-per-SM grid as spare CTAs: they sum the per-tile partials of the small leaves while the GEMM
+    // runs (D = 415 / A = 20 with 4 spare CTAs: 6,441 elements x 64 partials on 2,048 threads outlasted the GEMM itself)
+    const int gemm_budget = c->sm_count > 48 ? c->sm_count - 16 : c->sm_count;
+    int S = cfg->dw_splits > 0 ? cfg->dw_splits : (gemm_budget / (per_split > 0 ? per_split : 1));
     if (getenv("MINPPO_DW_SPLITS")) S = atoi(getenv("MINPPO_DW_SPLITS"));           // development probe
     // k-blocks (64 minibatch rows each) the splits share.  Padded row lists (env-sharded ranks): size the split for the
     // rows a minibatch is EXPECTED to have on this rank (mean + 3 sigma of the hypergeometric count), not for the

@@ -352,3 +352,34 @@ def test_update_rejects_bad_arguments(cuda_device):
     with pytest.raises(ValueError, match="obs"):
         lrn.update(ts, bad, z(16), torch.zeros(2, dtype=torch.int32, device=cuda_device))
     lrn.close()
+
+
+def test_row_list_overflow_raises_the_device_flag_and_poisons_the_losses(cuda_device, monkeypatch):
+    """Env-sharded ranks size their per-minibatch row lists for 1.5 x the mean + 256 rows.  A list that does not fit must
+    not bias the gradient silently: compact_rows raises the device-side error flag, every reported loss of that update
+    becomes NaN (visible without a host round trip), and Learner.check() names the cause.  MINPPO_FORCE_CAP undersizes the
+    list on one GPU."""
+    import torch
+
+    from minppo_b200 import _lib
+    from minppo_b200.learner import Learner, Memory, TrainState
+    from tests.helpers import hyper_to_config
+
+    monkeypatch.setenv("MINPPO_FORCE_CAP", "256")                # minibatches have 512 rows
+    hp = P.Hyper(**CASES["medium"]["hp"])
+    pr = synth.make_problem(hp, 225, 10, seed=3)
+    lrn = Learner(hyper_to_config(hp), 225, 10, cuda_device)
+    monkeypatch.delenv("MINPPO_FORCE_CAP")
+    t = lambda x: torch.as_tensor(np.ascontiguousarray(x)).to(cuda_device)
+    tr = pr["traj"]
+    mem = Memory(done=t(tr["done"]), action=t(tr["action"]), value=t(tr["value"]), reward=t(tr["reward"]),
+                 log_prob=t(tr["log_prob"]), obs=t(tr["obs"]))
+    ts = TrainState.create(P.flatten_params(pr["params"], hp.num_layers), cuda_device)
+    rng = torch.as_tensor(pr["rng"].view(np.int32)).to(cuda_device)
+    ts, _, losses = lrn.update(ts, mem, t(pr["last_val"]), rng)
+    torch.cuda.synchronize(cuda_device)
+    assert torch.isnan(losses).all()
+    with pytest.raises(_lib.MinppoError) as e:
+        lrn.check()
+    assert e.value.code in (_lib.ERR_WORKSPACE,)
+    lrn.close()
