@@ -101,7 +101,7 @@ struct alignas(64) FusedParams {
   float* part;                   // per-tile partials [m_tiles][part_stride]
   int part_stride, po_logstd;
   int H, A, Dp, m_tiles, cap;
-  int store_x;                   // 1: Dp <= 256, the X tile is stored for the dW GEMM (else that GEMM gathers by index itself)
+  int store_x;                   // 1: the critic CTAs store the gathered X tile for the dW GEMM (0: that GEMM gathers by index itself)
   int step;                      // minibatch step e * M + k of this launch (fused_step_kernel; the persistent kernel loops)
   float inv_mb, clip_eps, vf_coef;
   long long* trace;              // debug: [ctas][32] clock64 stamps (null = off)
@@ -255,6 +255,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
   uint64_t* h1r = bars + 41;            // [4] H1 columns [64 b, 64 b + 64) in R0 (k-block b of the L2 GEMM)
   uint64_t* dz2r = bars + 45;           // [4] dZ2 columns [64 b, 64 b + 64) in R1 (k-block b of the dH1 GEMM)
   uint64_t* dz1r = bars + 49;           // [4] dZ1 columns [64 b, 64 b + 64) in R1
+  uint64_t* x_stored = bars + 53;       // [4] the TMA store of the X k-block in slot s (for the dW GEMM) has read the slot
   const int32_t* rowidx_s = p.rowidx + static_cast<size_t>(step) * p.cap;     // this step's row list
   const int32_t* count_s = p.count + step;
 
@@ -288,7 +289,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     FS_STAMP(16);
     for (int s = 0; s < 8; ++s) { mbar_init(&l1_full[s], 1); mbar_init(&l1_empty[s], 1); }
     for (int s = 0; s < 4; ++s) {
-      mbar_init(&x_full[s], FS_NWW); mbar_init(&x_empty[s], 1);
+      mbar_init(&x_full[s], FS_NWW); mbar_init(&x_empty[s], 1); mbar_init(&x_stored[s], 1);
       mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
       mbar_init(&h1r[s], FS_NWW); mbar_init(&dz2r[s], FS_NWW); mbar_init(&dz1r[s], FS_NWW);
     }
@@ -523,6 +524,10 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     cp_async_commit();
     // the L1 GEMM needs only the gathered rows: publish them block by block, before the staging of the small operands;
     // for Dp > 256 the slots are refilled as the MMAs release them
+    // The critic CTA (relu epilogues: the shorter chain) also TMA-stores every X k-block for the first-layer dW GEMM, straight
+    // from its slot as soon as the block is complete; a slot is refilled only after that store has read it (x_stored).
+    const bool x_store_cta = p.store_x && net == 1;
+    const bool x_store = x_store_cta && wt == 0;
     {
       int issued = nb0 + 1;                                      // cp.async groups committed so far (X blocks, then W2T)
       for (int kb = 0; kb < nk0; ++kb) {
@@ -531,9 +536,19 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&x_full[kb & 3]);
+        if (x_store) {
+          mbar_wait(&x_full[kb & 3], (kb >> 2) & 1);             // all 16 warps' parts of the block are in the slot
+          tma_store_2d(R1 + (kb & 3) * 16384, &p.tm_xg, kb * 64, tile * 128);
+          tma_store_commit();
+        }
         // refill the slot of block kb - 1 (one block behind, so that publishing block kb never waits for an MMA)
         if (kb >= 1 && kb - 1 + FS_XSLOTS < nk0) {
+          if (x_store) {                                         // the store of block kb - 1 (all but the newest group) has read its slot
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            mbar_arrive(&x_stored[(kb - 1) & 3]);
+          }
           mbar_wait(&x_empty[(kb - 1) & 3], ((kb - 1) >> 2) & 1);
+          if (x_store_cta) mbar_wait(&x_stored[(kb - 1) & 3], ((kb - 1) >> 2) & 1);
           gather_block(kb - 1 + FS_XSLOTS);
           ++issued;
         }
@@ -557,11 +572,6 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     fence_proxy_async_smem();                                    // W2T / ones -> async proxy (UMMA)
     worker_bar();                                                // biases / hb / W2T visible to all workers; X complete
     if (wt == 0) FS_STAMP(1);
-    const bool x_store = p.store_x && net == 1 && wt == 0;       // the critic CTA (relu epilogues: the shorter chain) stores X
-    if (x_store) {
-      for (int kb = 0; kb < nk0; ++kb) tma_store_2d(R1 + kb * 16384, &p.tm_xg, kb * 64, tile * 128);
-      tma_store_commit();
-    }
     // ---- epilogue 1: H1 = act(acc0 + b0) -> R0, then TMA store to HBM ------------------------------
     mbar_wait(accf0, 0);
     tc_fence_after();

@@ -274,7 +274,7 @@ struct minppo_ctx {
   int head_stride, po_w3a, po_b3a, po_w3c, po_b3c, po_logstd, po_bh_a, po_bh_c, po_loss;
   int po_db[2][2];            // fused path: [net][layer] hidden-bias gradient partials (column sums of dZ), H floats each
   int ap;                     // padded head width of the fused step kernel: 16 (A <= 16) or 32
-  bool store_x;               // fused path, Dp <= 256: the fused kernel stores the gathered X tile for the first-layer dW GEMM
+  bool store_x;               // fused path: the fused kernel stores the gathered X tile for the first-layer dW GEMM
   int opt_blocks;
   // graph cache
   cudaStream_t cap_stream;
@@ -917,15 +917,14 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   c->tiles64 = c->M_pad / 64;
   c->fused = !cfg->disable_fused && c->L == 2;
   c->ap = c->A <= 16 ? 16 : 32;
-  c->store_x = c->fused && c->Dp <= 256;
+  c->store_x = c->fused;        // the fused kernel's critic CTAs store the gathered X tile (any Dp: block by block from the slots)
   c->head_parts = c->fused ? c->m_tiles : c->tiles64;
   c->P = build_layout(*cfg, &c->leaves);
   c->maxu = c->P <= dwopt_fast_capacity(c->sm_count, 1) ? 1 : (c->P <= dwopt_fast_capacity(c->sm_count, 2) ? 2 : 4);
   // split-K of the dW GEMMs: fill the SMs once
   {
     // N-halved dW tiles (fused path, H a multiple of 128): half the split-K factor for the same number of GEMM CTAs
-    // (only with TMA-fed A operands, i.e. Dp <= 256: the first-layer groups of wider observations gather their rows by index,
-    //  and two N halves would gather every row twice -- measured at D = 415: 10.5 ms halved vs 9.1 ms whole)
+    // (only with TMA-fed A operands: groups that gather their rows by index would gather every row twice)
     c->dw_nsplit = (c->fused && c->store_x && c->H % 128 == 0 && 2 * 2 * c->L <= GEMM_MAX_GROUPS &&
                     !(getenv("MINPPO_DW_NSPLIT") && atoi(getenv("MINPPO_DW_NSPLIT")) == 1)) ? 2 : 1;
     int per_split = 0;
@@ -950,7 +949,6 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
     if (S < 1) S = 1;
     // no empty splits: ceil(kb_total / S) * (S - 1) < kb_total
     while (S > 1 && ((kb_total + S - 1) / S) * (S - 1) >= kb_total) --S;
-    if (S > 1 && kb_total % S != 0 && kb_total % (S - 1) == 0) --S;     // equal splits (and a few more spare CTAs) over one ragged split
     c->S = S;
   }
   c->opt_blocks = c->sm_count;
