@@ -135,8 +135,11 @@ int minppo_ctx_set_peers(minppo_ctx* ctx, const void* handles_host /* [world_siz
  * done u8 [T, Nl], last_val f32 [Nl]  -- Nl = N / world_size, this rank's env shard.
  * key_in u32[2] -> key_out u32[2] (RunnerState.rng, train.py:280).
  * losses_out: f32 [E, M, 4] = (total, value_loss, actor_loss, entropy) per minibatch, may be NULL.
- * use_graph != 0: the step sequence is captured once into a CUDA graph per pointer set and
- * replayed; use_graph == 0: kernels are enqueued directly (also valid inside a caller's capture). */
+ * use_graph != 0: the step sequence is captured once into a CUDA graph per POINTER SET and replayed (the 4 most recently
+ * used pointer sets are kept: present the same buffers every call -- ping-pong pairs are fine -- or every call re-captures);
+ * use_graph == 0: kernels are enqueued directly (also valid inside a caller's capture: tests/test_gpu_capture.py).
+ * A device-side failure of the update (a row list that overflowed its capacity on an env-sharded rank, a grid-barrier or
+ * peer-exchange timeout) turns every value written to losses_out by the remaining steps into NaN; minppo_ctx_check names it. */
 int minppo_update(minppo_ctx* ctx, float* params, float* mu, float* nu, int32_t* count, const float* obs,
                   const float* action, const float* value, const float* reward, const float* log_prob,
                   const uint8_t* done, const float* last_val, const uint32_t* key_in, uint32_t* key_out,
@@ -155,7 +158,8 @@ int minppo_update(minppo_ctx* ctx, float* params, float* mu, float* nu, int32_t*
  * The normal draw is the GLOBAL jax.random.normal(action_rng, (N, A)): an env-sharded rank produces its rows of it.
  * flags: MINPPO_POLICY_WEIGHTS_CURRENT = the context's weight images already match `params` (true right after
  * minppo_update or a previous policy step with the same, unmodified arena) -> skips the image refresh launch.
- * Enqueues on `stream`, never synchronises; valid inside a caller's graph capture. */
+ * Enqueues on `stream`, never synchronises; valid inside a caller's graph capture.  Two-hidden-layer nets: ONE launch
+ * (observation conversion, both hidden layers, heads, sampler: policy_fused.cuh) after the optional image refresh. */
 #define MINPPO_POLICY_WEIGHTS_CURRENT 1
 int minppo_policy_step(minppo_ctx* ctx, const float* params, const float* obs, const uint32_t* key_in,
                        uint32_t* key_out, float* action, float* log_prob, float* value, float* mean,
