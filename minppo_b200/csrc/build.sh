@@ -6,9 +6,12 @@ OUT="${MINPPO_OUT:-$HERE/../lib}"      # MINPPO_OUT: build a development variant
 mkdir -p "$OUT"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function"
+pids=()
 for f in gae prng_sort minibatch head_loss policy adam learner; do
+  rm -f "$OUT/$f.o"                      # a failed compile must not link a stale object
   $NVCC $FLAGS "$@" -c "$HERE/$f.cu" -o "$OUT/$f.o" &
+  pids+=($!)
 done
-wait
+for pid in "${pids[@]}"; do wait "$pid"; done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libminppo_b200.so" "$OUT"/{gae,prng_sort,minibatch,head_loss,policy,adam,learner}.o -lcudart -ldl
 echo "built $OUT/libminppo_b200.so"

@@ -65,14 +65,19 @@ MINPPO_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
+// suspend-time hint of mbarrier.try_wait (ns): without it the attempt may return after an implementation-defined, short time and
+// the waiting warp re-issues it in a loop on the scheduler it shares with working warps
+#ifndef MINPPO_TRY_WAIT_HINT_NS
+#define MINPPO_TRY_WAIT_HINT_NS 1000000u
+#endif
 MINPPO_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(MINPPO_TRY_WAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
@@ -80,13 +85,21 @@ MINPPO_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // ~2 s instead of hanging the GPU.  try_wait suspends the warp in hardware for a bounded time per attempt; the clock is
 // only read every 64 attempts, so that a waiting warp costs its scheduler next to nothing (16 worker warps wait most of
 // the time, on the schedulers the working warps issue from).
+#ifndef MINPPO_WAIT_SLEEP_NS
+#define MINPPO_WAIT_SLEEP_NS 0
+#endif
+template <bool POLITE = true>
 MINPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   for (;;) {
 #pragma unroll 1
-    for (int i = 0; i < 64; ++i)
+    for (int i = 0; i < 64; ++i) {
       if (mbar_try_wait(bar, parity)) return;
+#if MINPPO_WAIT_SLEEP_NS
+      if (POLITE) asm volatile("nanosleep.u32 %0;" ::"r"(static_cast<uint32_t>(MINPPO_WAIT_SLEEP_NS)));
+#endif
+    }
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
@@ -118,7 +131,7 @@ MINPPO_DEVINL void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 #else
-  mbar_wait(bar, parity);
+  mbar_wait<false>(bar, parity);
 #endif
 }
 

@@ -45,6 +45,9 @@ constexpr int FS_STAGE = 16384;                         // one weight stage: [32
                                                         // or [H/2 n][64 k] (dH1, K-major B)
 constexpr int FS_XSLOTS = 4;                            // X k-block slots in R1 (16 KB each)
 constexpr int FS_MAX_AP = 32;
+constexpr int FS_STORE_THREAD = 480;                    // warp 15 lane 0 issues the H1 / dZ2 / dZ1 TMA stores: the highest-priority worker
+                                                        // warp of a scheduler that hosts neither the TMA nor the MMA warp (a low-priority
+                                                        // warp that starts an epilogue late finishes it last: measured +2k cycles on warp 1)
 
 template <int AP>
 struct FsLayout {
@@ -107,7 +110,14 @@ struct alignas(64) FusedParams {
   long long* trace;              // debug: [ctas][32] clock64 stamps (null = off)
 };
 
-#define FS_STAMP(slot) do { if (p.trace) p.trace[static_cast<size_t>(cta_id) * 32 + (slot)] = clock64(); } while (0)
+#ifdef FS_TRACE_EPI2_ALL
+constexpr int FS_TRACE_SLOTS = 128;                     // debug build: + [64, 128) every worker warp after each chunk of epilogue 2
+#else
+constexpr int FS_TRACE_SLOTS = 64;                      // clock64 stamps per unit: [0, 32) one thread per role, [32, 64) the four
+                                                        // worker warps of lane quadrant 0 around the four big epilogues
+#endif
+#define FS_STAMP(slot) do { if (p.trace) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + (slot)] = clock64(); } while (0)
+#define FS_STAMP_W(slot0) do { if (p.trace && q == 0 && lane == 0) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + (slot0) + sub] = clock64(); } while (0)
 
 MINPPO_DEVINL void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -124,6 +134,37 @@ MINPPO_DEVINL void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// TMEM -> registers: 32 lanes x 4 / 8 consecutive fp32 columns (the loss: a worker warp owns AP / 4 head columns)
+MINPPO_DEVINL void tmem_ld_32xn(uint32_t taddr, float (&v)[4]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+MINPPO_DEVINL void tmem_ld_32xn(uint32_t taddr, float (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+// N x 32 transpose-reduce (N = 8, 16): lane l ends with the sum over the 32 lanes of v[l & (N - 1)]
+template <int N>
+MINPPO_DEVINL float warp_colsum_n(float (&v)[N]) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? v[i + half] : v[i];
+      const float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (int o = N; o < 32; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
 }
 // TMEM -> registers: 32 lanes x 1 column
 MINPPO_DEVINL float tmem_ld_32x1(uint32_t taddr) {
@@ -154,75 +195,117 @@ MINPPO_DEVINL float act_deriv_t(float h) { return ACT == ACT_RELU ? (h > 0.f ? 1
 MINPPO_DEVINL float dclip_f(float x, float lo, float hi) {
   return (x > lo && x < hi) ? 1.f : ((x == lo || x == hi) ? 0.5f : 0.f);
 }
-// accumulator (16 columns per chunk) -> +bias, activation, bf16 -> swizzled smem tile
-// (not inlined: the epilogues share one copy of the code per activation -- the kernel's straight-line worker path is
-//  larger than the instruction cache otherwise)
+// The four epilogues walk `nchunks` 16-column chunks of an accumulator, chunk i at column col0 + i * cstride, and (bars != null)
+// publish chunk i on bars[i] as soon as it is in shared memory.  The TMEM read of chunk i + 1 is issued before chunk i is
+// processed (one tcgen05.ld outstanding at every tcgen05.wait::ld): with four warps per scheduler the read latency is
+// otherwise exposed in every chunk, and the MUFU time of a tanh chunk (16 x 8 cycles per warp) adds to it instead of hiding it.
+// (Not inlined: the epilogues share one copy of the code per activation -- the kernel's straight-line worker path is larger
+//  than the instruction cache otherwise.)
+MINPPO_DEVINL void chunk_publish(uint64_t* bar) {
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncwarp();
+  if (lane_id() == 0) mbar_arrive(bar);
+}
+// one chunk: +bias, activation, bf16 -> swizzled smem tile
 template <int ACT>
-__device__ __noinline__ void epilogue_act_t(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int row, int q, int col0,
-                                            int ncols) {
-  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-  for (int c0 = col0; c0 < col0 + ncols; c0 += 16) {
-    float v[16];
-    tmem_ld_32x16(taddr + c0, v);
-    const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);     // broadcast LDS.128
-    float4 bb[4];
+MINPPO_DEVINL void act_chunk(const float (&v)[16], uint32_t dst_base, const float* bias_s, int row, int c0) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);     // broadcast LDS.128
+  float4 bb[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) bb[j] = b4[j];
-    tmem_ld_wait();
+  for (int j = 0; j < 4; ++j) bb[j] = b4[j];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint32_t w[4];
-      const float bj[8] = {bb[2 * j].x, bb[2 * j].y, bb[2 * j].z, bb[2 * j].w,
-                           bb[2 * j + 1].x, bb[2 * j + 1].y, bb[2 * j + 1].z, bb[2 * j + 1].w};
+  for (int j = 0; j < 2; ++j) {
+    uint32_t w[4];
+    const float bj[8] = {bb[2 * j].x, bb[2 * j].y, bb[2 * j].z, bb[2 * j].w,
+                         bb[2 * j + 1].x, bb[2 * j + 1].y, bb[2 * j + 1].z, bb[2 * j + 1].w};
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int e = 8 * j + 2 * t;
-        const float x0 = act_apply<ACT>(v[e] + bj[2 * t]);
-        const float x1 = act_apply<ACT>(v[e + 1] + bj[2 * t + 1]);
-        w[t] = pack_bf16x2(x0, x1);
-      }
-      sts128(dst_base + sw_off(row, c0 + 8 * j), make_uint4(w[0], w[1], w[2], w[3]));
+    for (int t = 0; t < 4; ++t) {
+      const int e = 8 * j + 2 * t;
+      const float x0 = act_apply<ACT>(v[e] + bj[2 * t]);
+      const float x1 = act_apply<ACT>(v[e + 1] + bj[2 * t + 1]);
+      w[t] = pack_bf16x2(x0, x1);
     }
+    sts128(dst_base + sw_off(row, c0 + 8 * j), make_uint4(w[0], w[1], w[2], w[3]));
   }
 }
+template <int ACT>
+__device__ __noinline__ void epilogue_act_t(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int row, int q, int col0,
+                                            int cstride, int nchunks, uint64_t* bars) {
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+  float va[16], vb[16];
+  tmem_ld_32x16(taddr + col0, va);
+  for (int i = 0; i < nchunks; i += 2) {
+    const int c0 = col0 + i * cstride;
+    tmem_ld_wait();
+    tmem_ld_32x16(taddr + (i + 1 < nchunks ? c0 + cstride : c0), vb);          // branch-free: the last chunk re-reads itself
+    __syncwarp();
+    act_chunk<ACT>(va, dst_base, bias_s, row, c0);
+    if (bars) chunk_publish(bars + i);
+    if (i + 1 < nchunks) {
+      tmem_ld_wait();
+      tmem_ld_32x16(taddr + (i + 2 < nchunks ? c0 + 2 * cstride : c0), va);
+      __syncwarp();
+      act_chunk<ACT>(vb, dst_base, bias_s, row, c0 + cstride);
+      if (bars) chunk_publish(bars + i + 1);
+    }
+  }
+  tmem_ld_wait();                                                  // the trailing read must have landed before the registers are reused
+}
 MINPPO_DEVINL void epilogue_act(uint32_t tmem_acc, uint32_t dst_base, const float* bias_s, int act, int row, int q,
-                                int col0, int ncols) {
-  if (act == ACT_RELU) epilogue_act_t<ACT_RELU>(tmem_acc, dst_base, bias_s, row, q, col0, ncols);
-  else if (act == ACT_TANH_FAST) epilogue_act_t<ACT_TANH_FAST>(tmem_acc, dst_base, bias_s, row, q, col0, ncols);
-  else epilogue_act_t<ACT_TANH>(tmem_acc, dst_base, bias_s, row, q, col0, ncols);
+                                int col0, int cstride, int nchunks, uint64_t* bars) {
+  if (act == ACT_RELU) epilogue_act_t<ACT_RELU>(tmem_acc, dst_base, bias_s, row, q, col0, cstride, nchunks, bars);
+  else if (act == ACT_TANH_FAST) epilogue_act_t<ACT_TANH_FAST>(tmem_acc, dst_base, bias_s, row, q, col0, cstride, nchunks, bars);
+  else epilogue_act_t<ACT_TANH>(tmem_acc, dst_base, bias_s, row, q, col0, cstride, nchunks, bars);
 }
 
 // dZ = acc * f'(h): h read from `h_base`, bf16 result written to `dst_base` (may alias h_base:
 // every thread touches only its own 16-byte chunks).  The bias gradients (column sums of dZ) are
 // not formed here: they come from the tensor core as dZ^T x ones.
 template <int ACT>
-__device__ __noinline__ void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, int row, int q, int col0,
-                                             int ncols) {
-  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-  for (int c0 = col0; c0 < col0 + ncols; c0 += 16) {
-    float v[16];
-    tmem_ld_32x16(taddr + c0, v);
-    uint4 hh[2];
+MINPPO_DEVINL void dact_chunk(const float (&v)[16], uint32_t h_base, uint32_t dst_base, int row, int c0) {
+  uint4 hh[2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) hh[j] = lds128(h_base + sw_off(row, c0 + 8 * j));
-    tmem_ld_wait();
+  for (int j = 0; j < 2; ++j) hh[j] = lds128(h_base + sw_off(row, c0 + 8 * j));
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const uint32_t hw[4] = {hh[j].x, hh[j].y, hh[j].z, hh[j].w};
-      uint32_t w[4];
+  for (int j = 0; j < 2; ++j) {
+    const uint32_t hw[4] = {hh[j].x, hh[j].y, hh[j].z, hh[j].w};
+    uint32_t w[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int e = 8 * j + 2 * t;
-        w[t] = pack_bf16x2(v[e] * act_deriv_t<ACT>(bf16_lo(hw[t])), v[e + 1] * act_deriv_t<ACT>(bf16_hi(hw[t])));
-      }
-      sts128(dst_base + sw_off(row, c0 + 8 * j), make_uint4(w[0], w[1], w[2], w[3]));
+    for (int t = 0; t < 4; ++t) {
+      const int e = 8 * j + 2 * t;
+      w[t] = pack_bf16x2(v[e] * act_deriv_t<ACT>(bf16_lo(hw[t])), v[e + 1] * act_deriv_t<ACT>(bf16_hi(hw[t])));
     }
+    sts128(dst_base + sw_off(row, c0 + 8 * j), make_uint4(w[0], w[1], w[2], w[3]));
   }
 }
+template <int ACT>
+__device__ __noinline__ void epilogue_dact_t(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, int row, int q, int col0,
+                                             int cstride, int nchunks, uint64_t* bars) {
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+  float va[16], vb[16];
+  tmem_ld_32x16(taddr + col0, va);
+  for (int i = 0; i < nchunks; i += 2) {
+    const int c0 = col0 + i * cstride;
+    tmem_ld_wait();
+    tmem_ld_32x16(taddr + (i + 1 < nchunks ? c0 + cstride : c0), vb);          // branch-free: the last chunk re-reads itself
+    __syncwarp();
+    dact_chunk<ACT>(va, h_base, dst_base, row, c0);
+    if (bars) chunk_publish(bars + i);
+    if (i + 1 < nchunks) {
+      tmem_ld_wait();
+      tmem_ld_32x16(taddr + (i + 2 < nchunks ? c0 + 2 * cstride : c0), va);
+      __syncwarp();
+      dact_chunk<ACT>(vb, h_base, dst_base, row, c0 + cstride);
+      if (bars) chunk_publish(bars + i + 1);
+    }
+  }
+  tmem_ld_wait();                                                  // the trailing read must have landed before the registers are reused
+}
 MINPPO_DEVINL void epilogue_dact(uint32_t tmem_acc, uint32_t h_base, uint32_t dst_base, int act, int row, int q,
-                                 int col0, int ncols) {
-  if (act == ACT_RELU) epilogue_dact_t<ACT_RELU>(tmem_acc, h_base, dst_base, row, q, col0, ncols);
-  else epilogue_dact_t<ACT_TANH>(tmem_acc, h_base, dst_base, row, q, col0, ncols);
+                                 int col0, int cstride, int nchunks, uint64_t* bars) {
+  if (act == ACT_RELU) epilogue_dact_t<ACT_RELU>(tmem_acc, h_base, dst_base, row, q, col0, cstride, nchunks, bars);
+  else epilogue_dact_t<ACT_TANH>(tmem_acc, h_base, dst_base, row, q, col0, cstride, nchunks, bars);
 }
 
 // One (tile, net) unit of one minibatch step.  The whole CTA (FS_THREADS threads) calls this with the SAME arguments;
@@ -236,6 +319,8 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
   float* hb = reinterpret_cast<float*>(sm + LY::HB);            // [0, AP) head bias, [AP, 2AP) log_std,
                                                                 // [2AP, 3AP) 1 / scale, [3AP] sum log|scale|
   float* red = reinterpret_cast<float*>(sm + LY::RED);
+  float* qp = bias_s;                                           // [4 column groups][128 rows] partial quadratic forms of the actor loss:
+                                                                // aliases the hidden biases, dead once every warp is past epilogue 2 (headf)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + LY::BARS);
   uint64_t* l1_full = bars;             // [8] W0 half-k-block landed (TMA)
   uint64_t* l1_empty = bars + 8;        // [8] ... consumed (MMA commit)
@@ -250,7 +335,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
   uint64_t* dh1f = bars + 36;           // dH1 accumulator complete
   uint64_t* cs2f = bars + 37;           // column sums of dZ2 complete
   uint64_t* cs1f = bars + 38;           // column sums of dZ1 complete
-  uint64_t* h2r = bars + 39;            // H2 in R1, acc1 drained
+  uint64_t* h2r = bars + 57;            // [4] H2 columns [64 b, 64 b + 64) in R1 (k-block b of the head GEMM); all: acc1 drained
   uint64_t* gr = bars + 40;             // g^T hi/lo written
   uint64_t* h1r = bars + 41;            // [4] H1 columns [64 b, 64 b + 64) in R0 (k-block b of the L2 GEMM)
   uint64_t* dz2r = bars + 45;           // [4] dZ2 columns [64 b, 64 b + 64) in R1 (k-block b of the dH1 GEMM)
@@ -291,18 +376,19 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     for (int s = 0; s < 4; ++s) {
       mbar_init(&x_full[s], FS_NWW); mbar_init(&x_empty[s], 1); mbar_init(&x_stored[s], 1);
       mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
-      mbar_init(&h1r[s], FS_NWW); mbar_init(&dz2r[s], FS_NWW); mbar_init(&dz1r[s], FS_NWW);
+      mbar_init(&h1r[s], FS_NWW); mbar_init(&h2r[s], FS_NWW); mbar_init(&dz2r[s], FS_NWW); mbar_init(&dz1r[s], FS_NWW);
     }
     mbar_init(accf0, 1); mbar_init(accf1, 1); mbar_init(headf, 1); mbar_init(bwdf, 1); mbar_init(dh1f, 1);
     mbar_init(cs2f, 1); mbar_init(cs1f, 1);
-    mbar_init(h2r, FS_NWW); mbar_init(gr, FS_NWW);
+    mbar_init(gr, FS_NWW);
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256;
-  const uint32_t acc_head = acc1;               // [256, 256 + 2AP): head outputs, hi | lo halves (after acc1 is drained)
+  const uint32_t acc_head = acc0;               // [0, 2AP): head outputs, hi | lo halves (acc0 is free between epilogue 1 and dA2: the head
+                                                // MMAs of k-block b run while epilogue 2 still drains acc1 for the later blocks)
   const uint32_t acc_dw = acc1 + 2 * AP;        // + 2AP per 128-column tile of H: head-kernel gradient, hi | lo halves
   const uint32_t acc_cs2 = acc0;                // + 16 per 128-column tile: column sums of dZ2 (after acc0 = dA2 is drained)
   const uint32_t acc_cs1 = acc0 + 32;           // + 16 per 128-column tile: column sums of dZ1
@@ -390,19 +476,21 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
       umma_commit(accf1);
       FS_STAMP(21);
       // ---- head forward: [out_hi | out_lo][128 x 2AP] = H2 [W2_hi | W2_lo]; A = H2 K-major, B = W2T K-major with the
-      //      bf16 hi / lo halves stacked along N (the workers add the two halves)
-      mbar_wait_spin(h2r, 0);
-      tc_fence_after();
+      //      bf16 hi / lo halves stacked along N (the workers add the two halves); k-block b as soon as epilogue 2 has
+      //      published it
       {
         const uint32_t idesc_h = umma_idesc_bf16(128, 2u * AP, 0u, 0u);
         uint32_t accum = 0;
-        for (int kb = 0; kb < nkH; ++kb)
+        for (int kb = 0; kb < nkH; ++kb) {
+          mbar_wait_spin(&h2r[kb], 0);
+          tc_fence_after();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             umma_bf16(acc_head, umma_smem_desc(R1 + kb * 16384 + j * 32, 16, 1024),
                       umma_smem_desc(W2T + kb * PG + j * 32, 16, 1024), idesc_h, accum);
             accum = 1;
           }
+        }
         umma_commit(headf);
       }
       FS_STAMP(24);
@@ -434,7 +522,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
         umma_commit(bwdf);
       }
       FS_STAMP(25);
-      // ---- dH1: acc1 = dZ2 W1^T in two N halves.  Accumulates into acc1: every worker warp has read the head / dW2
+      // ---- dH1: acc1 = dZ2 W1^T in two N halves.  Accumulates into acc1: every worker warp has read the dW2
       //      columns of acc1 before its first arrival on dz2r[0], while acc0 (dA2) is still being drained by the dZ2 epilogue
       {
         const uint32_t idesc_h2 = umma_idesc_bf16(128, static_cast<uint32_t>(H >> 1), 0u, 0u);
@@ -490,9 +578,10 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     int src_g[2];
 #pragma unroll
     for (int g = 0; g < 2; ++g) src_g[g] = rowidx_s[tile * 128 + grow0 + 64 * g];
-    const int lrow = tile * 128 + erow;                          // loss row of this thread (sub == 0 warps)
+    const int lrow = tile * 128 + erow;                          // loss row of this thread (actor: the four warps of a lane
+                                                                 // quadrant share a row, AP / 4 head columns each; critic: sub == 0)
     const int count = min(*count_s, p.cap);
-    const bool live = (sub == 0) && (lrow < count);
+    const bool live = (sub == 0 || net == 0) && (lrow < count);
     const int src_l = live ? rowidx_s[lrow] : 0;
     // one warp instruction copies 4 rows x 128 contiguous bytes (4 L1 wavefronts; a lane-per-row mapping needed 32)
     auto gather_block = [&](int kb) {
@@ -508,6 +597,33 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     for (int kb = 0; kb < nb0; ++kb) gather_block(kb);
     if (wt == 0) FS_STAMP(26);
     const float adv_sum = p.adv_sum[step], adv_sq = p.adv_sq[step];
+    // per-row loss inputs (update-static: old log-prob / value, advantage / target, action), requested BEFORE the dependency
+    // wait: under PDL this part of the kernel runs while the previous optimizer step drains, so the loads -- each touches 32
+    // distinct lines -- are off the critical path.  Measured (configs[1], ms per update): here 5.48; after the X rows are
+    // published, in the shadow of the L1 GEMM, 5.70; after epilogue 2, where the values are needed, 5.67 -- there the burst of the
+    // warps that finish the epilogue first stalled the shared-memory traffic of the warp that finishes last by ~2k cycles.
+    constexpr int CW = AP / 4;                                   // head columns of one actor loss warp: [sub CW, sub CW + CW)
+    const int j0 = sub * CW;
+    float in0 = 0.f, in1 = 0.f, zz[CW];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) zz[j] = 0.f;
+    if (live) {
+      if (net == 0) {
+        in0 = p.logp_old[src_l]; in1 = p.adv[src_l];
+        const float* ap = p.action + static_cast<size_t>(src_l) * aout + j0;
+        if ((aout & 1) == 0) {                                     // rows are 8-byte aligned: half the load wavefronts
+#pragma unroll
+          for (int j = 0; j < CW; j += 2)
+            if (j0 + j < aout) { const float2 v = *reinterpret_cast<const float2*>(ap + j); zz[j] = v.x; zz[j + 1] = v.y; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) if (j0 + j < aout) zz[j] = ap[j];
+        }
+      } else {
+        in0 = p.v_old[src_l]; in1 = p.tgt[src_l];
+      }
+    }
+
     // ---- everything below reads what the previous optimizer step wrote (PDL: see common.cuh) -------
     griddep_wait();
     if (wt == 0) griddep_launch();
@@ -579,15 +695,15 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     // the X store has read R1 before this warp's h1r arrivals let the L2 GEMM (and then epilogue 2, which
     // overwrites R1) proceed
     if (x_store) tma_store_wait_read0();
-    for (int b = 0; b < nkH; ++b) {
-      epilogue_act(acc0, R0, bias_s, act, erow, q, b * 64 + sub * 16, 16);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&h1r[b]);
-    }
+#ifndef FS_TRACE_EPI2_ALL
+    FS_STAMP_W(32);
+#endif
+    epilogue_act(acc0, R0, bias_s, act, erow, q, sub * 16, 64, nkH, h1r);   // 64-column block b published on h1r[b]
+#ifndef FS_TRACE_EPI2_ALL
+    FS_STAMP_W(36);
+#endif
     if (wt == 0) FS_STAMP(3);
-    if (wt == 32) {                                               // warp 1 lane 0: its own arrivals are done
+    if (wt == FS_STORE_THREAD) {                                  // its own arrivals are done
       for (int b = 0; b < nkH; ++b) {
         mbar_wait(&h1r[b], 0);
         tma_store_2d(R0 + b * 16384, &G.tm_h1, b * 64, tile * 128);
@@ -599,60 +715,61 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     mbar_wait(accf1, 0);
     tc_fence_after();
     if (wt == 0) FS_STAMP(4);
-    epilogue_act(acc1, R1, bias_s + 256, act, erow, q, sub * (H >> 2), H >> 2);
-    fence_proxy_async_smem();                                    // H2 -> async proxy for the head MMAs
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(h2r);
+#ifdef FS_TRACE_EPI2_ALL                                         // debug build: all 16 warps around epilogue 2 (slots 32 + warp / 48 + warp)
+    if (p.trace && lane == 0) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + 32 + warp] = clock64();
+#else
+    FS_STAMP_W(40);
+#endif
+#ifndef FS_TRACE_EPI2_ALL
+    epilogue_act(acc1, R1, bias_s + 256, act, erow, q, sub * 16, 64, nkH, h2r);   // 64-column block b published on h2r[b] (head MMAs)
+    FS_STAMP_W(44);
+#else
+    for (int b = 0; b < nkH; ++b) {
+      epilogue_act(acc1, R1, bias_s + 256, act, erow, q, sub * 16 + 64 * b, 64, 1, h2r + b);
+      if (p.trace && lane == 0) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + 64 + warp * 4 + b] = clock64();
+    }
+    if (p.trace && lane == 0) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + 48 + warp] = clock64();
+#endif
     if (wt == 0) FS_STAMP(5);
 
-    // per-row loss inputs, requested here, in the shadow of the head MMAs (32 distinct lines per load instruction)
-    float in0 = 0.f, in1 = 0.f, zz[AP];
-#pragma unroll
-    for (int j = 0; j < AP; ++j) zz[j] = 0.f;
-    if (live) {
-      if (net == 0) {
-        in0 = p.logp_old[src_l]; in1 = p.adv[src_l];
-        const float* ap = p.action + static_cast<size_t>(src_l) * aout;
-        if ((aout & 1) == 0) {                                     // rows are 8-byte aligned: half the load wavefronts
-#pragma unroll
-          for (int j = 0; j < AP; j += 2)
-            if (j < aout) { const float2 v = *reinterpret_cast<const float2*>(ap + j); zz[j] = v.x; zz[j + 1] = v.y; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < AP; ++j) if (j < aout) zz[j] = ap[j];
-        }
-      } else {
-        in0 = p.v_old[src_l]; in1 = p.tgt[src_l];
-      }
-    }
-
-    // ---- loss and gradient seed g = dL/dout: thread = row (sub == 0 warps) ---------------------------
+    // ---- loss and gradient seed g = dL/dout ------------------------------------------------------------------
+    // actor: thread = (row, CW head columns) -- the four warps of a TMEM lane quadrant split the AP columns of a row and
+    // combine the quadratic form through shared memory; critic: thread = row on the sub == 0 warps (one column)
     mbar_wait(headf, 0);
     tc_fence_after();
     if (wt == 0) FS_STAMP(6);
-    if (sub == 0) {
+    {
       const uint32_t th = acc_head + (static_cast<uint32_t>(q * 32) << 16);
       const float inv_n = p.inv_mb;
-      float s_loss = 0.f, g_logp = 0.f, g0 = 0.f;
+      // g^T as bf16 hi/lo, [2AP j][128 rows] SW128 (the MN-major A of dA2 and the K-major B of dW2)
+      const uint32_t gcol = GT + (erow >> 6) * PG + ((erow & 7) << 1);
+      const int gch = (erow & 63) >> 3;
+      auto put_g = [&](int j, float gj) {
+        uint32_t hi, lo;
+        split_bf16(gj, hi, lo);
+        sts_u16(gcol + j * 128 + ((gch ^ (j & 7)) << 4), hi);
+        sts_u16(gcol + (AP + j) * 128 + ((gch ^ ((AP + j) & 7)) << 4), lo);
+      };
+      float* rw = red + q * RS;                                    // [0, AP) dlog_std, [AP, 2 AP) head bias, [2 AP] loss
       if (net == 0) {
         // distrax MultivariateNormalDiag: z = (a - loc) * (1/scale); train.py:223, 234-239.  zz: action -> z in place
+        float ohi[CW], olo[CW];
+        tmem_ld_32xn(th + j0, ohi);
+        tmem_ld_32xn(th + AP + j0, olo);
+        tmem_ld_wait();
         float quad = 0.f;
 #pragma unroll
-        for (int c = 0; c < AP / 16; ++c) {
-          float ohi[16], olo[16];
-          tmem_ld_32x16(th + 16 * c, ohi);
-          tmem_ld_32x16(th + AP + 16 * c, olo);
-          tmem_ld_wait();
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const int j = 16 * c + jj;
-            const float mean = (ohi[jj] + olo[jj]) + hb[j];                 // W2_hi and W2_lo contributions
-            const float z = j < aout ? (zz[j] - mean) * hb[2 * AP + j] : 0.f;
-            zz[j] = z;
-            if (j < aout) quad += -0.5f * z * z - 0.91893853320467274178f;
-          }
+        for (int jj = 0; jj < CW; ++jj) {
+          const int j = j0 + jj;
+          const float mean = (ohi[jj] + olo[jj]) + hb[j];                   // W2_hi and W2_lo contributions
+          const float z = j < aout ? (zz[jj] - mean) * hb[2 * AP + j] : 0.f;
+          zz[jj] = z;
+          if (j < aout) quad += -0.5f * z * z - 0.91893853320467274178f;
         }
+        qp[sub * 128 + erow] = quad;
+        worker_bar();
+        quad = ((qp[erow] + qp[128 + erow]) + qp[256 + erow]) + qp[384 + erow];   // fixed order: column groups 0..3
+        float s_loss = 0.f, g_logp = 0.f;
         if (live) {
           const float logp = quad - hb[3 * AP];
           const float ratio = expf(logp - in0);
@@ -667,10 +784,28 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
           const float dmin = (w1 + (1.f - w1) * dclip_f(ratio, lo, hi)) * adv;
           g_logp = -inv_n * dmin * ratio;
         }
-      } else {
+        // tile sums of dlog_std and of the head-bias gradient g through a 2 CW x 32 transpose-reduce
+        float v[2 * CW];
+#pragma unroll
+        for (int jj = 0; jj < CW; ++jj) {
+          const int j = j0 + jj;
+          const float gj = g_logp * (zz[jj] * hb[2 * AP + j]);
+          if (j < aout) put_g(j, gj);
+          v[jj] = j < aout ? g_logp * (zz[jj] * zz[jj] - 1.f) : 0.f;
+          v[CW + jj] = gj;
+        }
+        const float cs = warp_colsum_n<2 * CW>(v);
+        if (lane < CW) rw[j0 + lane] = cs;
+        else if (lane < 2 * CW) rw[AP + j0 + lane - CW] = cs;
+        if (sub == 0) {
+          s_loss = warp_sum(s_loss);
+          if (lane == 0) rw[2 * AP] = s_loss;
+        }
+      } else if (sub == 0) {
         const float ohi = tmem_ld_32x1(th);
         const float olo = tmem_ld_32x1(th + AP);
         tmem_ld_wait();
+        float s_loss = 0.f, g0 = 0.f;
         if (live) {
           // clipped value loss, train.py:226-231
           const float v = (ohi + olo) + hb[0];
@@ -682,43 +817,12 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
           const float wa = vl > vlc ? 1.f : (vl == vlc ? 0.5f : 0.f);
           g0 = p.vf_coef * 0.5f * inv_n * (wa * 2.f * e1 + (1.f - wa) * 2.f * e2 * dclip_f(dvv, -p.clip_eps, p.clip_eps));
         }
+        put_g(0, g0);
+        const float gs = warp_sum(g0);
+        s_loss = warp_sum(s_loss);
+        for (int i = lane; i < 2 * AP; i += 32) rw[i] = i == AP ? gs : 0.f;       // head bias gradient = sum of g; no log_std
+        if (lane == 0) rw[2 * AP] = s_loss;
       }
-      // g^T as bf16 hi/lo, [2AP j][128 rows] SW128 (the MN-major A of dA2 and the K-major B of dW2); tile sums of
-      // dlog_std and of the head-bias gradient g through a 32 x 32 transpose-reduce (lane j ends with column j)
-      const uint32_t gcol = GT + (erow >> 6) * PG + ((erow & 7) << 1);
-      const int gch = (erow & 63) >> 3;
-      auto put_g = [&](int j, float gj) {
-        uint32_t hi, lo;
-        split_bf16(gj, hi, lo);
-        sts_u16(gcol + j * 128 + ((gch ^ (j & 7)) << 4), hi);
-        sts_u16(gcol + (AP + j) * 128 + ((gch ^ ((AP + j) & 7)) << 4), lo);
-      };
-      float* rw = red + q * RS;
-      if (AP == 16) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float gj = net == 0 ? g_logp * (zz[j] * hb[2 * AP + j]) : (j == 0 ? g0 : 0.f);
-          if (j < aout) put_g(j, gj);
-          v[j] = (net == 0 && j < aout) ? g_logp * (zz[j] * zz[j] - 1.f) : 0.f;
-          v[16 + j] = gj;
-        }
-        rw[lane] = warp_colsum32(v);                               // [0, 16) dlog_std, [16, 32) head bias
-      } else {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (net == 0 && j < aout) ? g_logp * (zz[j] * zz[j] - 1.f) : 0.f;
-        rw[lane] = warp_colsum32(v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float gj = net == 0 ? g_logp * (zz[j] * hb[2 * AP + j]) : (j == 0 ? g0 : 0.f);
-          if (j < aout) put_g(j, gj);
-          v[j] = gj;
-        }
-        rw[32 + lane] = warp_colsum32(v);
-      }
-      s_loss = warp_sum(s_loss);
-      if (lane == 0) rw[2 * AP] = s_loss;
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -755,15 +859,15 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
         }
       }
     }
-    for (int b = 0; b < nkH; ++b) {
-      epilogue_dact(acc0, R1, R1, act, erow, q, b * 64 + sub * 16, 16);            // in place: H2 -> dZ2
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dz2r[b]);
-    }
+#ifndef FS_TRACE_EPI2_ALL
+    FS_STAMP_W(48);
+#endif
+    epilogue_dact(acc0, R1, R1, act, erow, q, sub * 16, 64, nkH, dz2r);            // in place: H2 -> dZ2, block b published on dz2r[b]
+#ifndef FS_TRACE_EPI2_ALL
+    FS_STAMP_W(52);
+#endif
     if (wt == 0) FS_STAMP(9);
-    if (wt == 32) {
+    if (wt == FS_STORE_THREAD) {
       for (int b = 0; b < nkH; ++b) {
         mbar_wait(&dz2r[b], 0);
         tma_store_2d(R1 + b * 16384, &G.tm_dz2, b * 64, tile * 128);
@@ -776,21 +880,21 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     mbar_wait(cs2f, 0);                                            // ... nor by the column-sum MMAs
     tc_fence_after();
     if (wt == 0) FS_STAMP(10);
-    if (wt == 32) tma_store_wait_read0();                          // ... nor by the dZ2 TMA store
+    if (wt == FS_STORE_THREAD) tma_store_wait_read0();                          // ... nor by the dZ2 TMA store
     float cs2 = 0.f;
     if (sub < mtH) cs2 = tmem_ld_32x1(acc_cs2 + 16 * sub + (static_cast<uint32_t>(q * 32) << 16));
     tmem_ld_wait();
     worker_bar();
     if (sub < mtH && sub * 128 + erow < H) part[G.po_db1 + sub * 128 + erow] = cs2;     // layer-1 bias gradient of this tile
-    for (int b = 0; b < nkH; ++b) {                                // 64-column blocks, each stored as soon as it is complete
-      epilogue_dact(acc1, R0, R1, act, erow, q, b * 64 + sub * 16, 16);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dz1r[b]);
-    }
+#ifndef FS_TRACE_EPI2_ALL
+    FS_STAMP_W(56);
+#endif
+    epilogue_dact(acc1, R0, R1, act, erow, q, sub * 16, 64, nkH, dz1r);   // 64-column blocks, each stored as soon as it is complete
+#ifndef FS_TRACE_EPI2_ALL
+    FS_STAMP_W(60);
+#endif
     if (wt == 0) FS_STAMP(11);
-    if (wt == 32) {
+    if (wt == FS_STORE_THREAD) {
       for (int b = 0; b < nkH; ++b) {
         mbar_wait(&dz1r[b], 0);
         tma_store_2d(R1 + b * 16384, &G.tm_dz1, b * 64, tile * 128);
@@ -807,7 +911,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     // The bulk stores must have READ shared memory before it is reused, and -- for a persistent caller, whose next phase
     // reads H1 / dZ / X from other CTAs after a grid barrier, not after a kernel boundary -- their global writes must be
     // complete and ordered before this thread's later (generic-proxy) barrier arrival.
-    if (wt == 32 || x_store) {
+    if (wt == FS_STORE_THREAD || x_store) {
       if (PERSISTENT) { tma_store_wait_all0(); fence_proxy_async_global(); }
       else tma_store_wait_read0();                                 // one launch per step: the writes complete with the grid
     }

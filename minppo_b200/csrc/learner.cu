@@ -250,7 +250,7 @@ struct minppo_ctx {
   // device buffers
   std::vector<void*> allocs;
   float *adv, *tgt, *stats, *gflat, *block_ss, *head_part, *gnorms, *losses_scratch;
-  long long* trace;           // debug cycle stamps of the fused kernel [2*m_tiles][32]
+  long long* trace;           // debug cycle stamps of the fused kernel [2*m_tiles][FS_TRACE_SLOTS]
   long long* trace2;          // debug cycle stamps of the dwopt kernel [sm_count][8]
   bool trace_on;
   bool pdl;                   // programmatic dependent launch between step kernels (MINPPO_PDL=0 disables)
@@ -991,7 +991,7 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   ALLOC(c->head_part, static_cast<size_t>(c->tiles64) * c->head_stride);
   ALLOC(c->gnorms, static_cast<size_t>(EM));
   ALLOC(c->losses_scratch, 4);
-  ALLOC(c->trace, static_cast<size_t>(2 * c->m_tiles) * 32);
+  ALLOC(c->trace, static_cast<size_t>(2 * c->m_tiles) * FS_TRACE_SLOTS);
   ALLOC(c->trace2, static_cast<size_t>(c->sm_count) * 16);
   c->trace_on = getenv("MINPPO_TRACE") != nullptr;
   c->pdl = !(getenv("MINPPO_PDL") && atoi(getenv("MINPPO_PDL")) == 0);
@@ -1307,7 +1307,7 @@ int minppo_ctx_read(minppo_ctx* c, int32_t what, void* dst, size_t bytes, void* 
     case 4: src = c->gnorms; have = EM * 4; break;
     case 5: src = c->counts; have = EM * 4; break;
     case 6: src = c->stats; have = 2 * EM * 4; break;
-    case 7: src = c->trace; have = static_cast<size_t>(2 * c->m_tiles) * 32 * 8; break;
+    case 7: src = c->trace; have = static_cast<size_t>(2 * c->m_tiles) * FS_TRACE_SLOTS * 8; break;
     case 8: src = c->trace2; have = static_cast<size_t>(c->sm_count) * 16 * 8; break;
     default: set_error("minppo_ctx_read: unknown buffer %d", what); return MINPPO_ERR_ARG;
   }

@@ -228,17 +228,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) policy_fused_kernel(const __gri
     // ---- epilogue 1: H1 -> R0 (published in 64-column blocks) ----
     mbar_wait(accf0, 0);
     tc_fence_after();
-    for (int b = 0; b < nkH; ++b) {
-      epilogue_act(acc0, R0, bias_s, act, erow, q, b * 64 + sub * 16, 16);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&h1r[b]);
-    }
+    epilogue_act(acc0, R0, bias_s, act, erow, q, sub * 16, 64, nkH, h1r);
     // ---- epilogue 2: H2 -> R1 ----
     mbar_wait(accf1, 0);
     tc_fence_after();
-    epilogue_act(acc1, R1, bias_s + 256, act, erow, q, sub * (H >> 2), H >> 2);
+    epilogue_act(acc1, R1, bias_s + 256, act, erow, q, sub * (H >> 2), 16, H >> 6, nullptr);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();

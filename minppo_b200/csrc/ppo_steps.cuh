@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) ppo_steps_kernel(const __grid_c
   const uint32_t tmem_base = tmem_slot;
 
   // debug stamps (MINPPO_TRACE): row b of the fused kernel's trace buffer, slots the tile body leaves free
-  long long* tr = (P.fs.trace && b < P.units && threadIdx.x == 0) ? P.fs.trace + static_cast<size_t>(b) * 32 : nullptr;
+  long long* tr = (P.fs.trace && b < P.units && threadIdx.x == 0) ? P.fs.trace + static_cast<size_t>(b) * FS_TRACE_SLOTS : nullptr;
 #define PS_STAMP(slot) do { if (tr) tr[(slot)] = clock64(); } while (0)
   for (int s = P.s0; s < P.s1; ++s) {
     PS_STAMP(13);
