@@ -179,6 +179,11 @@ MINPPO_DEVINL void tma_store_3d(uint32_t smem_src, const CUtensorMap* m, int c0,
                "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// 1-D bulk store shared -> global (16-byte aligned addresses, size a multiple of 16), part of the thread's bulk async-group
+MINPPO_DEVINL void bulk_store_1d(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+MINPPO_DEVINL void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 MINPPO_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 MINPPO_DEVINL void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 MINPPO_DEVINL void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

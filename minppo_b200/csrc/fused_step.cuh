@@ -844,6 +844,9 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     tc_fence_after();
     if (wt == 0) FS_STAMP(8);
     if (sub < mtH) {                                             // warp (q, sub) reads the 128-column tile mh = sub
+      // staged in shared memory as the [H][aout] fp32 block of the partial (the W2T image is dead once bwdf has fired) and
+      // written by ONE bulk copy: as per-thread stores (a row of aout floats per lane: ~11 lines per store instruction) this
+      // section held the dZ2 epilogue of these warps back by ~2k cycles
       const uint32_t td = acc_dw + 2 * AP * sub + (static_cast<uint32_t>(q * 32) << 16);
       const int c = sub * 128 + erow;
 #pragma unroll
@@ -855,8 +858,14 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
         if (c < H) {
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj)
-            if (16 * ch + jj < aout) part[G.po_w2 + c * aout + 16 * ch + jj] = dhi[jj] + dlo[jj];   // g_hi and g_lo contributions
+            if (16 * ch + jj < aout) sts32(W2T + static_cast<uint32_t>(c * aout + 16 * ch + jj) * 4u, dhi[jj] + dlo[jj]);   // g_hi and g_lo contributions
         }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, %0;" ::"r"(128 * mtH) : "memory");   // the warps with sub < mtH = threads [0, 128 mtH)
+      if (wt == 0) {
+        bulk_store_1d(part + G.po_w2, W2T, static_cast<uint32_t>(H * aout) * 4u);
+        tma_store_commit();
       }
     }
 #ifndef FS_TRACE_EPI2_ALL
@@ -911,7 +920,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     // The bulk stores must have READ shared memory before it is reused, and -- for a persistent caller, whose next phase
     // reads H1 / dZ / X from other CTAs after a grid barrier, not after a kernel boundary -- their global writes must be
     // complete and ordered before this thread's later (generic-proxy) barrier arrival.
-    if (wt == FS_STORE_THREAD || x_store) {
+    if (wt == FS_STORE_THREAD || wt == 0) {                       // thread 0: the dW2 bulk copy (and, critic CTA, the X stores)
       if (PERSISTENT) { tma_store_wait_all0(); fence_proxy_async_global(); }
       else tma_store_wait_read0();                                 // one launch per step: the writes complete with the grid
     }

@@ -956,9 +956,10 @@ int minppo_ctx_create(const minppo_config* cfg, const void* nccl_unique_id_host,
   const int H = c->H, L = c->L, A = c->A;
   // head partial layout
   {
-    int o = 0;
-    c->po_w3a = o; o += H * A;
+    int o = 0;                                       // (the head-kernel gradients start 16-byte aligned: the fused step writes
+    c->po_w3a = o; o += H * A;                       //  each of them with one bulk copy)
     c->po_b3a = o; o += A;
+    o = (o + 3) / 4 * 4;
     c->po_w3c = o; o += H;
     c->po_b3c = o; o += 1;
     c->po_logstd = o; o += A;
