@@ -11,7 +11,7 @@
 //   head out  = H2 W2    (N = 2 AP: bf16 hi | lo)               -> +b2 -> Gaussian log-prob / clipped
 //        surrogate (actor CTA) or clipped value loss (critic CTA), train.py:218-243 -> g = dL/dout
 //   bwd  dA2  = g W2^T   (K = AP),  dW2 = H2^T g (N = 2 AP)     -> dZ2 = dA2 * f'(H2) in place -> TMA store
-//   dH1  acc1 = dZ2 W1^T (two N halves)                         -> * f'(H1), bf16 -> R1 (dZ1) -> TMA store
+//   dH1  acc1 = dZ2 W1^T (two N halves)                         -> * f'(H1), bf16 -> R0 (dZ1, over H1) -> TMA store
 //   bias gradients: column sums of dZ2 / dZ1 as dZ^T x ones (N = 16) MMAs -> per-tile partials
 //
 // The output-head operands W2 and g are fp32 quantities: they enter the tensor cores as a bf16
@@ -54,8 +54,8 @@ struct FsLayout {
   static constexpr int NS = AP == 16 ? 4 : 2;           // ring stages (L2 / dH1 weight streams)
   static constexpr int NS1 = NS + 4;                    // L1 only: four more stages parked in R0 (free until epilogue 1)
   static constexpr int PG = 2 * AP * 128;               // bytes of one 64-column panel of W2T / GT: [2 AP rows][128 B], rows = hi | lo
-  static constexpr int R0 = 0;                          // H1                  64 KB
-  static constexpr int R1 = 65536;                      // X / H2 / dZ2 / dZ1  64 KB
+  static constexpr int R0 = 0;                          // H1 / dZ1            64 KB
+  static constexpr int R1 = 65536;                      // X / H2 / dZ2        64 KB
   static constexpr int RB = 131072;                     // weight ring
   static constexpr int W2T = RB + NS * FS_STAGE;        // head kernel^T bf16 hi / lo, SW128, 4 panels (H <= 256)
   static constexpr int GT = W2T + 4 * PG;               // g^T bf16 hi / lo, SW128, 2 panels (128 rows)
@@ -110,14 +110,11 @@ struct alignas(64) FusedParams {
   long long* trace;              // debug: [ctas][32] clock64 stamps (null = off)
 };
 
-#ifdef FS_TRACE_EPI2_ALL
-constexpr int FS_TRACE_SLOTS = 128;                     // debug build: + [64, 128) every worker warp after each chunk of epilogue 2
-#else
-constexpr int FS_TRACE_SLOTS = 64;                      // clock64 stamps per unit: [0, 32) one thread per role, [32, 64) the four
-                                                        // worker warps of lane quadrant 0 around the four big epilogues
-#endif
+constexpr int FS_TRACE_SLOTS = 256;                     // clock64 stamps per unit: [0, 32) one thread per role, [64, 84) the MMA issuer
+                                                        // inside the dH1 GEMM (k-block seen / stage landed / MMAs issued), [128, 256) every
+                                                        // worker warp around the four big epilogues (128 + 32 e + warp: start, + 16: end)
 #define FS_STAMP(slot) do { if (p.trace) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + (slot)] = clock64(); } while (0)
-#define FS_STAMP_W(slot0) do { if (p.trace && q == 0 && lane == 0) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + (slot0) + sub] = clock64(); } while (0)
+#define FS_STAMP_W(e, end) do { if (p.trace && lane == 0) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + 128 + 32 * (e) + 16 * (end) + warp] = clock64(); } while (0)
 
 MINPPO_DEVINL void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -336,6 +333,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
   uint64_t* cs2f = bars + 37;           // column sums of dZ2 complete
   uint64_t* cs1f = bars + 38;           // column sums of dZ1 complete
   uint64_t* h2r = bars + 57;            // [4] H2 columns [64 b, 64 b + 64) in R1 (k-block b of the head GEMM); all: acc1 drained
+  uint64_t* ldi = bars + 39;            // the TMA producer has issued its last weight load
   uint64_t* gr = bars + 40;             // g^T hi/lo written
   uint64_t* h1r = bars + 41;            // [4] H1 columns [64 b, 64 b + 64) in R0 (k-block b of the L2 GEMM)
   uint64_t* dz2r = bars + 45;           // [4] dZ2 columns [64 b, 64 b + 64) in R1 (k-block b of the dH1 GEMM)
@@ -380,7 +378,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     }
     mbar_init(accf0, 1); mbar_init(accf1, 1); mbar_init(headf, 1); mbar_init(bwdf, 1); mbar_init(dh1f, 1);
     mbar_init(cs2f, 1); mbar_init(cs1f, 1);
-    mbar_init(gr, FS_NWW);
+    mbar_init(gr, FS_NWW); mbar_init(ldi, 1);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -430,6 +428,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
           const int ii = i - n2;
           tma_load_2d(dst, &G.tm_w1k, &full_bar[s], (ii >> 1) * 64, (ii & 1) * (H >> 1));
         }
+        if (i == total - 1) mbar_arrive(ldi);
       }
     }
   } else if (warp == FS_MMA_WARP) {
@@ -528,9 +527,11 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
         const uint32_t idesc_h2 = umma_idesc_bf16(128, static_cast<uint32_t>(H >> 1), 0u, 0u);
         for (int kb = 0; kb < nkH; ++kb) {
           mbar_wait_spin(&dz2r[kb], 0);
+          FS_STAMP(64 + kb);
           for (int nh = 0; nh < 2; ++nh, ++i) {
             const int s = i % NS;
             mbar_wait_spin(&full_bar[s], (i / NS) & 1);
+            FS_STAMP(68 + 2 * kb + nh);
             tc_fence_after();
             const uint32_t sa = R1 + kb * 16384, sb = RB + s * FS_STAGE;
 #pragma unroll
@@ -538,6 +539,7 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
               umma_bf16(acc1 + nh * (H >> 1), umma_smem_desc(sa + jj * 32, 16, 1024), umma_smem_desc(sb + jj * 32, 16, 1024),
                         idesc_h2, (kb > 0 || jj > 0) ? 1u : 0u);
             umma_commit(&empty_bar[s]);
+            FS_STAMP(76 + 2 * kb + nh);
           }
         }
         umma_commit(dh1f);
@@ -553,14 +555,14 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
           umma_bf16(acc_cs2 + 16 * mh, umma_smem_desc(R1 + 2 * mh * 16384 + t * 2048, 16384, 1024),
                     umma_smem_desc(ONES + (t >> 2) * 2048 + (t & 3) * 32, 16, 1024), idesc_cs, t > 0 ? 1u : 0u);
       umma_commit(cs2f);
-      // dZ1: epilogue 3 overwrites R1 block by block (after dh1f: the MMAs above have retired by then)
+      // dZ1: epilogue 3 writes it over H1 in R0, block by block
       for (int mh = 0; mh < mtH; ++mh) {
         mbar_wait_spin(&dz1r[2 * mh], 0);
         if (2 * mh + 1 < nkH) mbar_wait_spin(&dz1r[2 * mh + 1], 0);
         tc_fence_after();
 #pragma unroll
         for (int t = 0; t < 8; ++t)
-          umma_bf16(acc_cs1 + 16 * mh, umma_smem_desc(R1 + 2 * mh * 16384 + t * 2048, 16384, 1024),
+          umma_bf16(acc_cs1 + 16 * mh, umma_smem_desc(R0 + 2 * mh * 16384 + t * 2048, 16384, 1024),
                     umma_smem_desc(ONES + (t >> 2) * 2048 + (t & 3) * 32, 16, 1024), idesc_cs, t > 0 ? 1u : 0u);
       }
       umma_commit(cs1f);
@@ -695,13 +697,9 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     // the X store has read R1 before this warp's h1r arrivals let the L2 GEMM (and then epilogue 2, which
     // overwrites R1) proceed
     if (x_store) tma_store_wait_read0();
-#ifndef FS_TRACE_EPI2_ALL
-    FS_STAMP_W(32);
-#endif
+    FS_STAMP_W(0, 0);
     epilogue_act(acc0, R0, bias_s, act, erow, q, sub * 16, 64, nkH, h1r);   // 64-column block b published on h1r[b]
-#ifndef FS_TRACE_EPI2_ALL
-    FS_STAMP_W(36);
-#endif
+    FS_STAMP_W(0, 1);
     if (wt == 0) FS_STAMP(3);
     if (wt == FS_STORE_THREAD) {                                  // its own arrivals are done
       for (int b = 0; b < nkH; ++b) {
@@ -715,21 +713,9 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
     mbar_wait(accf1, 0);
     tc_fence_after();
     if (wt == 0) FS_STAMP(4);
-#ifdef FS_TRACE_EPI2_ALL                                         // debug build: all 16 warps around epilogue 2 (slots 32 + warp / 48 + warp)
-    if (p.trace && lane == 0) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + 32 + warp] = clock64();
-#else
-    FS_STAMP_W(40);
-#endif
-#ifndef FS_TRACE_EPI2_ALL
+    FS_STAMP_W(1, 0);
     epilogue_act(acc1, R1, bias_s + 256, act, erow, q, sub * 16, 64, nkH, h2r);   // 64-column block b published on h2r[b] (head MMAs)
-    FS_STAMP_W(44);
-#else
-    for (int b = 0; b < nkH; ++b) {
-      epilogue_act(acc1, R1, bias_s + 256, act, erow, q, sub * 16 + 64 * b, 64, 1, h2r + b);
-      if (p.trace && lane == 0) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + 64 + warp * 4 + b] = clock64();
-    }
-    if (p.trace && lane == 0) p.trace[static_cast<size_t>(cta_id) * FS_TRACE_SLOTS + 48 + warp] = clock64();
-#endif
+    FS_STAMP_W(1, 1);
     if (wt == 0) FS_STAMP(5);
 
     // ---- loss and gradient seed g = dL/dout ------------------------------------------------------------------
@@ -868,45 +854,40 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
         tma_store_commit();
       }
     }
-#ifndef FS_TRACE_EPI2_ALL
-    FS_STAMP_W(48);
-#endif
+    FS_STAMP_W(2, 0);
     epilogue_dact(acc0, R1, R1, act, erow, q, sub * 16, 64, nkH, dz2r);            // in place: H2 -> dZ2, block b published on dz2r[b]
-#ifndef FS_TRACE_EPI2_ALL
-    FS_STAMP_W(52);
-#endif
+    FS_STAMP_W(2, 1);
     if (wt == 0) FS_STAMP(9);
+    // The dZ2 store is issued in one batch, and only once the TMA producer has issued its last weight load: the TMA unit works its
+    // queue in order and a 16 KB store drains at the SM's ~32 B/clk egress rate, so stores issued block by block held the last
+    // dH1 weight stages back by 1-2.7k cycles (measured: stage requested -> landed).  dZ2 stays in R1 until the end of the tile:
+    // epilogue 3 writes dZ1 over H1 in R0, so nothing waits for this store.
     if (wt == FS_STORE_THREAD) {
-      for (int b = 0; b < nkH; ++b) {
-        mbar_wait(&dz2r[b], 0);
-        tma_store_2d(R1 + b * 16384, &G.tm_dz2, b * 64, tile * 128);
-      }
+      for (int b = 0; b < nkH; ++b) mbar_wait(&dz2r[b], 0);
+      mbar_wait(ldi, 0);
+      for (int b = 0; b < nkH; ++b) tma_store_2d(R1 + b * 16384, &G.tm_dz2, b * 64, tile * 128);
       tma_store_commit();
     }
 
-    // ---- epilogue 3: dZ1 = acc1 * f'(H1) -> R1 -> TMA store ------------------------------------------
-    mbar_wait(dh1f, 0);                                            // dH1 MMAs done: R1 (dZ2) no longer read by those
-    mbar_wait(cs2f, 0);                                            // ... nor by the column-sum MMAs
+    // ---- epilogue 3: dZ1 = acc1 * f'(H1) -> R0 (in place over H1) -> TMA store ---------------------------------------
+    mbar_wait(dh1f, 0);                                            // dH1 accumulator complete
+    mbar_wait(cs2f, 0);                                            // column sums of dZ2 complete
     tc_fence_after();
     if (wt == 0) FS_STAMP(10);
-    if (wt == FS_STORE_THREAD) tma_store_wait_read0();                          // ... nor by the dZ2 TMA store
+    if (wt == FS_STORE_THREAD) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the H1 store (all but the newest group, dZ2) has read R0
     float cs2 = 0.f;
     if (sub < mtH) cs2 = tmem_ld_32x1(acc_cs2 + 16 * sub + (static_cast<uint32_t>(q * 32) << 16));
     tmem_ld_wait();
     worker_bar();
     if (sub < mtH && sub * 128 + erow < H) part[G.po_db1 + sub * 128 + erow] = cs2;     // layer-1 bias gradient of this tile
-#ifndef FS_TRACE_EPI2_ALL
-    FS_STAMP_W(56);
-#endif
-    epilogue_dact(acc1, R0, R1, act, erow, q, sub * 16, 64, nkH, dz1r);   // 64-column blocks, each stored as soon as it is complete
-#ifndef FS_TRACE_EPI2_ALL
-    FS_STAMP_W(60);
-#endif
+    FS_STAMP_W(3, 0);
+    epilogue_dact(acc1, R0, R0, act, erow, q, sub * 16, 64, nkH, dz1r);   // in place: H1 -> dZ1; 64-column blocks, each stored as soon as it is complete
+    FS_STAMP_W(3, 1);
     if (wt == 0) FS_STAMP(11);
     if (wt == FS_STORE_THREAD) {
       for (int b = 0; b < nkH; ++b) {
         mbar_wait(&dz1r[b], 0);
-        tma_store_2d(R1 + b * 16384, &G.tm_dz1, b * 64, tile * 128);
+        tma_store_2d(R0 + b * 16384, &G.tm_dz1, b * 64, tile * 128);
       }
       tma_store_commit();
     }

@@ -28,7 +28,7 @@ for _ in range(2):
     learner.update(ts, mem, t(last_val), rng)
 learner.check()
 n = 2 * (hp.minibatch_size // 128)
-out = torch.empty((n, 128 if os.environ.get("TRACE_EPI2_ALL") else 64), dtype=torch.int64, device=dev)
+out = torch.empty((n, 256), dtype=torch.int64, device=dev)
 _lib.check(learner.lib.minppo_ctx_read(learner._h, 7, out.data_ptr(), out.numel() * 8, torch.cuda.current_stream(dev).cuda_stream))
 torch.cuda.synchronize()
 tr = out.cpu().numpy()
@@ -45,17 +45,13 @@ for cta in (0, 1, n // 2, n - 1):
         d = int(tr[cta, k] - t0)
         print(f"  {names[k]:34s} {d:8d}  (+{d - prev})")
         prev = d
-    if os.environ.get("TRACE_EPI2_ALL"):                         # library built with -DFS_TRACE_EPI2_ALL
-        st = [int(tr[cta, 32 + w] - t0) for w in range(16)]
-        en = [int(tr[cta, 48 + w] - t0) for w in range(16)]
-        for qq in range(4):
-            print(f"  epilogue 2, quadrant {qq}: warps {[qq + 4 * i for i in range(4)]} start {[st[qq + 4 * i] for i in range(4)]} end {[en[qq + 4 * i] for i in range(4)]}")
-        continue
-    # the four worker warps of lane quadrant 0 (one scheduler) around the four big epilogues: start / end per warp
-    for nm, s0 in (("epilogue 1 (H1)", 32), ("epilogue 2 (H2)", 40), ("dZ2 epilogue", 48), ("epilogue 3 (dZ1)", 56)):
-        st = [int(tr[cta, s0 + w] - t0) for w in range(4)]
-        en = [int(tr[cta, s0 + 4 + w] - t0) for w in range(4)]
-        print(f"  {nm:18s} warps 0/4/8/12 start {st}  end {en}  own time {[e - s for s, e in zip(st, en)]}  window {max(en) - min(st)}")
+    print("  dH1 GEMM, MMA issuer: k-block seen", [int(tr[cta, 64 + k] - t0) for k in range(4)], "| stage landed", [int(tr[cta, 68 + k] - t0) for k in range(8)],
+          "| MMAs issued", [int(tr[cta, 76 + k] - t0) for k in range(8)])
+    # every worker warp around the four big epilogues (warp w: lane quadrant w & 3 = scheduler, column share w >> 2)
+    for e, nm in enumerate(("epilogue 1 (H1)", "epilogue 2 (H2)", "dZ2 epilogue", "epilogue 3 (dZ1)")):
+        st = tr[cta, 128 + 32 * e:128 + 32 * e + 16] - t0
+        en = tr[cta, 128 + 32 * e + 16:128 + 32 * e + 32] - t0
+        print(f"  {nm:18s} window {int(en.max() - st.min()):5d}  median warp {int(np.median(en - st)):5d}  start {int(st.min())}..{int(st.max())}  end per warp {[int(x) for x in en]}")
 if os.environ.get("MINPPO_PERSISTENT", "1") != "0":
     # persistent kernel: cta_id of the tile body is net-major, the loop stamps are in row b = blockIdx.x
     print("--- persistent loop, last step, cycles (mean over CTAs 0..127 | max): step start -> phase A done -> barrier 1 passed -> dwopt done -> barrier 2 passed")
@@ -64,25 +60,13 @@ if os.environ.get("MINPPO_PERSISTENT", "1") != "0":
         d = tr[:n, b_] - tr[:n, a_]
         print(f"  {name:48s} mean {d.mean():9.0f} min {d.min():9.0f} max {d.max():9.0f}")
     print(f"  whole step (13 -> 22)                            mean {(tr[:n, 22] - tr[:n, 13]).mean():9.0f}")
-if os.environ.get("TRACE_EPI2_ALL"):
-    # which warps finish epilogue 2 late (> 1000 cycles after the median warp of their CTA)?
-    en = tr[:, 48:64] - tr[:, 16:17]
-    st = tr[:, 32:48] - tr[:, 16:17]
-    med = np.median(en, axis=1, keepdims=True)
-    late = en - med
-    # per-chunk completion times of the worst straggler of the first actor CTAs that have one
-    shown = 0
-    for cta in range(n // 2):
-        w = int(late[cta].argmax())
-        if late[cta, w] > 1500 and shown < 6:
-            shown += 1
-            ch = tr[cta, 64:128].reshape(16, 4) - tr[cta, 16]
-            ref = int(np.argsort(en[cta])[8])
-            print(f"  CTA {cta}: straggler warp {w}: start {int(st[cta, w])} chunks done at {ch[w].tolist()} | median warp {ref}: start {int(st[cta, ref])} chunks {ch[ref].tolist()}")
-    for lo, hi, nm in ((0, n // 2, "actor"), (n // 2, n, "critic")):
-        cnt = (late[lo:hi] > 1000).sum(axis=0)
-        print(f"epilogue 2, {nm} CTAs: stragglers (> 1000 cycles after the CTA's median warp) per warp id: {cnt.tolist()}; "
-              f"window mean {(en[lo:hi].max(axis=1) - st[lo:hi].min(axis=1)).mean():.0f}, median-warp time {(med[lo:hi, 0] - st[lo:hi].min(axis=1)).mean():.0f}")
+for e, nm in enumerate(("epilogue 1 (H1)", "epilogue 2 (H2)", "dZ2 epilogue", "epilogue 3 (dZ1)")):
+    st = tr[:, 128 + 32 * e:128 + 32 * e + 16] - tr[:, 16:17]
+    en = tr[:, 128 + 32 * e + 16:128 + 32 * e + 32] - tr[:, 16:17]
+    late = en - np.median(en, axis=1, keepdims=True)
+    for lo, hi, who in ((0, n // 2, "actor"), (n // 2, n, "critic")):
+        print(f"{nm:18s} {who:6s} CTAs: window mean {(en[lo:hi].max(axis=1) - st[lo:hi].min(axis=1)).mean():6.0f}  median-warp time {np.median(en[lo:hi] - st[lo:hi], axis=1).mean():6.0f}  "
+              f"warps > 1000 cycles behind their CTA's median, per warp id: {(late[lo:hi] > 1000).sum(axis=0).tolist()}")
 tot = tr[:, 12] - tr[:, 16]
 print("total cycles per CTA: actor mean", tot[:n // 2].mean(), "critic mean", tot[n // 2:].mean(), "max", tot.max())
 
