@@ -160,8 +160,14 @@ MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw,
     s_seq = __ldcg(p.px.seq) + 1u;                       // number of this exchange
     s_dead = __ldcg(a.err_flag) != 0;
   }
-  if (build_tab) leaf_tab_build(T, a, t, NT);            // a persistent caller builds the table once (it only depends on the launch)
-  __syncthreads();
+  // The leaf table (kernel parameters -> shared memory: cold constant-bank misses, ~2k cycles at the head of a launch) is first
+  // read in phase 2.  GEMM CTAs: the helper warps copy it while the GEMM is in flight (the CTA-wide barrier at the end of the GEMM
+  // body orders it); spare CTAs need it at once.  (A persistent caller builds the table once: it only depends on the launch.)
+  const bool gemm_cta = b < p.gemm_ctas;
+  if (!gemm_cta) {
+    if (build_tab) leaf_tab_build(T, a, t, NT);
+    __syncthreads();
+  }
   DW_STAMP(14);
 
   // Per-step scalars (two powf, A exp/log): computed by the last thread, whose warp has no GEMM role, while the
@@ -182,12 +188,13 @@ MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw,
   };
 
   // ---- phase 1 ----------------------------------------------------------------------------------
-  if (b < p.gemm_ctas) {
+  if (gemm_cta) {
     // Helper warps (idle until the accumulator is complete): the per-step scalars, and this CTA's share of the L2
     // prefetch of the NEXT minibatch's observation rows (row lists and the observation image are static during an
     // update: no dependency on the preceding kernel).  Spread over all GEMM CTAs so that it never rides on the few
     // spare CTAs, whose number depends on the split-K factor.
     auto idle_work = [&]() {
+      if (build_tab) leaf_tab_build(T, a, t - GEMM_THREADS, NT - GEMM_THREADS);
       scalars();
       if (next_ridx) {
         const int HELPERS = NT - GEMM_THREADS;

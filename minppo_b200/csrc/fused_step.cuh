@@ -198,6 +198,8 @@ MINPPO_DEVINL float dclip_f(float x, float lo, float hi) {
 // otherwise exposed in every chunk, and the MUFU time of a tanh chunk (16 x 8 cycles per warp) adds to it instead of hiding it.
 // (Not inlined: the epilogues share one copy of the code per activation -- the kernel's straight-line worker path is larger
 //  than the instruction cache otherwise.)
+// (Publishing the 64-column blocks in pairs where no GEMM is fed block by block -- epilogues 2 and 3 -- saves two of the four
+//  generic -> async proxy fences per warp, ~130 cycles each in isolation, but measured no faster in the kernel: 5.287 vs 5.263 ms.)
 MINPPO_DEVINL void chunk_publish(uint64_t* bar) {
   fence_proxy_async_smem();
   tc_fence_before();
@@ -370,6 +372,10 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
   __syncthreads();                       // persistent callers: the previous unit / phase is done with this memory
   if (threadIdx.x == FS_WORKERS) {
     FS_STAMP(16);
+    // tensor maps into the descriptor cache first (weights: in front of the first L1 stage; stores: off any critical path)
+    tma_prefetch_desc(&G.tm_w0); tma_prefetch_desc(&G.tm_w1); tma_prefetch_desc(&G.tm_w1k);
+    tma_prefetch_desc(&G.tm_h1); tma_prefetch_desc(&G.tm_dz2); tma_prefetch_desc(&G.tm_dz1);
+    if (p.store_x && net == 1) tma_prefetch_desc(&p.tm_xg);
     for (int s = 0; s < 8; ++s) { mbar_init(&l1_full[s], 1); mbar_init(&l1_empty[s], 1); }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&x_full[s], FS_NWW); mbar_init(&x_empty[s], 1); mbar_init(&x_stored[s], 1);
@@ -394,7 +400,6 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
   if (warp == FS_TMA_WARP) {
     // ===================== weight producer ======================================================================
     if (elect_one()) {
-      tma_prefetch_desc(&G.tm_w0); tma_prefetch_desc(&G.tm_w1); tma_prefetch_desc(&G.tm_w1k);
       griddep_wait();                 // the weight images are rewritten by the previous optimizer step
       if (PERSISTENT) fence_proxy_async_global();   // ... published through a grid barrier (generic-proxy acquire)
       const uint32_t bytes = static_cast<uint32_t>(H) * 64u;

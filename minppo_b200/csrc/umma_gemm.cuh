@@ -158,6 +158,10 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
 
   if (threadIdx.x == 0) {
     GEMM_STAMP(13);
+    // tensor maps into the descriptor cache first: a cold descriptor fetch sits in front of the first operand load otherwise
+    if (kTmaA) tma_prefetch_desc(&G.tmA);
+    tma_prefetch_desc(&G.tmB);
+    if (EPI == EPI_PARTIAL) tma_prefetch_desc(&G.tmC);
     for (int s = 0; s < GEMM_STAGES; ++s) {
       mbar_init(&full_bar[s], 1 + (kGather ? GEMM_EPI_THREADS : 0));
       mbar_init(&empty_bar[s], 1);
@@ -189,8 +193,6 @@ MINPPO_DEVINL void umma_gemm_body(const GemmParams& p, uint8_t* smem_raw, long l
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      if (kTmaA) tma_prefetch_desc(&G.tmA);
-      tma_prefetch_desc(&G.tmB);
       griddep_wait();                  // PDL (common.cuh): operands are written by the preceding kernel
       griddep_launch();
       if (ext_tmem != GEMM_NO_TMEM)    // persistent callers: the operands were published through a grid barrier (generic-proxy

@@ -6,10 +6,12 @@
 
 using namespace minppo;
 
-template <int KIND>   // 0: act stride 16, 1: act stride 64, 2: dact stride 64
+template <int KIND>   // 0: act stride 16, 1: act stride 64, 2: dact stride 64, 3: dact stride 64 publishing every chunk on an mbarrier
 __global__ void __launch_bounds__(FS_THREADS, 1) probe(int act, int iters, int sync_each, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t slot;
+  __shared__ uint64_t pub[4];                                   // never waited on: arrival counts far above what the probe delivers
+  if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mbar_init(&pub[i], (1u << 20) - 1u); fence_mbar_init(); }
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   float* bias_s = reinterpret_cast<float*>(smem_raw + (base - raw) + 131072);
@@ -29,7 +31,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) probe(int act, int iters, int s
       if (sync_each) worker_bar();                               // single-shot: every pass starts with all 16 warps aligned, as after an mbarrier
       if (KIND == 0) epilogue_act(acc, base, bias_s, act, erow, q, sub * 64, 16, 4, nullptr);
       else if (KIND == 1) epilogue_act(acc, base, bias_s, act, erow, q, sub * 16, 64, 4, nullptr);
-      else epilogue_dact(acc, base + 65536, base, act, erow, q, sub * 16, 64, 4, nullptr);
+      else if (KIND == 2) epilogue_dact(acc, base + 65536, base, act, erow, q, sub * 16, 64, 4, nullptr);
+      else epilogue_dact(acc, base + 65536, base, act, erow, q, sub * 16, 64, 4, pub);
     }
     worker_bar();
     const long long t1 = clock64();
@@ -71,5 +74,7 @@ int main() {
   run<1>("H1 epilogue (stride 64), tanh.approx", ACT_TANH_FAST, d_cycles, nsm);
   run<2>("dZ epilogue (stride 64), relu", ACT_RELU, d_cycles, nsm);
   run<2>("dZ epilogue (stride 64), tanh", ACT_TANH, d_cycles, nsm);
+  run<3>("dZ epilogue, published per chunk, relu", ACT_RELU, d_cycles, nsm);
+  run<3>("dZ epilogue, published per chunk, tanh", ACT_TANH, d_cycles, nsm);
   return 0;
 }
