@@ -310,12 +310,13 @@ MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw,
     const float4 sent4 = make_float4(-0.f, -0.f, -0.f, -0.f);
     float gl = 0.f;
     if (eidx >= 0) gl = canon(__ldcg(a.gflat + eidx));
-    // TWO-PHASE (X.two_phase, used for W >= 4): the units of CTA b are reduced by rank b % W only.  A non-owner pushes its
+    // TWO-PHASE (X.two_phase, used for W >= 4): the units of warp w of CTA b are reduced by rank (b + w) % W only (dealt per warp,
+    // not per CTA: the owner's W - 1 polls and W - 1 result pushes per unit then spread over all SMs).  A non-owner pushes its
     // unit to the owner (one store instead of W - 1) and polls the result slot; the owner polls the W - 1 contributions,
     // sums in rank order and pushes the result to everybody.  Two NVLink latencies instead of one, but (W - 1) / W of a
     // gradient sent and received per rank instead of W - 1 gradients -- and the same sums, bit for bit, as ONE-SHOT.
     const bool two = X.two_phase != 0;
-    const int owner = two ? b % W : R;
+    const int owner = two ? (b + (t >> 5)) % W : R;        // per warp: every CTA holds NT / 32 / W owner warps of each rank
     const bool reduce_here = owner == R;
     // ---- pushes (all units first: every store is in flight before the first poll) ----
 #pragma unroll

@@ -757,6 +757,10 @@ MINPPO_DEVINL void fused_tile(const FusedParams& p, int unit, int step, uint8_t*
           zz[jj] = z;
           if (j < aout) quad += -0.5f * z * z - 0.91893853320467274178f;
         }
+        // qp aliases the hidden biases, last read in epilogue 2.  Every warp's reads precede its h2r arrivals, which precede
+        // the head MMAs, headf and this point -- an mbarrier / tcgen05.commit chain that compute-sanitizer's racecheck does not
+        // follow (it reported the pair); the named barrier makes the order explicit (~100 cycles, all 16 warps arrive together)
+        worker_bar();
         qp[sub * 128 + erow] = quad;
         worker_bar();
         quad = ((qp[erow] + qp[128 + erow]) + qp[256 + erow]) + qp[384 + erow];   // fixed order: column groups 0..3
