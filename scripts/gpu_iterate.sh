@@ -1,5 +1,5 @@
 #!/bin/bash
-# parity subset + quick benches + cycle trace
+# one tuning iteration on a B200 box: parity subset (update, capture, policy tests), quick benches at D = 225 / A = 10 and D = 415 / A = 20, cycle trace
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_update.py tests/test_gpu_capture.py tests/test_gpu_policy.py -m gpu -q -x --timeout=600 -p no:cacheprovider -k "not configs3" > gpurun_out/pytest_update.log 2>&1
