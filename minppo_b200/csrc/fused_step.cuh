@@ -8,7 +8,7 @@
 //   gather X k-blocks (cp.async by row index, SW128) -> 4 slots in R1 (streamed for obs_dim > 256)
 //   L1   acc0 = X  W0    (W0 half-k-blocks streamed by TMA)     -> +b0, act, bf16 -> R0 (H1) -> TMA store
 //   L2   acc1 = H1 W1                                           -> +b1, act, bf16 -> R1 (H2)
-//   head out  = H2 W2    (N = 2 AP: bf16 hi | lo)               -> +b2 -> Gaussian log-prob / clipped
+//   head out  = H2 W2    (N = 2 AP: bf16 hi | lo; in acc0, per k-block of epilogue 2) -> +b2 -> Gaussian log-prob / clipped
 //        surrogate (actor CTA) or clipped value loss (critic CTA), train.py:218-243 -> g = dL/dout
 //   bwd  dA2  = g W2^T   (K = AP),  dW2 = H2^T g (N = 2 AP)     -> dZ2 = dA2 * f'(H2) in place -> TMA store
 //   dH1  acc1 = dZ2 W1^T (two N halves)                         -> * f'(H1), bf16 -> R0 (dZ1, over H1) -> TMA store
@@ -25,8 +25,14 @@
 // Warp roles: warps 0..15 workers (gather, epilogues, loss), FOUR per TMEM lane quadrant -- a worker warp owns 16 of every
 // 64 accumulator columns, so each scheduler has four epilogue warps to hide the tcgen05.ld / MUFU / st.shared latencies
 // behind; warp 16 TMA producer (weight stages of 16 KB through a ring); warp 17 TMEM allocator + MMA issuer.
-// H1, dZ2, dZ1 (and, for Dp <= 256, the gathered X rows) are also written to HBM (bf16, TMA stores) for the split-K
+// H1, dZ2, dZ1 and (critic CTA) the gathered X rows are also written to HBM (bf16, TMA stores) for the split-K
 // weight-gradient GEMM (dwopt.cuh), which runs as its own launch over all tiles.
+//
+// Scheduling rules this kernel follows (each one measured): global accesses with many lines per instruction
+// (row gathers of the loss inputs, per-row partial stores) stay out of the epilogues -- issued by the warps that are done,
+// they stall the shared-memory traffic of the warp that is not: the loss inputs are requested before griddepcontrol.wait,
+// the head-kernel gradient leaves through shared memory and one bulk copy; the TMA unit is a FIFO whose stores drain at
+// ~32 B/clk, so no store is queued in front of a weight load the MMAs are about to wait for.
 #pragma once
 
 #include "common.cuh"
