@@ -449,6 +449,23 @@ MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw,
   DW_STAMP(4);
 
   // ---- phase 3 ----------------------------------------------------------------------------------
+  // This thread's element of the SMALL leaves (at most one when they fit one sweep of the grid): gradient and optimizer state
+  // are requested first, so that the L2 round trip runs under the norm reduction and the register-resident units below --
+  // the launch ends with its slowest CTA, and the CTAs that carry the small leaves are those (phase 3: 4.4k cycles mean,
+  // 8.8k on them).  Same job numbering and the same arithmetic as apply_adam_class<false>.
+  const bool early_one = fast && !px_on && T.n_early <= GT_;   // (sharded ranks keep the loop below: measured at 2 / 8 ranks as is)
+  int el = -1, ei = 0;
+  float eg = 0.f, ep = 0.f, em = 0.f, en = 0.f;
+  if (early_one && gtid < T.n_early) {
+    int x = gtid, l = 0;
+    for (; l < T.nleaves; ++l) {
+      if (T.leaf[l].late) continue;
+      if (x < T.size[l]) break;
+      x -= T.size[l];
+    }
+    el = l; ei = T.leaf[l].offset + x;
+    eg = __ldcg(a.gflat + ei); ep = __ldcg(a.params + ei); em = __ldcg(a.mu + ei); en = __ldcg(a.nu + ei);
+  }
   {
     // one load per thread (G <= DWOPT_THREADS): a serial loop over the per-block sums cost five dependent
     // L2 round trips on lines every SM is hammering at the same time
@@ -472,7 +489,15 @@ MINPPO_DEVINL void dwopt_body(const DwOptParams& p, int step, uint8_t* smem_raw,
       if (L.img_n)             // 4 consecutive bf16 of the kernel image (unit index is a multiple of 4: 8-byte aligned)
         *reinterpret_cast<uint2*>(L.img_n + (ui[u] - L.offset)) = make_uint2(pack_bf16x2(pv[u][0], pv[u][1]), pack_bf16x2(pv[u][2], pv[u][3]));
     }
-    apply_adam_class<false>(a, T, sc, gtid, GT_);
+    if (early_one) {
+      if (el >= 0) {
+        adam_element(a, sc, eg, ep, em, en);
+        a.params[ei] = ep; a.mu[ei] = em; a.nu[ei] = en;
+        write_images(T.leaf[el], ei, ep);
+      }
+    } else {
+      apply_adam_class<false>(a, T, sc, gtid, GT_);
+    }
   } else {
     apply_adam(a, T, sc, gtid, GT_);
   }
