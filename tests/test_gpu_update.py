@@ -354,6 +354,28 @@ def test_update_rejects_bad_arguments(cuda_device):
     lrn.close()
 
 
+@pytest.mark.parametrize("name", ["medium", "wide"])
+def test_persistent_all_steps_kernel_equals_per_step_launches(name, cuda_device, monkeypatch):
+    """The optional one-launch-for-all-steps kernel (MINPPO_PERSISTENT=1: fused tile -> grid barrier -> dW GEMM + optimizer
+    -> grid barrier, per step) runs the SAME tile and optimizer bodies as the per-step launches, on a different grid (hence
+    other split-K factors and fp32 summation orders: close, not bit-identical).  Both are separately held to the oracle by
+    test_update_parity (the persistent mode when the suite is run with MINPPO_PERSISTENT=1); this test keeps the optional
+    mode from rotting.  (It is not the default: measured slower)"""
+    case = CASES[name]
+    hp = P.Hyper(**case["hp"])
+    pr = synth.make_problem(hp, case["D"], case["A"], seed=11, done_p=0.02)
+    a = run_gpu_update(hp, pr, cuda_device)
+    monkeypatch.setenv("MINPPO_PERSISTENT", "1")                 # read when the context is created
+    b = run_gpu_update(hp, pr, cuda_device)
+    monkeypatch.delenv("MINPPO_PERSISTENT")
+    assert b["launches"] < a["launches"]
+    assert np.all(np.isfinite(b["losses"])) and np.all(np.isfinite(b["params"]))
+    assert rel_err(a["losses"], b["losses"]) < 1e-3
+    assert rel_err(a["grad_norms"], b["grad_norms"]) < 1e-2
+    lr = hp.opt_lr if not hp.anneal_lr else hp.training_lr
+    assert np.abs(a["params"] - b["params"]).max() < lr * (2.0 + 0.15 * hp.update_epochs * hp.num_minibatches)
+
+
 def test_row_list_overflow_raises_the_device_flag_and_poisons_the_losses(cuda_device, monkeypatch):
     """Env-sharded ranks size their per-minibatch row lists for 1.5 x the mean + 256 rows.  A list that does not fit must
     not bias the gradient silently: compact_rows raises the device-side error flag, every reported loss of that update
