@@ -109,6 +109,46 @@ def test_adam_first_step_closed_form_and_clip_branches():
         np.testing.assert_allclose(P.get_leaf(p2, pth) - P.get_leaf(params, pth), -1e-3 * gg / (np.abs(gg) + 1e-5), rtol=1e-9)
 
 
+def test_adam_chain_equals_torch_optim_adam_over_many_steps():
+    """Independent-library anchor for the optimizer beyond step 1: optax.adam(lr, eps=1e-5) (train.py:118-121) is the
+    Kingma-Ba update with both bias corrections and eps OUTSIDE the square root -- which is also what torch.optim.Adam
+    implements.  25 steps with a changing gradient, clip never triggering (||g|| < max_grad_norm), fp64: the oracle's
+    params / mu / nu / count follow torch's to 1e-12."""
+    import torch
+
+    hp = P.Hyper(anneal_lr=False, opt_lr=3e-4, max_grad_norm=1e9, hidden_size=8, num_layers=2)
+    params = P.init_params(5, 3, 8, 2, seed=2)
+    order = P.leaf_order(2)
+    tparams = [torch.tensor(P.get_leaf(params, pth), dtype=torch.float64, requires_grad=True) for pth in order]
+    topt = torch.optim.Adam(tparams, lr=3e-4, betas=(0.9, 0.999), eps=1e-5)
+    opt = P.init_opt_state(params)
+    g = np.random.default_rng(5)
+    for step in range(25):
+        grads = P.tree_like(params, lambda x: (0.3 + 0.1 * step) * g.standard_normal(x.shape))
+        for tp, pth in zip(tparams, order):
+            tp.grad = torch.tensor(P.get_leaf(grads, pth), dtype=torch.float64)
+        topt.step()
+        params, opt, _ = P.clip_adam_step(params, grads, opt, hp)
+    assert opt["count"] == 25
+    for tp, pth in zip(tparams, order):
+        np.testing.assert_allclose(P.get_leaf(params, pth), tp.detach().numpy(), rtol=1e-12, atol=1e-14)
+        st = topt.state[tp]
+        np.testing.assert_allclose(P.get_leaf(opt["mu"], pth), st["exp_avg"].numpy(), rtol=1e-12, atol=1e-16)
+        np.testing.assert_allclose(P.get_leaf(opt["nu"], pth), st["exp_avg_sq"].numpy(), rtol=1e-12, atol=1e-18)
+
+
+def test_gaussian_logprob_equals_torch_distributions():
+    """Second independent anchor for distrax.MultivariateNormalDiag(loc, exp(log_std)) (train.py:80-83, 223, 240):
+    torch.distributions.Independent(Normal(loc, scale), 1) -- log_prob of a batch and the entropy, fp64."""
+    import torch
+
+    g = np.random.default_rng(9)
+    mean, log_std, act = g.standard_normal((7, 6)), 0.3 * g.standard_normal(6), g.standard_normal((7, 6))
+    d = torch.distributions.Independent(torch.distributions.Normal(torch.tensor(mean), torch.tensor(np.exp(log_std))), 1)
+    np.testing.assert_allclose(P.gaussian_log_prob(mean, log_std, act)[0], d.log_prob(torch.tensor(act)).numpy(), rtol=1e-12)
+    np.testing.assert_allclose(P.gaussian_entropy(log_std, 6), d.entropy().numpy()[0], rtol=1e-12)
+
+
 def test_lr_schedule_quirk_F8():
     """train.py:98-101 divides the Adam count by minibatch_size * update_epochs (NOT num_minibatches):
     with "one update" (total_timesteps = 160) the LR reaches zero at step 20 and goes negative."""
