@@ -197,3 +197,46 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Ret<ffi::Buffer<ffi::F32>>()   // log_prob [N]
         .Ret<ffi::Buffer<ffi::F32>>()   // value [N]
         .Ret<ffi::Buffer<ffi::U32>>()); // rng' [2]
+
+// ---- bootstrap value --------------------------------------------------------------------------
+// Replaces `_, last_val = network.apply(runner_state.train_state.params, runner_state.last_obs)` (train.py:182-183): the
+// critic-only form of minppo_policy_step (action == log_prob == mean == NULL, no key).  Same static attributes as the
+// other two calls, so that all three resolve to one context.
+static ffi::Error BootstrapValueImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params, ffi::Buffer<ffi::F32> last_obs,
+                                     int32_t num_steps, int32_t act_dim, int32_t num_minibatches, int32_t update_epochs,
+                                     int64_t total_timesteps, bool anneal_lr, int32_t hidden_size, int32_t num_layers,
+                                     bool use_tanh, int32_t prng_mode, float training_lr, float opt_lr,
+                                     float max_grad_norm, float gamma, float gae_lambda, float clip_eps, float ent_coef,
+                                     float vf_coef, bool weights_current, ffi::ResultBuffer<ffi::F32> value) {
+  const auto od = last_obs.dimensions();                        // [N, D]
+  if (od.size() != 2) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "last_obs must be [N, D]");
+  minppo_config c = {};
+  c.num_steps = num_steps; c.num_envs = static_cast<int32_t>(od[0]);
+  c.obs_dim = static_cast<int32_t>(od[1]); c.act_dim = act_dim;
+  c.num_minibatches = num_minibatches; c.update_epochs = update_epochs; c.total_timesteps = total_timesteps;
+  c.anneal_lr = anneal_lr; c.hidden_size = hidden_size; c.num_layers = num_layers; c.use_tanh = use_tanh;
+  c.prng_mode = prng_mode; c.world_size = 1; c.rank = 0; c.fast_tanh = 1;
+  c.training_lr = training_lr; c.opt_lr = opt_lr; c.max_grad_norm = max_grad_norm; c.gamma = gamma;
+  c.gae_lambda = gae_lambda; c.clip_eps = clip_eps; c.ent_coef = ent_coef; c.vf_coef = vf_coef;
+  c.adam_b1 = 0.9; c.adam_b2 = 0.999; c.adam_eps = 1e-5; c.adam_eps_root = 0.0;
+  int device = 0, err = 0;
+  cudaGetDevice(&device);
+  minppo_ctx* ctx = GetCtx(c, device, &err);
+  if (!ctx) return ToError(err);
+  return ToError(minppo_policy_step(ctx, params.typed_data(), last_obs.typed_data(), nullptr, nullptr, nullptr, nullptr,
+                                    value->typed_data(), nullptr,
+                                    weights_current ? MINPPO_POLICY_WEIGHTS_CURRENT : 0, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(
+    MinppoBootstrapValue, BootstrapValueImpl,
+    ffi::Ffi::Bind()
+        .Ctx<ffi::PlatformStream<cudaStream_t>>()
+        .Arg<ffi::Buffer<ffi::F32>>()   // params arena [P]
+        .Arg<ffi::Buffer<ffi::F32>>()   // last_obs [N, D]
+        .Attr<int32_t>("num_steps").Attr<int32_t>("act_dim")
+        .Attr<int32_t>("num_minibatches").Attr<int32_t>("update_epochs").Attr<int64_t>("total_timesteps")
+        .Attr<bool>("anneal_lr").Attr<int32_t>("hidden_size").Attr<int32_t>("num_layers").Attr<bool>("use_tanh")
+        .Attr<int32_t>("prng_mode").Attr<float>("training_lr").Attr<float>("opt_lr").Attr<float>("max_grad_norm")
+        .Attr<float>("gamma").Attr<float>("gae_lambda").Attr<float>("clip_eps").Attr<float>("ent_coef")
+        .Attr<float>("vf_coef").Attr<bool>("weights_current")
+        .Ret<ffi::Buffer<ffi::F32>>()); // value [N]

@@ -45,6 +45,7 @@ def register() -> None:
     jax.ffi.register_ffi_target("minppo_gae", jax.ffi.pycapsule(lib.MinppoGae), platform="CUDA")
     jax.ffi.register_ffi_target("minppo_update", jax.ffi.pycapsule(lib.MinppoUpdate), platform="CUDA")
     jax.ffi.register_ffi_target("minppo_policy_step", jax.ffi.pycapsule(lib.MinppoPolicyStep), platform="CUDA")
+    jax.ffi.register_ffi_target("minppo_bootstrap_value", jax.ffi.pycapsule(lib.MinppoBootstrapValue), platform="CUDA")
     _registered = True
 
 
@@ -130,4 +131,19 @@ def policy_step(flat_params, last_obs, rng, config, act_dim: int, weights_curren
             jax.ShapeDtypeStruct((2,), jnp.uint32))
     return jax.ffi.ffi_call("minppo_policy_step", outs)(
         flat_params, last_obs, rng, num_steps=np.int32(config.training.num_steps), act_dim=np.int32(act_dim),
+        weights_current=bool(weights_current), **_static_attrs(config, prng_mode))
+
+
+def bootstrap_value(flat_params, last_obs, config, act_dim: int, weights_current: bool = True,
+                    prng_mode: int | None = None):
+    """Drop-in for ``_, last_val = network.apply(params, last_obs)`` (train.py:182-183): the critic only, no key.
+
+    flat_params: f32[P]; last_obs: f32[N, D].  Returns value f32[N].  ``weights_current`` defaults to True: the call follows
+    the rollout's policy steps on the same, unmodified arena."""
+    register()
+    if prng_mode is None:
+        prng_mode = int(bool(jax.config.jax_threefry_partitionable))
+    n = last_obs.shape[0]
+    return jax.ffi.ffi_call("minppo_bootstrap_value", jax.ShapeDtypeStruct((n,), jnp.float32))(
+        flat_params, last_obs, num_steps=np.int32(config.training.num_steps), act_dim=np.int32(act_dim),
         weights_current=bool(weights_current), **_static_attrs(config, prng_mode))

@@ -32,6 +32,21 @@ def test_shim_compiles_against_the_mock_ffi_header():
     assert r.returncode == 0, r.stderr[-3000:]
 
 
+def test_mock_build_exports_every_handler_the_python_side_registers():
+    """minppo_b200/jax_ffi.py registers MinppoGae, MinppoUpdate, MinppoPolicyStep and MinppoBootstrapValue (the critic-only
+    bootstrap value, train.py:182-183): the shim defines each of them (through the mock's handler macro: <name>_mock_symbol)."""
+    import re
+
+    r = build_mock()
+    assert r.returncode == 0, r.stderr[-3000:]
+    src = open(os.path.join(ROOT, "minppo_b200", "jax_ffi.py")).read()
+    wanted = sorted(set(re.findall(r"pycapsule\(lib\.(\w+)\)", src)))
+    assert wanted == ["MinppoBootstrapValue", "MinppoGae", "MinppoPolicyStep", "MinppoUpdate"]
+    nm = subprocess.run(["nm", "-D", "--defined-only", MOCK_SO], capture_output=True, text=True).stdout
+    for name in wanted:
+        assert f"{name}_mock_symbol" in nm, name
+
+
 @pytest.mark.gpu
 def test_shim_handlers_forward_and_key_contexts_on_the_whole_config(cuda_device):
     import torch
